@@ -1,0 +1,408 @@
+// b2sv: the extern "C" boundary (include/b2sv.h). Thin: argument marshalling + error capture.
+#include "../../include/b2sv.h"
+
+#include "adjoint.hpp"
+#include "comm.hpp"
+#include "obs.hpp"
+#include "state.hpp"
+
+#include <cstring>
+
+using namespace b2sv;
+
+struct b2sv_state {
+    std::unique_ptr<State> s;
+};
+struct b2sv_obs {
+    ObsPtr o;
+};
+struct b2sv_ops {
+    OpsData d;
+};
+struct b2sv_csr {
+    std::shared_ptr<CsrDevice> m;
+};
+
+namespace {
+thread_local std::string g_err;
+
+template <class F> int guard(F &&f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return 1;
+    } catch (...) {
+        g_err = "unknown error";
+        return 1;
+    }
+}
+std::vector<int64_t> wires_vec(const int64_t *w, int nw) {
+    B2_ABORT_IF(nw < 0 || (nw > 0 && !w), "invalid wires argument");
+    return std::vector<int64_t>(w, w + nw);
+}
+std::vector<cplx> cplx_vec(const double *p, size_t n) {
+    B2_ABORT_IF(n > 0 && !p, "invalid complex buffer argument");
+    std::vector<cplx> v(n);
+    for (size_t i = 0; i < n; i++)
+        v[i] = cplx(p[2 * i], p[2 * i + 1]);
+    return v;
+}
+State &st(b2sv_state *s) {
+    B2_ABORT_IF(!s || !s->s, "null state handle");
+    return *s->s;
+}
+const State &st(const b2sv_state *s) {
+    B2_ABORT_IF(!s || !s->s, "null state handle");
+    return *s->s;
+}
+void copy_str(const std::string &s, char *buf, size_t cap) {
+    B2_ABORT_IF(!buf || cap == 0, "invalid string buffer");
+    const size_t n = std::min(cap - 1, s.size());
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+}
+} // namespace
+
+extern "C" {
+
+const char *b2sv_last_error(void) { return g_err.c_str(); }
+const char *b2sv_version(void) { return "b2sv 0.1.0 (sm_100a)"; }
+
+int b2sv_device_count(int *count) {
+    return guard([&] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) {
+            n = 0;
+            cudaGetLastError();
+        }
+        *count = n;
+    });
+}
+int b2sv_backend_info(char *buf, size_t cap) {
+    return guard([&] {
+        std::ostringstream os;
+        os << "backend: b2sv hand-written CUDA (sm_100a), no Kokkos\n";
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) {
+            n = 0;
+            cudaGetLastError();
+        }
+        os << "devices: " << n << "\n";
+        for (int d = 0; d < n; d++) {
+            cudaDeviceProp p;
+            if (cudaGetDeviceProperties(&p, d) == cudaSuccess)
+                os << "  [" << d << "] " << p.name << " sm_" << p.major << p.minor << " SMs="
+                   << p.multiProcessorCount << " mem=" << (p.totalGlobalMem >> 20) << " MiB\n";
+        }
+        int B, R;
+        tile_config(B2SV_C128, &B, &R);
+        os << "tile: c128 2^" << B << " amplitudes, 2^" << R << " per thread\n";
+        copy_str(os.str(), buf, cap);
+    });
+}
+
+int b2sv_create(int num_qubits, int dtype, int device_id, b2sv_state **out) {
+    return guard([&] {
+        B2_ABORT_IF(!out, "null output pointer");
+        auto h = std::make_unique<b2sv_state>();
+        h->s = std::make_unique<State>(num_qubits, dtype, device_id);
+        *out = h.release();
+    });
+}
+int b2sv_create_sharded(int num_qubits_total, int dtype, int device_id, int rank, int world,
+                        const void *nccl_unique_id, b2sv_state **out) {
+    return guard([&] {
+        B2_ABORT_IF(!out, "null output pointer");
+        B2_ABORT_IF(world > 1 && !nccl_unique_id, "sharded state needs an NCCL unique id");
+        auto h = std::make_unique<b2sv_state>();
+        h->s = std::make_unique<State>(num_qubits_total, dtype, device_id, rank, world, nccl_unique_id);
+        *out = h.release();
+    });
+}
+int b2sv_comm_unique_id(void *out128) {
+    return guard([&] { comm_unique_id(out128); });
+}
+int b2sv_destroy(b2sv_state *s) {
+    return guard([&] { delete s; });
+}
+int b2sv_clone(const b2sv_state *src, b2sv_state **out) {
+    return guard([&] {
+        auto h = std::make_unique<b2sv_state>();
+        h->s = st(src).clone();
+        *out = h.release();
+    });
+}
+int b2sv_copy(b2sv_state *dst, const b2sv_state *src) {
+    return guard([&] { st(dst).copy_from(st(src)); });
+}
+int b2sv_reset(b2sv_state *s) {
+    return guard([&] { st(s).reset(); });
+}
+int b2sv_init_zeros(b2sv_state *s) {
+    return guard([&] { st(s).init_zeros(); });
+}
+int b2sv_set_basis_state(b2sv_state *s, uint64_t index) {
+    return guard([&] { st(s).set_basis_state(index); });
+}
+int b2sv_set_state_vector(b2sv_state *s, const uint64_t *indices, const double *values, size_t n) {
+    return guard([&] {
+        auto v = cplx_vec(values, n);
+        st(s).set_state_vector(indices, v.data(), n);
+    });
+}
+int b2sv_h2d(b2sv_state *s, const void *host, size_t length) {
+    return guard([&] { st(s).h2d(host, length); });
+}
+int b2sv_d2h(const b2sv_state *s, void *host, size_t length) {
+    return guard([&] { st(s).d2h(host, length); });
+}
+int b2sv_num_qubits(const b2sv_state *s, int *n) {
+    return guard([&] { *n = st(s).num_qubits(); });
+}
+int b2sv_data_length(const b2sv_state *s, uint64_t *len) {
+    return guard([&] { *len = st(s).local_length(); });
+}
+int b2sv_device_ptr(const b2sv_state *s, void **ptr) {
+    return guard([&] { *ptr = st(s).data(); });
+}
+int b2sv_stream(const b2sv_state *s, void **stream) {
+    return guard([&] { *stream = static_cast<void *>(st(s).stream()); });
+}
+int b2sv_sync(const b2sv_state *s) {
+    return guard([&] { st(s).sync(); });
+}
+
+int b2sv_apply(b2sv_state *s, const char *name, const int64_t *wires, int nw, int inverse,
+               const double *params, int np) {
+    return guard([&] {
+        GateOp op;
+        op.name = name;
+        op.wires = wires_vec(wires, nw);
+        op.inverse = inverse != 0;
+        if (np > 0)
+            op.params.assign(params, params + np);
+        B2_ABORT_IF(op.name != "Identity" && !is_named_gate(op.name),
+                    "operation '" + op.name + "' is not a named gate; use b2sv_apply_matrix");
+        st(s).apply_gate(op);
+    });
+}
+int b2sv_apply_matrix(b2sv_state *s, const int64_t *wires, int nw, int inverse,
+                      const double *matrix) {
+    return guard([&] {
+        GateOp op;
+        op.name = "__matrix__";
+        op.wires = wires_vec(wires, nw);
+        op.inverse = inverse != 0;
+        op.matrix = cplx_vec(matrix, size_t(1) << (2 * nw));
+        st(s).apply_gate(op);
+    });
+}
+int b2sv_apply_ops(b2sv_state *s, const b2sv_ops *ops, int adjoint) {
+    return guard([&] {
+        B2_ABORT_IF(!ops, "null ops handle");
+        st(s).apply_ops(ops->d.ops, adjoint != 0);
+    });
+}
+int b2sv_apply_generator(b2sv_state *s, const char *name, const int64_t *wires, int nw, int adj,
+                         double *scale) {
+    (void)adj; // ignored by every generator of the reference
+    return guard([&] { *scale = st(s).apply_generator(name, wires_vec(wires, nw)); });
+}
+int b2sv_set_fusion(b2sv_state *s, int fuse) {
+    return guard([&] { st(s).set_fusion(fuse != 0); });
+}
+int b2sv_get_stats(const b2sv_state *s, uint64_t *sweeps, uint64_t *launches) {
+    return guard([&] {
+        if (sweeps)
+            *sweeps = st(s).sweeps;
+        if (launches)
+            *launches = st(s).launches + st(s).reduce_launches;
+    });
+}
+int b2sv_reset_stats(b2sv_state *s) {
+    return guard([&] {
+        st(s).sweeps = 0;
+        st(s).launches = 0;
+        st(s).reduce_launches = 0;
+    });
+}
+
+int b2sv_ops_create(int nops, const char *const *names, const double *params, const int *nparams,
+                    const int64_t *wires, const int *nwires, const int *inverses,
+                    const double *const *matrices, b2sv_ops **out) {
+    return guard([&] {
+        B2_ABORT_IF(nops < 0 || !out, "invalid arguments");
+        auto h = std::make_unique<b2sv_ops>();
+        size_t po = 0, wo = 0;
+        for (int i = 0; i < nops; i++) {
+            GateOp op;
+            op.name = names[i];
+            op.params.assign(params + po, params + po + nparams[i]);
+            po += nparams[i];
+            op.wires.assign(wires + wo, wires + wo + nwires[i]);
+            wo += nwires[i];
+            op.inverse = inverses[i] != 0;
+            if (matrices && matrices[i])
+                op.matrix = cplx_vec(matrices[i], size_t(1) << (2 * nwires[i]));
+            if (!op.params.empty())
+                h->d.num_par_ops++;
+            h->d.ops.push_back(std::move(op));
+        }
+        *out = h.release();
+    });
+}
+int b2sv_ops_destroy(b2sv_ops *ops) {
+    return guard([&] { delete ops; });
+}
+int b2sv_ops_size(const b2sv_ops *ops, int *nops, int *n_par_ops) {
+    return guard([&] {
+        B2_ABORT_IF(!ops, "null ops handle");
+        if (nops)
+            *nops = static_cast<int>(ops->d.ops.size());
+        if (n_par_ops)
+            *n_par_ops = static_cast<int>(ops->d.num_par_ops);
+    });
+}
+
+int b2sv_expval_named(const b2sv_state *s, const char *name, const int64_t *wires, int nw,
+                      double *out) {
+    return guard([&] { *out = st(s).expval_named(name, wires_vec(wires, nw)); });
+}
+int b2sv_expval_matrix(const b2sv_state *s, const int64_t *wires, int nw, const double *matrix,
+                       double *out) {
+    return guard([&] {
+        *out = st(s).expval_matrix(wires_vec(wires, nw), cplx_vec(matrix, size_t(1) << (2 * nw)));
+    });
+}
+int b2sv_expval_csr(const b2sv_state *s, const double *data, const uint64_t *indices,
+                    const uint64_t *indptr, size_t nnz, size_t nrows, double *out) {
+    return guard([&] {
+        auto d = cplx_vec(data, nnz);
+        auto m = csr_upload(st(s).device(), d.data(), indices, indptr, nnz, nrows);
+        *out = st(s).expval_csr(*m);
+    });
+}
+int b2sv_csr_create(const b2sv_state *like, const double *data, const uint64_t *indices,
+                    const uint64_t *indptr, size_t nnz, size_t nrows, b2sv_csr **out) {
+    return guard([&] {
+        auto d = cplx_vec(data, nnz);
+        auto h = std::make_unique<b2sv_csr>();
+        h->m = csr_upload(st(like).device(), d.data(), indices, indptr, nnz, nrows);
+        *out = h.release();
+    });
+}
+int b2sv_csr_destroy(b2sv_csr *m) {
+    return guard([&] { delete m; });
+}
+int b2sv_expval_csr_resident(const b2sv_state *s, const b2sv_csr *m, double *out) {
+    return guard([&] {
+        B2_ABORT_IF(!m || !m->m, "null CSR handle");
+        *out = st(s).expval_csr(*m->m);
+    });
+}
+int b2sv_expval_obs(const b2sv_state *s, const b2sv_obs *ob, double *out) {
+    return guard([&] {
+        B2_ABORT_IF(!ob || !ob->o, "null observable handle");
+        *out = expval_obs(st(s), *ob->o);
+    });
+}
+int b2sv_var_obs(const b2sv_state *s, const b2sv_obs *ob, double *out) {
+    return guard([&] {
+        B2_ABORT_IF(!ob || !ob->o, "null observable handle");
+        *out = var_obs(st(s), *ob->o);
+    });
+}
+int b2sv_probs(const b2sv_state *s, const int64_t *wires, int nw, double *out) {
+    return guard([&] { st(s).probs(wires_vec(wires, nw), out); });
+}
+int b2sv_generate_samples(const b2sv_state *s, size_t shots, uint64_t seed, uint64_t *out) {
+    return guard([&] { st(s).generate_samples(shots, seed, out); });
+}
+int b2sv_inner_product(const b2sv_state *a, const b2sv_state *b, double *re, double *im) {
+    return guard([&] { st(a).inner_product(st(b), re, im); });
+}
+int b2sv_axpy(double ar, double ai, const b2sv_state *x, b2sv_state *y) {
+    return guard([&] { st(y).axpy(cplx(ar, ai), st(x)); });
+}
+
+int b2sv_obs_named(const char *name, const int64_t *wires, int nw, b2sv_obs **out) {
+    return guard([&] { *out = new b2sv_obs{make_named_obs(name, wires_vec(wires, nw))}; });
+}
+int b2sv_obs_hermitian(const double *matrix, const int64_t *wires, int nw, b2sv_obs **out) {
+    return guard([&] {
+        *out = new b2sv_obs{
+            make_hermitian_obs(cplx_vec(matrix, size_t(1) << (2 * nw)), wires_vec(wires, nw))};
+    });
+}
+int b2sv_obs_tensor(b2sv_obs *const *obs, int n, b2sv_obs **out) {
+    return guard([&] {
+        std::vector<ObsPtr> v;
+        for (int i = 0; i < n; i++) {
+            B2_ABORT_IF(!obs[i] || !obs[i]->o, "null observable handle");
+            v.push_back(obs[i]->o);
+        }
+        *out = new b2sv_obs{make_tensor_obs(v)};
+    });
+}
+int b2sv_obs_hamiltonian(const double *coeffs, b2sv_obs *const *obs, int n, b2sv_obs **out) {
+    return guard([&] {
+        std::vector<ObsPtr> v;
+        for (int i = 0; i < n; i++) {
+            B2_ABORT_IF(!obs[i] || !obs[i]->o, "null observable handle");
+            v.push_back(obs[i]->o);
+        }
+        *out = new b2sv_obs{make_hamiltonian_obs(std::vector<double>(coeffs, coeffs + n), v)};
+    });
+}
+int b2sv_obs_sparse(const double *data, const uint64_t *indices, const uint64_t *indptr, size_t nnz,
+                    size_t nrows, const int64_t *wires, int nw, b2sv_obs **out) {
+    return guard([&] {
+        *out = new b2sv_obs{make_sparse_obs(cplx_vec(data, nnz),
+                                            std::vector<uint64_t>(indices, indices + nnz),
+                                            std::vector<uint64_t>(indptr, indptr + nrows + 1),
+                                            wires_vec(wires, nw))};
+    });
+}
+int b2sv_obs_destroy(b2sv_obs *ob) {
+    return guard([&] { delete ob; });
+}
+int b2sv_obs_name(const b2sv_obs *ob, char *buf, size_t cap) {
+    return guard([&] {
+        B2_ABORT_IF(!ob || !ob->o, "null observable handle");
+        copy_str(ob->o->name(), buf, cap);
+    });
+}
+int b2sv_obs_wires(const b2sv_obs *ob, int64_t *wires, int cap, int *nw) {
+    return guard([&] {
+        B2_ABORT_IF(!ob || !ob->o, "null observable handle");
+        const auto w = ob->o->wires();
+        *nw = static_cast<int>(w.size());
+        for (int i = 0; i < cap && i < *nw; i++)
+            wires[i] = w[i];
+    });
+}
+int b2sv_obs_apply(const b2sv_obs *ob, b2sv_state *s) {
+    return guard([&] {
+        B2_ABORT_IF(!ob || !ob->o, "null observable handle");
+        ob->o->apply_in_place(st(s));
+    });
+}
+
+int b2sv_adjoint_jacobian(const b2sv_state *s, b2sv_obs *const *obs, int n_obs,
+                          const b2sv_ops *ops, const uint64_t *trainable_params, int n_tp,
+                          double *jac_out) {
+    return guard([&] {
+        B2_ABORT_IF(!ops, "null ops handle");
+        std::vector<ObsPtr> v;
+        for (int i = 0; i < n_obs; i++) {
+            B2_ABORT_IF(!obs[i] || !obs[i]->o, "null observable handle");
+            v.push_back(obs[i]->o);
+        }
+        adjoint_jacobian(st(s), v, ops->d,
+                         std::vector<uint64_t>(trainable_params, trainable_params + n_tp), jac_out);
+    });
+}
+}

@@ -1,0 +1,696 @@
+// b2sv: stand-alone CUDA kernels -- state initialisation, generic k-qubit matrices, reductions
+// (expectation values, inner products), Pauli-sum application, CSR SpMV, probabilities, sampling.
+//
+// Reference counterparts (one Kokkos functor each):
+//   InitView / setBasisStateFunctor / setStateVectorFunctor   StateVectorKokkos.hpp:46-90
+//   multiQubitOpFunctor                                       GateFunctors.hpp:195-300
+//   getExpectationValue*Functor                               ExpValFunctors.hpp:13-280
+//   getReal/ImagOfComplexInnerProductFunctor, axpy, SparseMV  LinearAlgebraKokkos.hpp:30-236
+//   getProbFunctor / getSubProbFunctor / getCDFFunctor / Sampler   MeasuresFunctors.hpp:15-210
+// All reductions accumulate in double (also for complex64), each block writes its partial sums
+// and a single-block finalize kernel adds them in a fixed order: results are deterministic.
+#include "kernels.cuh"
+#include "common.hpp"
+
+namespace b2sv {
+namespace {
+
+template <typename real> struct AmpT;
+template <> struct AmpT<double> {
+    using type = double2;
+};
+template <> struct AmpT<float> {
+    using type = float2;
+};
+
+__device__ __forceinline__ uint64_t insert_zero(uint64_t k, int p) {
+    return ((k >> p) << (p + 1)) | (k & ((uint64_t(1) << p) - 1));
+}
+
+// ---- block reduction of NV doubles, result written to partials[blockIdx.x * NV + v]
+template <int NV> __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *partials) {
+    __shared__ double red[NV][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        double x = v[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0)
+            red[j][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            double x = lane < nw ? red[j][lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0)
+                partials[blockIdx.x * NV + j] = x;
+        }
+    }
+}
+
+__global__ void k_finalize(const double *__restrict__ partials, int nblocks, int nv,
+                           double *__restrict__ out) {
+    // one block; thread t sums blocks t, t+256, ... in a fixed order
+    __shared__ double red[kReduceThreads];
+    for (int j = 0; j < nv; j++) {
+        double x = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+            x += partials[b * nv + j];
+        red[threadIdx.x] = x;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s)
+                red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0)
+            out[j] = red[0];
+        __syncthreads();
+    }
+}
+
+// ---- state management ---------------------------------------------------------------------------
+template <typename amp_t>
+__global__ void k_set_basis(amp_t *__restrict__ state, uint64_t len, uint64_t index) {
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        amp_t v;
+        v.x = (i == index) ? 1 : 0;
+        v.y = 0;
+        state[i] = v;
+    }
+}
+template <typename amp_t>
+__global__ void k_scatter(amp_t *__restrict__ state, const uint64_t *__restrict__ idx,
+                          const double2 *__restrict__ val, size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        amp_t v;
+        v.x = val[i].x;
+        v.y = val[i].y;
+        state[idx[i]] = v;
+    }
+}
+template <typename amp_t, typename real>
+__global__ void k_axpy(real ar, real ai, const amp_t *__restrict__ x, amp_t *__restrict__ y,
+                       uint64_t len) {
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const amp_t a = x[i];
+        amp_t b = y[i];
+        b.x += ar * a.x - ai * a.y;
+        b.y += ar * a.y + ai * a.x;
+        y[i] = b;
+    }
+}
+
+// ---- generic k-qubit matrix ---------------------------------------------------------------------
+struct MatKParams {
+    int k;
+    int bits[10];   // bits[0] = MSB of the local index
+    int sorted[10]; // ascending
+};
+// One CTA works on G = max(1, blockDim/dim) groups at a time: gather 2^k amps per group to shared
+// memory, each thread produces one output row (looping when dim > blockDim), scatter back.
+template <typename amp_t>
+__global__ void k_matk(amp_t *__restrict__ state, const double2 *__restrict__ mat, MatKParams p,
+                       uint64_t ngroups) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *v = reinterpret_cast<double2 *>(smem_raw);
+    const int dim = 1 << p.k;
+    const int G = blockDim.x >= dim ? blockDim.x / dim : 1;
+    const uint64_t niter = (ngroups + G - 1) / G;
+    for (uint64_t it = blockIdx.x; it < niter; it += gridDim.x) {
+        // gather
+        for (int e = threadIdx.x; e < G * dim; e += blockDim.x) {
+            const int gs = e / dim, c = e % dim;
+            const uint64_t grp = it * G + gs;
+            if (grp < ngroups) {
+                uint64_t base = grp;
+                for (int j = 0; j < p.k; j++)
+                    base = insert_zero(base, p.sorted[j]);
+                uint64_t off = 0;
+                for (int j = 0; j < p.k; j++)
+                    if ((c >> (p.k - 1 - j)) & 1)
+                        off |= uint64_t(1) << p.bits[j];
+                const amp_t a = state[base | off];
+                v[e] = make_double2(a.x, a.y);
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < G * dim; e += blockDim.x) {
+            const int gs = e / dim, r = e % dim;
+            const uint64_t grp = it * G + gs;
+            if (grp < ngroups) {
+                double sr = 0.0, si = 0.0;
+                const double2 *row = mat + size_t(r) * dim;
+                const double2 *vin = v + gs * dim;
+                for (int c = 0; c < dim; c++) {
+                    const double2 m = row[c];
+                    const double2 x = vin[c];
+                    sr += m.x * x.x - m.y * x.y;
+                    si += m.x * x.y + m.y * x.x;
+                }
+                uint64_t base = grp;
+                for (int j = 0; j < p.k; j++)
+                    base = insert_zero(base, p.sorted[j]);
+                uint64_t off = 0;
+                for (int j = 0; j < p.k; j++)
+                    if ((r >> (p.k - 1 - j)) & 1)
+                        off |= uint64_t(1) << p.bits[j];
+                amp_t o;
+                o.x = sr;
+                o.y = si;
+                state[base | off] = o;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- reductions ---------------------------------------------------------------------------------
+template <typename amp_t>
+__global__ void __launch_bounds__(kReduceThreads)
+    k_norm2(const amp_t *__restrict__ s, uint64_t len, double *__restrict__ partials) {
+    double acc[1] = {0.0};
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const amp_t a = s[i];
+        acc[0] += double(a.x) * a.x + double(a.y) * a.y;
+    }
+    block_reduce_store<1>(acc, partials);
+}
+template <typename amp_t>
+__global__ void __launch_bounds__(kReduceThreads)
+    k_dot(const amp_t *__restrict__ x, const amp_t *__restrict__ y, uint64_t len,
+          double *__restrict__ partials) {
+    double acc[2] = {0.0, 0.0};
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const amp_t a = x[i], b = y[i];
+        acc[0] += double(a.x) * b.x + double(a.y) * b.y; // Re conj(a) b
+        acc[1] += double(a.x) * b.y - double(a.y) * b.x; // Im conj(a) b
+    }
+    block_reduce_store<2>(acc, partials);
+}
+struct M8 {
+    double m[8];
+};
+template <typename amp_t>
+__global__ void __launch_bounds__(kReduceThreads)
+    k_expval_1q(const amp_t *__restrict__ s, uint64_t npairs, int tbit, M8 mm,
+                double *__restrict__ partials) {
+    double acc[1] = {0.0};
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < npairs; k += stride) {
+        const uint64_t i0 = insert_zero(k, tbit), i1 = i0 | (uint64_t(1) << tbit);
+        const amp_t a0 = s[i0], a1 = s[i1];
+        const double v0r = a0.x, v0i = a0.y, v1r = a1.x, v1i = a1.y;
+        // w = M v ; acc += Re(conj(v) . w)
+        const double w0r = mm.m[0] * v0r - mm.m[1] * v0i + mm.m[2] * v1r - mm.m[3] * v1i;
+        const double w0i = mm.m[0] * v0i + mm.m[1] * v0r + mm.m[2] * v1i + mm.m[3] * v1r;
+        const double w1r = mm.m[4] * v0r - mm.m[5] * v0i + mm.m[6] * v1r - mm.m[7] * v1i;
+        const double w1i = mm.m[4] * v0i + mm.m[5] * v0r + mm.m[6] * v1i + mm.m[7] * v1r;
+        acc[0] += v0r * w0r + v0i * w0i + v1r * w1r + v1i * w1i;
+    }
+    block_reduce_store<1>(acc, partials);
+}
+template <typename amp_t>
+__global__ void __launch_bounds__(kReduceThreads)
+    k_expval_2q(const amp_t *__restrict__ s, uint64_t nquads, int bit_a, int bit_b,
+                const double2 *__restrict__ m16, double *__restrict__ partials) {
+    __shared__ double2 sm[16];
+    if (threadIdx.x < 16)
+        sm[threadIdx.x] = m16[threadIdx.x];
+    __syncthreads();
+    const int lo = bit_a < bit_b ? bit_a : bit_b, hi = bit_a < bit_b ? bit_b : bit_a;
+    double acc[1] = {0.0};
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < nquads; k += stride) {
+        const uint64_t base = insert_zero(insert_zero(k, lo), hi);
+        double vr[4], vi[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) { // local index c = (a_bit << 1) | b_bit
+            const uint64_t idx = base | (uint64_t((c >> 1) & 1) << bit_a) | (uint64_t(c & 1) << bit_b);
+            const amp_t a = s[idx];
+            vr[c] = a.x;
+            vi[c] = a.y;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            double wr = 0.0, wi = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const double2 m = sm[r * 4 + c];
+                wr += m.x * vr[c] - m.y * vi[c];
+                wi += m.x * vi[c] + m.y * vr[c];
+            }
+            acc[0] += vr[r] * wr + vi[r] * wi;
+        }
+    }
+    block_reduce_store<1>(acc, partials);
+}
+template <typename amp_t>
+__global__ void __launch_bounds__(kReduceThreads)
+    k_pauli_expval(const amp_t *__restrict__ s, uint64_t len, uint64_t x, uint64_t z, double phr,
+                   double phi, double *__restrict__ partials) {
+    double acc[1] = {0.0};
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const uint64_t j = i ^ x;
+        const amp_t a = s[i], b = s[j];
+        // (P psi)_i = ph * (-1)^popc(j & z) * psi_j
+        const double sg = (__popcll(j & z) & 1) ? -1.0 : 1.0;
+        const double wr = sg * (phr * b.x - phi * b.y);
+        const double wi = sg * (phr * b.y + phi * b.x);
+        acc[0] += double(a.x) * wr + double(a.y) * wi;
+    }
+    block_reduce_store<1>(acc, partials);
+}
+
+template <typename amp_t>
+__global__ void __launch_bounds__(256)
+    k_pauli_sum_apply(const amp_t *__restrict__ in, amp_t *__restrict__ out, uint64_t len,
+                      const PauliTerm *__restrict__ terms, int nterms) {
+    constexpr int CH = 128;
+    __shared__ PauliTerm st[CH];
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    const uint64_t i0 = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    // all threads of a block iterate the same number of times (len is a multiple of the stride
+    // or the tail is guarded), so the __syncthreads below are uniform
+    const uint64_t iters = (len + stride - 1) / stride;
+    for (uint64_t it = 0; it < iters; it++) {
+        const uint64_t i = i0 + it * stride;
+        double sr = 0.0, si = 0.0;
+        for (int t0 = 0; t0 < nterms; t0 += CH) {
+            const int nt = min(CH, nterms - t0);
+            __syncthreads();
+            if (threadIdx.x < nt)
+                st[threadIdx.x] = terms[t0 + threadIdx.x];
+            __syncthreads();
+            if (i < len) {
+                for (int t = 0; t < nt; t++) {
+                    const uint64_t j = i ^ st[t].x;
+                    const amp_t b = in[j];
+                    const double sg = (__popcll(j & st[t].z) & 1) ? -1.0 : 1.0;
+                    const double cr = sg * st[t].cr, ci = sg * st[t].ci;
+                    sr += cr * b.x - ci * b.y;
+                    si += cr * b.y + ci * b.x;
+                }
+            }
+        }
+        if (i < len) {
+            amp_t o;
+            o.x = sr;
+            o.y = si;
+            out[i] = o;
+        }
+    }
+}
+
+// ---- CSR ----------------------------------------------------------------------------------------
+template <typename amp_t, bool EXPVAL>
+__global__ void __launch_bounds__(kReduceThreads)
+    k_csr(const amp_t *__restrict__ x, amp_t *__restrict__ y, const double2 *__restrict__ data,
+          const uint32_t *__restrict__ ind, const uint64_t *__restrict__ ptr, uint64_t nrows,
+          int L, double *__restrict__ partials) {
+    // L lanes (power of two <= 32) cooperate on one row
+    const int sub = threadIdx.x & (L - 1);
+    const uint64_t grp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / L;
+    const uint64_t ngrp = uint64_t(gridDim.x) * blockDim.x / L;
+    double acc[1] = {0.0};
+    const uint64_t iters = (nrows + ngrp - 1) / ngrp;
+    for (uint64_t it = 0; it < iters; it++) {
+        const uint64_t row = grp + it * ngrp;
+        double sr = 0.0, si = 0.0;
+        if (row < nrows) {
+            const uint64_t b = ptr[row], e = ptr[row + 1];
+            for (uint64_t j = b + sub; j < e; j += L) {
+                const double2 d = data[j];
+                const amp_t v = x[ind[j]];
+                sr += d.x * v.x - d.y * v.y;
+                si += d.x * v.y + d.y * v.x;
+            }
+        }
+        for (int o = L >> 1; o > 0; o >>= 1) {
+            sr += __shfl_xor_sync(0xffffffffu, sr, o);
+            si += __shfl_xor_sync(0xffffffffu, si, o);
+        }
+        if (row < nrows && sub == 0) {
+            if (EXPVAL) {
+                const amp_t a = x[row];
+                acc[0] += double(a.x) * sr + double(a.y) * si; // Re(conj(psi_row) * (H psi)_row)
+            } else {
+                amp_t o;
+                o.x = sr;
+                o.y = si;
+                y[row] = o;
+            }
+        }
+    }
+    if (EXPVAL)
+        block_reduce_store<1>(acc, partials);
+}
+
+// ---- probabilities ------------------------------------------------------------------------------
+template <typename amp_t>
+__global__ void k_probs_full(const amp_t *__restrict__ s, uint64_t len, double *__restrict__ out) {
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const amp_t a = s[i];
+        out[i] = double(a.x) * a.x + double(a.y) * a.y;
+    }
+}
+struct BitList {
+    int m;
+    int pos[64];
+};
+constexpr int kMargSmemBits = 11;
+template <typename amp_t, bool PRIVATE>
+__global__ void __launch_bounds__(256)
+    k_probs_marginal(const amp_t *__restrict__ s, uint64_t len, BitList bl,
+                     double *__restrict__ out) {
+    __shared__ double hist[PRIVATE ? (1 << kMargSmemBits) : 1];
+    const int nb = 1 << bl.m;
+    if (PRIVATE) {
+        for (int b = threadIdx.x; b < nb; b += blockDim.x)
+            hist[b] = 0.0;
+        __syncthreads();
+    }
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const amp_t a = s[i];
+        const double p = double(a.x) * a.x + double(a.y) * a.y;
+        uint64_t bin = 0;
+        for (int j = 0; j < bl.m; j++)
+            bin |= ((i >> bl.pos[j]) & 1ull) << (bl.m - 1 - j);
+        if (PRIVATE)
+            atomicAdd(&hist[bin], p);
+        else if (p != 0.0)
+            atomicAdd(&out[bin], p);
+    }
+    if (PRIVATE) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nb; b += blockDim.x)
+            if (hist[b] != 0.0)
+                atomicAdd(&out[b], hist[b]);
+    }
+}
+
+// ---- sampling: chunk sums -> exclusive scan of chunk sums -> per-shot two-level search ----------
+template <typename amp_t>
+__global__ void __launch_bounds__(256)
+    k_chunk_sums(const amp_t *__restrict__ s, uint64_t len, double *__restrict__ chunk) {
+    // one block per chunk of 2^kSampleChunkBits amplitudes (or the whole state if smaller)
+    const uint64_t csz = uint64_t(1) << kSampleChunkBits;
+    const uint64_t b = uint64_t(blockIdx.x) * csz;
+    const uint64_t e = (b + csz < len) ? b + csz : len;
+    double acc = 0.0;
+    for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const amp_t a = s[i];
+        acc += double(a.x) * a.x + double(a.y) * a.y;
+    }
+    __shared__ double red[8];
+    for (int o = 16; o > 0; o >>= 1)
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0)
+        red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++)
+            t += red[w];
+        chunk[blockIdx.x] = t;
+    }
+}
+// single block, 1024 threads: in-place exclusive scan of n chunk sums; chunk[n] = total
+__global__ void __launch_bounds__(1024) k_scan_chunks(double *__restrict__ chunk, uint64_t n) {
+    __shared__ double part[1024];
+    const uint64_t per = (n + 1023) / 1024;
+    const uint64_t b = uint64_t(threadIdx.x) * per;
+    const uint64_t e = (b + per < n) ? b + per : n;
+    double sum = 0.0;
+    for (uint64_t i = b; i < e; i++)
+        sum += chunk[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double run = 0.0;
+        for (int t = 0; t < 1024; t++) {
+            const double v = part[t];
+            part[t] = run;
+            run += v;
+        }
+        chunk[n] = run;
+    }
+    __syncthreads();
+    double run = part[threadIdx.x];
+    for (uint64_t i = b; i < e; i++) {
+        const double v = chunk[i];
+        chunk[i] = run;
+        run += v;
+    }
+}
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// one warp per shot: inverse-transform sampling, index k with cdf[k] < U <= cdf[k+1]
+template <typename amp_t>
+__global__ void __launch_bounds__(256)
+    k_sample(const amp_t *__restrict__ s, uint64_t len, const double *__restrict__ ccdf,
+             uint64_t nchunks, int nq, size_t shots, uint64_t seed,
+             unsigned long long *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const size_t shot = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (shot >= shots)
+        return;
+    const double total = ccdf[nchunks];
+    const uint64_t r = splitmix64(seed ^ splitmix64(shot));
+    const double U = (double((r >> 11) + 1) * 0x1.0p-53) * total; // (0, total]
+    // binary search over chunks: largest c with ccdf[c] < U
+    uint64_t lo = 0, hi = nchunks; // invariant: ccdf[lo] < U (ccdf[0] = 0 < U), answer in [lo, hi)
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (ccdf[mid] < U)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const uint64_t csz = uint64_t(1) << kSampleChunkBits;
+    const uint64_t b = lo * csz;
+    const uint64_t e = (b + csz < len) ? b + csz : len;
+    double run = ccdf[lo];
+    uint64_t found = e - 1;
+    bool have = false;
+    uint64_t last_nz = b;
+    for (uint64_t i0 = b; i0 < e && !have; i0 += 32) {
+        const uint64_t i = i0 + lane;
+        double p = 0.0;
+        if (i < e) {
+            const amp_t a = s[i];
+            p = double(a.x) * a.x + double(a.y) * a.y;
+        }
+        double incl = p; // inclusive warp scan
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, (i < e) && (run + incl >= U) && p > 0.0);
+        const unsigned nz = __ballot_sync(0xffffffffu, p > 0.0);
+        if (hit) {
+            found = i0 + (__ffs(hit) - 1);
+            have = true;
+        } else {
+            if (nz)
+                last_nz = i0 + (31 - __clz(nz));
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    if (!have)
+        found = last_nz; // rounding at the chunk end: fall back to the last populated entry
+    if (lane == 0) {
+        for (int j = 0; j < nq; j++) // MSB (wire 0) first, as the reference (MF.hpp:113-115)
+            out[shot * nq + (nq - 1 - j)] = (found >> j) & 1ull;
+    }
+}
+
+int reduce_grid(uint64_t work) {
+    const uint64_t b = (work + kReduceThreads - 1) / kReduceThreads;
+    return static_cast<int>(b < 1 ? 1 : (b > kReduceBlocks ? kReduceBlocks : b));
+}
+} // namespace
+
+#define DISPATCH_DTYPE(dtype, expr_f, expr_d)                                                   \
+    do {                                                                                        \
+        if ((dtype) == 1) {                                                                     \
+            expr_d;                                                                             \
+        } else {                                                                                \
+            expr_f;                                                                             \
+        }                                                                                       \
+        CUDA_CHECK(cudaGetLastError());                                                         \
+    } while (0)
+
+void launch_set_basis(int dtype, void *state, uint64_t len, uint64_t index, cudaStream_t st) {
+    const int grid = reduce_grid(len);
+    DISPATCH_DTYPE(dtype,
+                   (k_set_basis<float2><<<grid, 256, 0, st>>>(static_cast<float2 *>(state), len, index)),
+                   (k_set_basis<double2><<<grid, 256, 0, st>>>(static_cast<double2 *>(state), len, index)));
+}
+void launch_scatter(int dtype, void *state, const uint64_t *d_idx, const double2 *d_val, size_t n,
+                    cudaStream_t st) {
+    if (n == 0)
+        return;
+    const int grid = static_cast<int>((n + 255) / 256);
+    DISPATCH_DTYPE(dtype,
+                   (k_scatter<float2><<<grid, 256, 0, st>>>(static_cast<float2 *>(state), d_idx, d_val, n)),
+                   (k_scatter<double2><<<grid, 256, 0, st>>>(static_cast<double2 *>(state), d_idx, d_val, n)));
+}
+void launch_axpy(int dtype, double ar, double ai, const void *x, void *y, uint64_t len,
+                 cudaStream_t st) {
+    const int grid = reduce_grid(len);
+    DISPATCH_DTYPE(dtype,
+                   (k_axpy<float2, float><<<grid, 256, 0, st>>>(float(ar), float(ai), static_cast<const float2 *>(x), static_cast<float2 *>(y), len)),
+                   (k_axpy<double2, double><<<grid, 256, 0, st>>>(ar, ai, static_cast<const double2 *>(x), static_cast<double2 *>(y), len)));
+}
+void launch_matk(int dtype, void *state, int n_eff, const double2 *d_mat, const int *h_bits, int k,
+                 cudaStream_t st) {
+    MatKParams p{};
+    p.k = k;
+    for (int j = 0; j < k; j++)
+        p.bits[j] = p.sorted[j] = h_bits[j];
+    for (int a = 0; a < k; a++)
+        for (int b = a + 1; b < k; b++)
+            if (p.sorted[b] < p.sorted[a]) {
+                const int t = p.sorted[a];
+                p.sorted[a] = p.sorted[b];
+                p.sorted[b] = t;
+            }
+    const int dim = 1 << k;
+    const int threads = 128;
+    const int G = threads >= dim ? threads / dim : 1;
+    const uint64_t ngroups = uint64_t(1) << (n_eff - k);
+    const uint64_t niter = (ngroups + G - 1) / G;
+    const int grid = static_cast<int>(niter < 148 * 16 ? niter : 148 * 16);
+    const size_t smem = sizeof(double2) * size_t(G) * dim;
+    DISPATCH_DTYPE(dtype,
+                   (k_matk<float2><<<grid, threads, smem, st>>>(static_cast<float2 *>(state), d_mat, p, ngroups)),
+                   (k_matk<double2><<<grid, threads, smem, st>>>(static_cast<double2 *>(state), d_mat, p, ngroups)));
+}
+
+void launch_norm2(int dtype, const void *state, uint64_t len, double *d_partials, cudaStream_t st) {
+    DISPATCH_DTYPE(dtype,
+                   (k_norm2<float2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), len, d_partials)),
+                   (k_norm2<double2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), len, d_partials)));
+}
+void launch_dot(int dtype, const void *x, const void *y, uint64_t len, double *d_partials,
+                cudaStream_t st) {
+    DISPATCH_DTYPE(dtype,
+                   (k_dot<float2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(x), static_cast<const float2 *>(y), len, d_partials)),
+                   (k_dot<double2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(x), static_cast<const double2 *>(y), len, d_partials)));
+}
+void launch_expval_1q(int dtype, const void *state, uint64_t len, int tbit, const double *m8,
+                      double *d_partials, cudaStream_t st) {
+    M8 mm;
+    for (int i = 0; i < 8; i++)
+        mm.m[i] = m8[i];
+    DISPATCH_DTYPE(dtype,
+                   (k_expval_1q<float2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), len / 2, tbit, mm, d_partials)),
+                   (k_expval_1q<double2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), len / 2, tbit, mm, d_partials)));
+}
+void launch_expval_2q(int dtype, const void *state, uint64_t len, int bit_a, int bit_b,
+                      const double2 *d_m16, double *d_partials, cudaStream_t st) {
+    DISPATCH_DTYPE(dtype,
+                   (k_expval_2q<float2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), len / 4, bit_a, bit_b, d_m16, d_partials)),
+                   (k_expval_2q<double2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), len / 4, bit_a, bit_b, d_m16, d_partials)));
+}
+void launch_pauli_expval(int dtype, const void *state, uint64_t len, uint64_t x, uint64_t z,
+                         double phr, double phi, double *d_partials, cudaStream_t st) {
+    DISPATCH_DTYPE(dtype,
+                   (k_pauli_expval<float2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), len, x, z, phr, phi, d_partials)),
+                   (k_pauli_expval<double2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), len, x, z, phr, phi, d_partials)));
+}
+void launch_finalize(const double *d_partials, int nblocks, int nv, double *d_out,
+                     cudaStream_t st) {
+    k_finalize<<<1, kReduceThreads, 0, st>>>(d_partials, nblocks, nv, d_out);
+    CUDA_CHECK(cudaGetLastError());
+}
+void launch_pauli_sum_apply(int dtype, const void *in, void *out, uint64_t len,
+                            const PauliTerm *d_terms, int nterms, cudaStream_t st) {
+    const uint64_t b = (len + 255) / 256;
+    const int grid = static_cast<int>(b < 148 * 8 ? b : 148 * 8);
+    DISPATCH_DTYPE(dtype,
+                   (k_pauli_sum_apply<float2><<<grid, 256, 0, st>>>(static_cast<const float2 *>(in), static_cast<float2 *>(out), len, d_terms, nterms)),
+                   (k_pauli_sum_apply<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(in), static_cast<double2 *>(out), len, d_terms, nterms)));
+}
+void launch_csr_expval(int dtype, const void *state, const double2 *d_data, const uint32_t *d_ind,
+                       const uint64_t *d_ptr, uint64_t nrows, int L, double *d_partials,
+                       cudaStream_t st) {
+    DISPATCH_DTYPE(dtype,
+                   (k_csr<float2, true><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), nullptr, d_data, d_ind, d_ptr, nrows, L, d_partials)),
+                   (k_csr<double2, true><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), nullptr, d_data, d_ind, d_ptr, nrows, L, d_partials)));
+}
+void launch_csr_spmv(int dtype, const void *x, void *y, const double2 *d_data,
+                     const uint32_t *d_ind, const uint64_t *d_ptr, uint64_t nrows, int L,
+                     cudaStream_t st) {
+    DISPATCH_DTYPE(dtype,
+                   (k_csr<float2, false><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(x), static_cast<float2 *>(y), d_data, d_ind, d_ptr, nrows, L, nullptr)),
+                   (k_csr<double2, false><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(x), static_cast<double2 *>(y), d_data, d_ind, d_ptr, nrows, L, nullptr)));
+}
+void launch_probs_full(int dtype, const void *state, uint64_t len, double *d_out, cudaStream_t st) {
+    const int grid = reduce_grid(len);
+    DISPATCH_DTYPE(dtype,
+                   (k_probs_full<float2><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), len, d_out)),
+                   (k_probs_full<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, d_out)));
+}
+void launch_probs_marginal(int dtype, const void *state, uint64_t len, const int *h_bitpos, int m,
+                           double *d_out, cudaStream_t st) {
+    BitList bl{};
+    bl.m = m;
+    for (int j = 0; j < m; j++)
+        bl.pos[j] = h_bitpos[j];
+    const int grid = reduce_grid(len);
+    if (m <= kMargSmemBits) {
+        DISPATCH_DTYPE(dtype,
+                       (k_probs_marginal<float2, true><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), len, bl, d_out)),
+                       (k_probs_marginal<double2, true><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, bl, d_out)));
+    } else {
+        DISPATCH_DTYPE(dtype,
+                       (k_probs_marginal<float2, false><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), len, bl, d_out)),
+                       (k_probs_marginal<double2, false><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, bl, d_out)));
+    }
+}
+void launch_chunk_sums(int dtype, const void *state, uint64_t len, double *d_chunk,
+                       cudaStream_t st) {
+    const uint64_t csz = uint64_t(1) << kSampleChunkBits;
+    const int grid = static_cast<int>((len + csz - 1) / csz);
+    DISPATCH_DTYPE(dtype,
+                   (k_chunk_sums<float2><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), len, d_chunk)),
+                   (k_chunk_sums<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, d_chunk)));
+}
+void launch_scan_chunks(double *d_chunk, uint64_t nchunks, cudaStream_t st) {
+    k_scan_chunks<<<1, 1024, 0, st>>>(d_chunk, nchunks);
+    CUDA_CHECK(cudaGetLastError());
+}
+void launch_sample(int dtype, const void *state, uint64_t len, const double *d_chunk_cdf,
+                   uint64_t nchunks, int num_qubits, size_t shots, uint64_t seed,
+                   unsigned long long *d_out, cudaStream_t st) {
+    if (shots == 0)
+        return;
+    const int grid = static_cast<int>((shots * 32 + 255) / 256);
+    DISPATCH_DTYPE(dtype,
+                   (k_sample<float2><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), len, d_chunk_cdf, nchunks, num_qubits, shots, seed, d_out)),
+                   (k_sample<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, d_chunk_cdf, nchunks, num_qubits, shots, seed, d_out)));
+}
+
+} // namespace b2sv

@@ -1,0 +1,74 @@
+// b2sv: host-callable launchers of the stand-alone CUDA kernels (kernels.cu, tile_kernel.cu).
+// dtype: 0 = complex64, 1 = complex128. All launches are asynchronous on `stream`.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b2sv {
+
+constexpr int kReduceBlocks = 1184; // 148 SMs x 8 resident CTAs of 256 threads
+constexpr int kReduceThreads = 256;
+constexpr int kMaxReduceVals = 8;
+
+// ---- tile executor (tile_kernel.cu)
+void tile_config(int dtype, int *B, int *R);
+void launch_tile_pass(int dtype, void *state, const unsigned char *dev_blob, int n_eff,
+                      uint64_t rank_bits, cudaStream_t stream);
+
+// ---- state management
+void launch_set_basis(int dtype, void *state, uint64_t len, uint64_t index, cudaStream_t st);
+void launch_scatter(int dtype, void *state, const uint64_t *d_idx, const double2 *d_val, size_t n,
+                    cudaStream_t st);
+void launch_axpy(int dtype, double ar, double ai, const void *x, void *y, uint64_t len,
+                 cudaStream_t st);
+// generic k-qubit matrix (row-major, device, complex128), bits[0] = MSB of the local index
+void launch_matk(int dtype, void *state, int n_eff, const double2 *d_mat, const int *h_bits, int k,
+                 cudaStream_t st);
+
+// ---- reductions: every kernel writes kReduceBlocks x nv partials; finalize sums them (fixed order)
+void launch_norm2(int dtype, const void *state, uint64_t len, double *d_partials, cudaStream_t st);
+void launch_dot(int dtype, const void *x, const void *y, uint64_t len, double *d_partials,
+                cudaStream_t st); // 2 values: Re<x|y>, Im<x|y>
+void launch_expval_1q(int dtype, const void *state, uint64_t len, int tbit, const double *m8,
+                      double *d_partials, cudaStream_t st);
+void launch_expval_2q(int dtype, const void *state, uint64_t len, int bit_a, int bit_b,
+                      const double2 *d_m16, double *d_partials, cudaStream_t st);
+// <psi| P |psi> for a Pauli word: P|j> = ph * (-1)^popc(j & z) |j ^ x>, ph = i^nY
+void launch_pauli_expval(int dtype, const void *state, uint64_t len, uint64_t x, uint64_t z,
+                         double phr, double phi, double *d_partials, cudaStream_t st);
+void launch_finalize(const double *d_partials, int nblocks, int nv, double *d_out,
+                     cudaStream_t st);
+
+struct PauliTerm {
+    uint64_t x, z;
+    double cr, ci; // coefficient * i^nY
+};
+// out = sum_t coef_t P_t in   (in != out)
+void launch_pauli_sum_apply(int dtype, const void *in, void *out, uint64_t len,
+                            const PauliTerm *d_terms, int nterms, cudaStream_t st);
+
+// ---- CSR (device-resident, 32- or 64-bit indices chosen by the caller: here always 64-bit ptr,
+// 32-bit column indices when nrows < 2^32)
+void launch_csr_expval(int dtype, const void *state, const double2 *d_data, const uint32_t *d_ind,
+                       const uint64_t *d_ptr, uint64_t nrows, int lanes_per_row,
+                       double *d_partials, cudaStream_t st);
+void launch_csr_spmv(int dtype, const void *x, void *y, const double2 *d_data,
+                     const uint32_t *d_ind, const uint64_t *d_ptr, uint64_t nrows,
+                     int lanes_per_row, cudaStream_t st);
+
+// ---- probabilities and sampling
+void launch_probs_full(int dtype, const void *state, uint64_t len, double *d_out, cudaStream_t st);
+// d_out must be zeroed; bitpos[j] = index bit of requested wire j (wire order = output bit order,
+// first wire = MSB of the output index)
+void launch_probs_marginal(int dtype, const void *state, uint64_t len, const int *h_bitpos, int m,
+                           double *d_out, cudaStream_t st);
+constexpr int kSampleChunkBits = 12;
+void launch_chunk_sums(int dtype, const void *state, uint64_t len, double *d_chunk,
+                       cudaStream_t st);
+void launch_scan_chunks(double *d_chunk, uint64_t nchunks, cudaStream_t st); // exclusive, + total
+void launch_sample(int dtype, const void *state, uint64_t len, const double *d_chunk_cdf,
+                   uint64_t nchunks, int num_qubits, size_t shots, uint64_t seed,
+                   unsigned long long *d_out, cudaStream_t st);
+
+} // namespace b2sv

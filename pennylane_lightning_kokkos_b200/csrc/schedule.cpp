@@ -1,0 +1,323 @@
+// b2sv: fusion scheduler implementation (see schedule.hpp).
+#include "schedule.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace b2sv {
+namespace {
+
+inline int popc(uint64_t x) { return __builtin_popcountll(x); }
+inline int ctz(uint64_t x) { return __builtin_ctzll(x); }
+
+bool is_plain_1q(const Prim &p) {
+    if (p.tag >= 0 || p.cmask != 0)
+        return false;
+    if (p.type == Prim::C1Q)
+        return true;
+    return p.type == Prim::DIAG && popc(p.pmask) == 1;
+}
+int bit_of_1q(const Prim &p) { return p.type == Prim::C1Q ? p.target : ctz(p.pmask); }
+void matrix_of_1q(const Prim &p, cplx m[4]) {
+    if (p.type == Prim::C1Q) {
+        for (int i = 0; i < 4; i++)
+            m[i] = p.m[i];
+    } else {
+        m[0] = p.m[0];
+        m[1] = 0;
+        m[2] = 0;
+        m[3] = p.m[1];
+    }
+}
+void store_1q(Prim &p, int t, const cplx m[4]) {
+    p.cmask = p.cval = 0;
+    if (m[1] == cplx(0.0) && m[2] == cplx(0.0)) {
+        p.type = Prim::DIAG;
+        p.target = -1;
+        p.pmask = bit(t);
+        p.m[0] = m[0];
+        p.m[1] = m[3];
+        p.m[2] = p.m[3] = 0;
+    } else {
+        p.type = Prim::C1Q;
+        p.target = t;
+        p.pmask = 0;
+        for (int i = 0; i < 4; i++)
+            p.m[i] = m[i];
+    }
+}
+} // namespace
+
+std::vector<Prim> fuse_single_qubit(const std::vector<Prim> &prims) {
+    std::vector<Prim> out;
+    out.reserve(prims.size());
+    int last_touch[64];
+    for (int &x : last_touch)
+        x = -1;
+    for (const Prim &p : prims) {
+        if (is_plain_1q(p)) {
+            const int t = bit_of_1q(p);
+            const int j = last_touch[t];
+            if (j >= 0 && is_plain_1q(out[j]) && bit_of_1q(out[j]) == t) {
+                // nothing between out[j] and p touches bit t, so p commutes back to out[j]
+                cplx a[4], b[4], c[4];
+                matrix_of_1q(p, a);
+                matrix_of_1q(out[j], b);
+                c[0] = a[0] * b[0] + a[1] * b[2];
+                c[1] = a[0] * b[1] + a[1] * b[3];
+                c[2] = a[2] * b[0] + a[3] * b[2];
+                c[3] = a[2] * b[1] + a[3] * b[3];
+                store_1q(out[j], t, c);
+                continue;
+            }
+        }
+        const int idx = static_cast<int>(out.size());
+        out.push_back(p);
+        if (out.back().type == Prim::C1Q && out.back().m[1] == cplx(0.0) &&
+            out.back().m[2] == cplx(0.0)) { // diagonal 2x2 -> DIAG (keeps its control)
+            Prim &q = out.back();
+            q.type = Prim::DIAG;
+            q.pmask = bit(q.target);
+            q.target = -1;
+            q.m[1] = q.m[3];
+            q.m[2] = q.m[3] = 0;
+        }
+        uint64_t s = out.back().support();
+        while (s) {
+            last_touch[ctz(s)] = idx;
+            s &= s - 1;
+        }
+    }
+    return out;
+}
+
+namespace {
+
+OpKind classify(const Prim &p) {
+    if (p.type == Prim::DIAG)
+        return KIND_DIAG;
+    const cplx *m = p.m;
+    if (m[0] == cplx(0.0) && m[3] == cplx(0.0) && m[1] == cplx(1.0) && m[2] == cplx(1.0))
+        return KIND_PERM;
+    if (m[0].imag() == 0 && m[1].imag() == 0 && m[2].imag() == 0 && m[3].imag() == 0)
+        return KIND_REAL;
+    return KIND_GENERAL;
+}
+
+// Dependency filter shared by pass- and round-level greedy selection.
+struct Blocker {
+    uint64_t t = 0; // bits some skipped op acts on non-diagonally
+    uint64_t d = 0; // bits some skipped op uses diagonally (control / phase)
+    bool blocked(const Prim &p) const {
+        const uint64_t tm = p.target_mask(), dm = p.support() & ~tm;
+        return (tm & (t | d)) || (dm & t);
+    }
+    void skip(const Prim &p) {
+        const uint64_t tm = p.target_mask();
+        t |= tm;
+        d |= p.support() & ~tm;
+    }
+};
+
+DevOp make_devop(const Prim &p, const uint8_t *tile_bits, int B, const uint8_t *regbits, int R,
+                 int jac) {
+    DevOp o;
+    std::memset(&o, 0, sizeof(o));
+    o.kind = classify(p);
+    o.jac = static_cast<int16_t>(jac);
+    if (p.type == Prim::DIAG) {
+        o.m[0] = p.m[0].real();
+        o.m[1] = p.m[0].imag();
+        o.m[2] = p.m[1].real();
+        o.m[3] = p.m[1].imag();
+    } else {
+        for (int i = 0; i < 4; i++) {
+            o.m[2 * i] = p.m[i].real();
+            o.m[2 * i + 1] = p.m[i].imag();
+        }
+    }
+    uint64_t tile_mask = 0;
+    for (int j = 0; j < B; j++)
+        tile_mask |= bit(tile_bits[j]);
+    o.gcm = p.cmask & ~tile_mask;
+    o.gcv = p.cval & ~tile_mask;
+    o.gpm = p.pmask & ~tile_mask;
+    uint32_t rcm = 0, rcv = 0, rpm = 0;
+    int tslot = -1;
+    for (int j = 0; j < B; j++) {
+        const uint64_t g = bit(tile_bits[j]);
+        int slot = -1;
+        for (int s = 0; s < R; s++)
+            if (regbits[s] == j)
+                slot = s;
+        if (p.type == Prim::C1Q && p.target == tile_bits[j]) {
+            B2_ASSERT(slot >= 0);
+            tslot = slot;
+        }
+        if (p.cmask & g) {
+            if (slot >= 0) {
+                rcm |= 1u << slot;
+                if (p.cval & g)
+                    rcv |= 1u << slot;
+            } else {
+                o.lcm |= 1u << j;
+                if (p.cval & g)
+                    o.lcv |= 1u << j;
+            }
+        }
+        if (p.pmask & g) {
+            if (slot >= 0)
+                rpm |= 1u << slot;
+            else
+                o.lpm |= 1u << j;
+        }
+    }
+    if (p.type == Prim::C1Q) {
+        B2_ASSERT(tslot >= 0);
+        o.tslot = static_cast<uint8_t>(tslot);
+    }
+    for (uint32_t s = 0; s < (1u << R); s++) {
+        if ((s & rcm) == rcv)
+            o.slot_act |= 1u << s;
+        if (__builtin_popcount(s & rpm) & 1)
+            o.slot_par |= 1u << s;
+    }
+    return o;
+}
+
+} // namespace
+
+std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedConfig &cfg) {
+    const int B = cfg.B, R = cfg.R, low = std::min(cfg.low, cfg.B);
+    B2_ASSERT(B <= kMaxTileBits && R <= kMaxRegBits && R <= B);
+    const std::vector<Prim> prims = fuse_single_qubit(prims_in);
+    const int N = static_cast<int>(prims.size());
+    std::vector<char> done(N, 0);
+    std::vector<Pass> passes;
+    const uint64_t low_mask = bit(low) - 1;
+
+    int first = 0;
+    while (first < N) {
+        if (done[first]) {
+            first++;
+            continue;
+        }
+        if (prims[first].type == Prim::MATK) {
+            Pass ps;
+            ps.is_matk = true;
+            ps.matk = prims[first];
+            passes.push_back(std::move(ps));
+            done[first++] = 1;
+            continue;
+        }
+        // ---- choose the ops and the tile bits of this pass
+        uint64_t tile_mask = low_mask;
+        int free_bits = B - low;
+        Blocker blk;
+        std::vector<int> chosen;
+        for (int i = first; i < N && static_cast<int>(chosen.size()) < kMaxOpsPerPass; i++) {
+            if (done[i])
+                continue;
+            const Prim &p = prims[i];
+            if (p.type == Prim::MATK)
+                break; // full barrier
+            bool fits = !blk.blocked(p);
+            if (fits && p.type == Prim::C1Q) {
+                B2_ABORT_IF(p.target >= cfg.n_local,
+                            "internal: non-diagonal target on a global (rank) qubit");
+                if (!(tile_mask & bit(p.target))) {
+                    if (free_bits > 0) {
+                        tile_mask |= bit(p.target);
+                        free_bits--;
+                    } else {
+                        fits = false;
+                    }
+                }
+            }
+            if (fits) {
+                chosen.push_back(i);
+                done[i] = 1;
+            } else {
+                blk.skip(p);
+            }
+        }
+        B2_ASSERT(!chosen.empty());
+        for (int b = 0; free_bits > 0; b++) { // pad the tile with the lowest unused local bits
+            B2_ASSERT(b < cfg.n_local);
+            if (!(tile_mask & bit(b))) {
+                tile_mask |= bit(b);
+                free_bits--;
+            }
+        }
+        Pass ps;
+        ps.hdr.low_bits = low;
+        {
+            int j = 0;
+            for (int b = 0; b < 64; b++)
+                if (tile_mask & bit(b))
+                    ps.hdr.tile_bits[j++] = static_cast<uint8_t>(b);
+            B2_ASSERT(j == B);
+        }
+        // ---- rounds
+        std::vector<int> remaining = chosen;
+        int n_rounds = 0;
+        while (!remaining.empty()) {
+            B2_ABORT_IF(n_rounds >= kMaxRounds, "internal: too many rounds in a pass");
+            uint32_t reg_mask = 0; // over tile-local positions
+            int reg_free = R;
+            Blocker rb;
+            std::vector<int> now, later;
+            for (int i : remaining) {
+                const Prim &p = prims[i];
+                bool fits = !rb.blocked(p);
+                if (fits && p.type == Prim::C1Q) {
+                    int j = 0;
+                    while (ps.hdr.tile_bits[j] != p.target)
+                        j++;
+                    if (!(reg_mask & (1u << j))) {
+                        if (reg_free > 0) {
+                            reg_mask |= 1u << j;
+                            reg_free--;
+                        } else {
+                            fits = false;
+                        }
+                    }
+                }
+                if (fits) {
+                    now.push_back(i);
+                } else {
+                    rb.skip(p);
+                    later.push_back(i);
+                }
+            }
+            for (int j = B - 1; reg_free > 0; j--) { // pad with the highest unused tile bits
+                B2_ASSERT(j >= 0);
+                if (!(reg_mask & (1u << j))) {
+                    reg_mask |= 1u << j;
+                    reg_free--;
+                }
+            }
+            uint8_t *rbits = ps.hdr.round_regbits[n_rounds];
+            {
+                int s = 0;
+                for (int j = 0; j < B; j++)
+                    if (reg_mask & (1u << j))
+                        rbits[s++] = static_cast<uint8_t>(j);
+            }
+            ps.hdr.round_begin[n_rounds] = static_cast<uint16_t>(ps.ops.size());
+            for (int i : now) {
+                ps.ops.push_back(make_devop(prims[i], ps.hdr.tile_bits, B, rbits, R, -1));
+                ps.tags.push_back(prims[i].tag);
+            }
+            n_rounds++;
+            remaining.swap(later);
+        }
+        ps.hdr.round_begin[n_rounds] = static_cast<uint16_t>(ps.ops.size());
+        ps.hdr.n_rounds = n_rounds;
+        ps.hdr.n_ops = static_cast<int32_t>(ps.ops.size());
+        passes.push_back(std::move(ps));
+    }
+    return passes;
+}
+
+} // namespace b2sv

@@ -1,0 +1,533 @@
+// b2sv: State implementation (see state.hpp).
+#include "state.hpp"
+#include "comm.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace b2sv {
+
+namespace {
+void order_after(cudaStream_t waiter, cudaStream_t signaler) {
+    if (waiter == signaler)
+        return;
+    cudaEvent_t ev;
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(ev, signaler));
+    CUDA_CHECK(cudaStreamWaitEvent(waiter, ev, 0));
+    CUDA_CHECK(cudaEventDestroy(ev));
+}
+int log2_exact(int x) {
+    int g = 0;
+    while ((1 << g) < x)
+        g++;
+    B2_ABORT_IF((1 << g) != x, "world size must be a power of two");
+    return g;
+}
+} // namespace
+
+CsrDevice::~CsrDevice() {
+    cudaSetDevice(device);
+    cudaFree(data);
+    cudaFree(ind);
+    cudaFree(ptr);
+}
+
+std::shared_ptr<CsrDevice> csr_upload(int device, const cplx *data, const uint64_t *indices,
+                                      const uint64_t *indptr, size_t nnz, size_t nrows) {
+    CUDA_CHECK(cudaSetDevice(device));
+    B2_ABORT_IF(nrows >= (uint64_t(1) << 32), "CSR matrices with 2^32 or more rows are not supported");
+    B2_ABORT_IF(indptr[nrows] != nnz, "CSR indptr does not match the number of non-zeros");
+    auto m = std::make_shared<CsrDevice>();
+    m->device = device;
+    m->nrows = nrows;
+    m->nnz = nnz;
+    std::vector<uint32_t> ind32(nnz);
+    for (size_t i = 0; i < nnz; i++) {
+        B2_ABORT_IF(indices[i] >= nrows, "CSR column index out of range");
+        ind32[i] = static_cast<uint32_t>(indices[i]);
+    }
+    CUDA_CHECK(cudaMalloc(&m->data, sizeof(double2) * std::max<size_t>(nnz, 1)));
+    CUDA_CHECK(cudaMalloc(&m->ind, sizeof(uint32_t) * std::max<size_t>(nnz, 1)));
+    CUDA_CHECK(cudaMalloc(&m->ptr, sizeof(uint64_t) * (nrows + 1)));
+    CUDA_CHECK(cudaMemcpy(m->data, data, sizeof(double2) * nnz, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(m->ind, ind32.data(), sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(m->ptr, indptr, sizeof(uint64_t) * (nrows + 1), cudaMemcpyHostToDevice));
+    const double avg = nrows ? double(nnz) / double(nrows) : 1.0;
+    int L = 1;
+    while (L < 32 && L < avg)
+        L <<= 1;
+    m->lanes = L;
+    return m;
+}
+
+State::State(int num_qubits, int dtype, int device, int rank, int world, const void *nccl_id)
+    : n_(num_qubits), dtype_(dtype), device_(device), rank_(rank), world_(world) {
+    B2_ABORT_IF(dtype != 0 && dtype != 1, "dtype must be B2SV_C64 (0) or B2SV_C128 (1)");
+    B2_ABORT_IF(num_qubits < 1 || num_qubits > 60, "number of qubits out of range");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    B2_ABORT_IF(e != cudaSuccess || ndev == 0,
+                "no CUDA device available: b2sv has no CPU fallback (" +
+                    std::string(cudaGetErrorString(e)) + ")");
+    B2_ABORT_IF(device < 0 || device >= ndev, "device_id out of range");
+    CUDA_CHECK(cudaSetDevice(device_));
+    gbits_ = log2_exact(world);
+    B2_ABORT_IF(rank < 0 || rank >= world, "rank out of range");
+    B2_ABORT_IF(num_qubits - gbits_ < 1, "too few qubits for this many ranks");
+    n_local_ = n_ - gbits_;
+    tile_config(dtype_, &B_, &R_);
+    n_eff_ = std::max(n_local_, B_);
+    B2_ABORT_IF(world > 1 && n_local_ < B_ + gbits_,
+                "sharded states need at least tile_bits + log2(world) local qubits");
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    e = cudaMalloc(&d_state_, alloc_length() * amp_bytes());
+    B2_ABORT_IF(e != cudaSuccess, std::string("cannot allocate the state vector: ") +
+                                      cudaGetErrorString(e));
+    CUDA_CHECK(cudaEventCreateWithFlags(&blob_evt_, cudaEventDisableTiming));
+    CUDA_CHECK(cudaMalloc(&d_partials_, sizeof(double) * kReduceBlocks * kMaxReduceVals));
+    CUDA_CHECK(cudaMalloc(&d_out_, sizeof(double) * 64));
+    CUDA_CHECK(cudaMallocHost(&h_out_, sizeof(double) * 64));
+    if (world_ > 1)
+        comm_ = comm_create(rank_, world_, nccl_id, device_);
+    reset();
+}
+
+State::~State() {
+    cudaSetDevice(device_);
+    if (stream_)
+        cudaStreamSynchronize(stream_);
+    if (comm_)
+        comm_destroy(comm_);
+    for (void *p : scratch_)
+        cudaFree(p);
+    cudaFree(d_state_);
+    cudaFree(d_blob_);
+    if (h_blob_)
+        cudaFreeHost(h_blob_);
+    cudaFree(d_partials_);
+    cudaFree(d_out_);
+    if (h_out_)
+        cudaFreeHost(h_out_);
+    if (blob_evt_)
+        cudaEventDestroy(blob_evt_);
+    if (stream_)
+        cudaStreamDestroy(stream_);
+}
+
+void State::sync() const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+// ---- initialisation / copies ----------------------------------------------------------------------
+void State::reset() { set_basis_state(0); }
+void State::init_zeros() {
+    CUDA_CHECK(cudaSetDevice(device_));
+    CUDA_CHECK(cudaMemsetAsync(d_state_, 0, alloc_length() * amp_bytes(), stream_));
+}
+void State::set_basis_state(uint64_t index) {
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(n_ < 64 && index >= (uint64_t(1) << n_), "basis-state index out of range");
+    const uint64_t owner = index >> n_local_;
+    const uint64_t local = (owner == static_cast<uint64_t>(rank_)) ? (index & (local_length() - 1))
+                                                                    : ~uint64_t(0);
+    launch_set_basis(dtype_, d_state_, alloc_length(), local, stream_);
+    launches++;
+}
+void State::set_state_vector(const uint64_t *indices, const cplx *values, size_t n) {
+    CUDA_CHECK(cudaSetDevice(device_));
+    init_zeros();
+    std::vector<uint64_t> idx;
+    std::vector<double2> val;
+    for (size_t i = 0; i < n; i++) {
+        B2_ABORT_IF(n_ < 64 && indices[i] >= (uint64_t(1) << n_), "state index out of range");
+        if ((indices[i] >> n_local_) == static_cast<uint64_t>(rank_)) {
+            idx.push_back(indices[i] & (local_length() - 1));
+            val.push_back(make_double2(values[i].real(), values[i].imag()));
+        }
+    }
+    if (idx.empty())
+        return;
+    uint64_t *d_idx;
+    double2 *d_val;
+    CUDA_CHECK(cudaMallocAsync(&d_idx, sizeof(uint64_t) * idx.size(), stream_));
+    CUDA_CHECK(cudaMallocAsync(&d_val, sizeof(double2) * val.size(), stream_));
+    CUDA_CHECK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(uint64_t) * idx.size(),
+                               cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(d_val, val.data(), sizeof(double2) * val.size(),
+                               cudaMemcpyHostToDevice, stream_));
+    launch_scatter(dtype_, d_state_, d_idx, d_val, idx.size(), stream_);
+    launches++;
+    CUDA_CHECK(cudaFreeAsync(d_idx, stream_));
+    CUDA_CHECK(cudaFreeAsync(d_val, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_)); // host vectors go out of scope
+}
+void State::h2d(const void *host, size_t length) {
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(length != local_length(), "HostToDevice: length does not match the state vector");
+    CUDA_CHECK(cudaMemcpyAsync(d_state_, host, length * amp_bytes(), cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+void State::d2h(void *host, size_t length) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(length != local_length(), "DeviceToHost: length does not match the state vector");
+    CUDA_CHECK(cudaMemcpyAsync(host, d_state_, length * amp_bytes(), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+void State::copy_from(const State &o) {
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(o.n_ != n_ || o.dtype_ != dtype_ || o.world_ != world_ || o.device_ != device_,
+                "state vectors are not compatible");
+    order_after(stream_, o.stream_);
+    CUDA_CHECK(cudaMemcpyAsync(d_state_, o.d_state_, alloc_length() * amp_bytes(),
+                               cudaMemcpyDeviceToDevice, stream_));
+    order_after(o.stream_, stream_);
+}
+std::unique_ptr<State> State::clone() const {
+    B2_ABORT_IF(world_ > 1, "clone of a sharded state must go through b2sv_create_sharded + copy");
+    auto c = std::make_unique<State>(n_, dtype_, device_);
+    c->fuse_ = fuse_;
+    c->copy_from(*this);
+    return c;
+}
+void State::swap_buffer(void *&other) { std::swap(d_state_, other); }
+void *State::acquire_scratch() const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    if (!scratch_.empty()) {
+        void *p = scratch_.back();
+        scratch_.pop_back();
+        return p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, alloc_length() * amp_bytes());
+    B2_ABORT_IF(e != cudaSuccess, std::string("cannot allocate a scratch state vector: ") +
+                                      cudaGetErrorString(e));
+    return p;
+}
+void State::release_scratch(void *p) const {
+    if (scratch_.size() < 2) {
+        scratch_.push_back(p);
+    } else {
+        cudaStreamSynchronize(stream_);
+        cudaFree(p);
+    }
+}
+
+// ---- gates ----------------------------------------------------------------------------------------
+void State::lower(const GateOp &op, bool flip_inverse, std::vector<Prim> &out) const {
+    const std::vector<int> bits = wires_to_bits(op.wires, n_);
+    const bool inv = op.inverse ^ flip_inverse;
+    if (op.name == "Identity")
+        return;
+    if (lower_gate(op.name, bits, inv, op.params, out))
+        return;
+    // not a named gate: the matrix path (reference StateVectorKokkos.hpp:592-598)
+    B2_ABORT_IF(op.matrix.empty(),
+                "operation '" + op.name + "' is not a named gate and no matrix was provided");
+    lower_matrix(bits, inv, op.matrix, out);
+}
+
+void State::apply_gate(const GateOp &op) {
+    std::vector<Prim> prims;
+    lower(op, false, prims);
+    apply_prims(std::move(prims));
+}
+
+void State::apply_ops(const std::vector<GateOp> &ops, bool adjoint) {
+    std::vector<Prim> prims;
+    auto flush = [&]() {
+        if (!prims.empty())
+            apply_prims(std::move(prims));
+        prims.clear();
+    };
+    if (!adjoint) {
+        for (const auto &op : ops) {
+            lower(op, false, prims);
+            if (!fuse_)
+                flush();
+        }
+    } else {
+        for (auto it = ops.rbegin(); it != ops.rend(); ++it) {
+            lower(*it, true, prims);
+            if (!fuse_)
+                flush();
+        }
+    }
+    flush();
+}
+
+double State::apply_generator(const std::string &name, const std::vector<int64_t> &wires) {
+    std::vector<Prim> prims;
+    double scale = 0.0;
+    const bool ok = lower_generator(name, wires_to_bits(wires, n_), prims, &scale);
+    B2_ABORT_IF(!ok, "Generator does not exist for " + name); // SV.hpp:692-693
+    apply_prims(std::move(prims));
+    return scale;
+}
+
+void State::apply_prims(std::vector<Prim> prims) {
+    if (prims.empty())
+        return;
+    CUDA_CHECK(cudaSetDevice(device_));
+    if (comm_)
+        comm_localize(comm_, *this, prims); // global<->local qubit swaps where needed
+    SchedConfig cfg;
+    cfg.B = B_;
+    cfg.R = R_;
+    cfg.low = 5;
+    cfg.n_local = n_local_;
+    upload_and_run(build_schedule(prims, cfg));
+}
+
+void State::upload_and_run(const std::vector<Pass> &passes) {
+    size_t total = 0;
+    std::vector<size_t> offs(passes.size(), 0);
+    for (size_t i = 0; i < passes.size(); i++) {
+        if (passes[i].is_matk)
+            continue;
+        offs[i] = total;
+        total += sizeof(DevPassHeader) + sizeof(DevOp) * passes[i].ops.size();
+        total = (total + 255) & ~size_t(255);
+    }
+    if (total > blob_cap_) {
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        cudaFree(d_blob_);
+        if (h_blob_)
+            cudaFreeHost(h_blob_);
+        blob_cap_ = std::max<size_t>(total * 2, 1 << 16);
+        CUDA_CHECK(cudaMalloc(&d_blob_, blob_cap_));
+        CUDA_CHECK(cudaMallocHost(&h_blob_, blob_cap_));
+    }
+    if (total) {
+        CUDA_CHECK(cudaEventSynchronize(blob_evt_)); // previous upload has left the staging buffer
+        for (size_t i = 0; i < passes.size(); i++) {
+            if (passes[i].is_matk)
+                continue;
+            std::memcpy(h_blob_ + offs[i], &passes[i].hdr, sizeof(DevPassHeader));
+            std::memcpy(h_blob_ + offs[i] + sizeof(DevPassHeader), passes[i].ops.data(),
+                        sizeof(DevOp) * passes[i].ops.size());
+        }
+        CUDA_CHECK(cudaMemcpyAsync(d_blob_, h_blob_, total, cudaMemcpyHostToDevice, stream_));
+        CUDA_CHECK(cudaEventRecord(blob_evt_, stream_));
+    }
+    const uint64_t rank_bits = uint64_t(rank_) << n_local_;
+    for (size_t i = 0; i < passes.size(); i++) {
+        const Pass &ps = passes[i];
+        if (ps.is_matk) {
+            const int k = static_cast<int>(ps.matk.bits.size());
+            for (int b : ps.matk.bits)
+                B2_ABORT_IF(b >= n_local_, "matrix operations on global (rank) qubits are not supported");
+            double2 *d_mat;
+            const size_t bytes = sizeof(double2) * ps.matk.mat.size();
+            CUDA_CHECK(cudaMallocAsync(&d_mat, bytes, stream_));
+            CUDA_CHECK(cudaMemcpyAsync(d_mat, ps.matk.mat.data(), bytes, cudaMemcpyHostToDevice, stream_));
+            launch_matk(dtype_, d_state_, n_eff_, d_mat, ps.matk.bits.data(), k, stream_);
+            CUDA_CHECK(cudaFreeAsync(d_mat, stream_));
+            CUDA_CHECK(cudaStreamSynchronize(stream_)); // the host matrix lives in `passes`
+        } else {
+            launch_tile_pass(dtype_, d_state_, d_blob_ + offs[i], n_eff_, rank_bits, stream_);
+        }
+        sweeps++;
+        launches++;
+    }
+}
+
+// ---- reductions -----------------------------------------------------------------------------------
+void State::finish_reduce(int nv, double *out) const {
+    launch_finalize(d_partials_, kReduceBlocks, nv, d_out_, stream_);
+    reduce_launches += 2;
+    if (comm_)
+        comm_allreduce_sum(comm_, d_out_, nv, stream_);
+    CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(double) * nv, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (int i = 0; i < nv; i++)
+        out[i] = h_out_[i];
+}
+double State::norm2() const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    launch_norm2(dtype_, d_state_, local_length(), d_partials_, stream_);
+    double r;
+    finish_reduce(1, &r);
+    return r;
+}
+void State::inner_product_buf(const void *x, const void *y, double *re, double *im) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    launch_dot(dtype_, x, y, local_length(), d_partials_, stream_);
+    double r[2];
+    finish_reduce(2, r);
+    if (re)
+        *re = r[0];
+    if (im)
+        *im = r[1];
+}
+void State::inner_product(const State &o, double *re, double *im) const {
+    B2_ABORT_IF(o.n_ != n_ || o.dtype_ != dtype_ || o.device_ != device_,
+                "state vectors are not compatible");
+    order_after(stream_, o.stream_);
+    inner_product_buf(d_state_, o.d_state_, re, im);
+}
+double State::expval_pauli(uint64_t x, uint64_t z, cplx ph) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(x >> n_local_, "Pauli X/Y on a global (rank) qubit needs the apply path");
+    // Z factors on rank bits contribute a per-rank constant sign
+    if (__builtin_popcountll((uint64_t(rank_) << n_local_) & z) & 1)
+        ph = -ph;
+    launch_pauli_expval(dtype_, d_state_, local_length(), x, z & (local_length() - 1), ph.real(),
+                        ph.imag(), d_partials_, stream_);
+    double r;
+    finish_reduce(1, &r);
+    return r;
+}
+double State::expval_named(const std::string &name, const std::vector<int64_t> &wires) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    if (name == "Identity")
+        return norm2(); // EVF.hpp:13-28
+    B2_ABORT_IF(wires.size() != 1, "named observables act on exactly one wire");
+    const int t = wires_to_bits(wires, n_)[0];
+    const double s = 0.70710678118654752440;
+    double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (name == "PauliX") { // EVF.hpp:30-58
+        m[2] = 1;
+        m[4] = 1;
+    } else if (name == "PauliY") { // EVF.hpp:60-92
+        m[3] = -1;
+        m[5] = 1;
+    } else if (name == "PauliZ") { // EVF.hpp:94-121
+        m[0] = 1;
+        m[6] = -1;
+    } else if (name == "Hadamard") { // EVF.hpp:123-153
+        m[0] = s;
+        m[2] = s;
+        m[4] = s;
+        m[6] = -s;
+    } else {
+        B2_ABORT("unknown named observable '" + name + "'");
+    }
+    if (t >= n_local_) { // global qubit: only diagonal observables are local
+        B2_ABORT_IF(name != "PauliZ", "non-diagonal observable on a global (rank) qubit");
+        return expval_pauli(0, bit(t), 1.0);
+    }
+    launch_expval_1q(dtype_, d_state_, local_length(), t, m, d_partials_, stream_);
+    double r;
+    finish_reduce(1, &r);
+    return r;
+}
+double State::expval_matrix(const std::vector<int64_t> &wires, const std::vector<cplx> &mat) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    const std::vector<int> bits = wires_to_bits(wires, n_);
+    const size_t k = bits.size();
+    B2_ABORT_IF(k == 0, "matrix observable needs at least one wire");
+    B2_ABORT_IF(mat.size() != (size_t(1) << (2 * k)), "matrix size does not match the number of wires");
+    for (int b : bits)
+        B2_ABORT_IF(b >= n_local_, "matrix observable on a global (rank) qubit is not supported");
+    double r;
+    if (k == 1) { // MK.hpp:283-300
+        double m[8];
+        for (int i = 0; i < 4; i++) {
+            m[2 * i] = mat[i].real();
+            m[2 * i + 1] = mat[i].imag();
+        }
+        launch_expval_1q(dtype_, d_state_, local_length(), bits[0], m, d_partials_, stream_);
+        finish_reduce(1, &r);
+    } else if (k == 2) { // MK.hpp:302-320
+        double2 *d_m = reinterpret_cast<double2 *>(d_out_ + 16); // 16 complex = 32 doubles
+        CUDA_CHECK(cudaMemcpyAsync(d_m, mat.data(), sizeof(double2) * 16, cudaMemcpyHostToDevice, stream_));
+        launch_expval_2q(dtype_, d_state_, local_length(), bits[0], bits[1], d_m, d_partials_, stream_);
+        finish_reduce(1, &r);
+    } else { // MK.hpp:340-345: copy, apply, Re<psi|O psi>
+        void *tmp = acquire_scratch();
+        CUDA_CHECK(cudaMemcpyAsync(tmp, d_state_, alloc_length() * amp_bytes(), cudaMemcpyDeviceToDevice, stream_));
+        double2 *d_mat;
+        CUDA_CHECK(cudaMallocAsync(&d_mat, sizeof(double2) * mat.size(), stream_));
+        CUDA_CHECK(cudaMemcpyAsync(d_mat, mat.data(), sizeof(double2) * mat.size(), cudaMemcpyHostToDevice, stream_));
+        launch_matk(dtype_, tmp, n_eff_, d_mat, bits.data(), static_cast<int>(k), stream_);
+        CUDA_CHECK(cudaFreeAsync(d_mat, stream_));
+        inner_product_buf(d_state_, tmp, &r, nullptr);
+        release_scratch(tmp);
+    }
+    return r;
+}
+double State::expval_csr(const CsrDevice &m) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(world_ > 1, "CSR expectation values are not supported on sharded states");
+    B2_ABORT_IF(m.nrows != local_length(), "CSR matrix dimension does not match the state vector");
+    launch_csr_expval(dtype_, d_state_, m.data, m.ind, m.ptr, m.nrows, m.lanes, d_partials_, stream_);
+    double r;
+    finish_reduce(1, &r);
+    return r;
+}
+void State::axpy(cplx alpha, const State &x) {
+    CUDA_CHECK(cudaSetDevice(device_));
+    order_after(stream_, x.stream_);
+    launch_axpy(dtype_, alpha.real(), alpha.imag(), x.d_state_, d_state_, local_length(), stream_);
+    launches++;
+    order_after(x.stream_, stream_);
+}
+
+// ---- probabilities / sampling -----------------------------------------------------------------------
+void State::probs(const std::vector<int64_t> &wires_in, double *out) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(world_ > 1, "probs on a sharded state: use the per-rank slices");
+    std::vector<int64_t> wires = wires_in;
+    bool all_sorted = wires.empty();
+    if (!wires.empty() && static_cast<int>(wires.size()) == n_) {
+        all_sorted = true;
+        for (int i = 0; i < n_; i++)
+            all_sorted = all_sorted && wires[i] == i;
+    }
+    double *d_p;
+    if (all_sorted) { // MK.hpp:389-408
+        const uint64_t len = local_length();
+        CUDA_CHECK(cudaMallocAsync(&d_p, sizeof(double) * len, stream_));
+        launch_probs_full(dtype_, d_state_, len, d_p, stream_);
+        CUDA_CHECK(cudaMemcpyAsync(out, d_p, sizeof(double) * len, cudaMemcpyDeviceToHost, stream_));
+    } else { // MK.hpp:418-517, result directly in the requested wire order
+        // Output digit j reports wire wires[argsort[argsort[j]]]: the reference's transposition
+        // (MeasuresFunctors.hpp:162-191, MK.hpp:493-509) uses argsort where rank is meant, and
+        // its own literals pin that (src/tests/Test_StateVectorKokkos_Measure.cpp:21-46). For sorted
+        // wires -- all the Python layer allows (lightning_kokkos.py:488-495) -- it is the identity.
+        std::vector<size_t> arg(wires.size());
+        for (size_t i = 0; i < arg.size(); i++)
+            arg[i] = i;
+        std::stable_sort(arg.begin(), arg.end(), [&](size_t a, size_t b) { return wires[a] < wires[b]; });
+        std::vector<int64_t> eff(wires.size());
+        for (size_t j = 0; j < eff.size(); j++)
+            eff[j] = wires[arg[arg[j]]];
+        const std::vector<int> bits = wires_to_bits(eff, n_);
+        const int m = static_cast<int>(bits.size());
+        const uint64_t nb = uint64_t(1) << m;
+        CUDA_CHECK(cudaMallocAsync(&d_p, sizeof(double) * nb, stream_));
+        CUDA_CHECK(cudaMemsetAsync(d_p, 0, sizeof(double) * nb, stream_));
+        launch_probs_marginal(dtype_, d_state_, local_length(), bits.data(), m, d_p, stream_);
+        CUDA_CHECK(cudaMemcpyAsync(out, d_p, sizeof(double) * nb, cudaMemcpyDeviceToHost, stream_));
+    }
+    CUDA_CHECK(cudaFreeAsync(d_p, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    reduce_launches += 1;
+}
+
+void State::generate_samples(size_t shots, uint64_t seed, uint64_t *out) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(world_ > 1, "sampling on a sharded state is not supported yet");
+    if (shots == 0)
+        return;
+    const uint64_t len = local_length();
+    const uint64_t csz = uint64_t(1) << kSampleChunkBits;
+    const uint64_t nchunks = (len + csz - 1) / csz;
+    double *d_chunk;
+    unsigned long long *d_s;
+    CUDA_CHECK(cudaMallocAsync(&d_chunk, sizeof(double) * (nchunks + 1), stream_));
+    CUDA_CHECK(cudaMallocAsync(&d_s, sizeof(unsigned long long) * shots * n_, stream_));
+    launch_chunk_sums(dtype_, d_state_, len, d_chunk, stream_);
+    launch_scan_chunks(d_chunk, nchunks, stream_);
+    launch_sample(dtype_, d_state_, len, d_chunk, nchunks, n_, shots, seed, d_s, stream_);
+    CUDA_CHECK(cudaMemcpyAsync(out, d_s, sizeof(unsigned long long) * shots * n_,
+                               cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaFreeAsync(d_chunk, stream_));
+    CUDA_CHECK(cudaFreeAsync(d_s, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    reduce_launches += 3;
+}
+
+} // namespace b2sv

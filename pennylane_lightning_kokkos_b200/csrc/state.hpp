@@ -1,0 +1,122 @@
+// b2sv: the device-resident state vector and its host-side driver.
+// Counterpart of the reference's StateVectorKokkos<P> (reference simulator/StateVectorKokkos.hpp:109)
+// and of the drivers in MeasuresKokkos<P> (reference simulator/MeasuresKokkos.hpp:14).
+#pragma once
+#include "ir.hpp"
+#include "kernels.cuh"
+#include "schedule.hpp"
+
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace b2sv {
+
+struct Comm; // NCCL communicator wrapper (comm.cpp); nullptr for single-GPU states
+
+// One gate of an op list in the reference's wire format (reference AdjointDiffKokkos.hpp:40-56)
+struct GateOp {
+    std::string name;
+    std::vector<int64_t> wires;
+    bool inverse = false;
+    std::vector<double> params;
+    std::vector<cplx> matrix; // used when `name` is not a named gate
+};
+
+struct CsrDevice {
+    int device = 0;
+    double2 *data = nullptr;
+    uint32_t *ind = nullptr;
+    uint64_t *ptr = nullptr;
+    uint64_t nrows = 0, nnz = 0;
+    int lanes = 1;
+    ~CsrDevice();
+};
+std::shared_ptr<CsrDevice> csr_upload(int device, const cplx *data, const uint64_t *indices,
+                                      const uint64_t *indptr, size_t nnz, size_t nrows);
+
+class State {
+  public:
+    State(int num_qubits, int dtype, int device, int rank = 0, int world = 1,
+          const void *nccl_id = nullptr);
+    ~State();
+    State(const State &) = delete;
+    State &operator=(const State &) = delete;
+
+    // ---- geometry
+    int num_qubits() const { return n_; }       // total wires
+    int num_local() const { return n_local_; }  // index bits held on this GPU
+    int dtype() const { return dtype_; }
+    int device() const { return device_; }
+    int rank() const { return rank_; }
+    int world() const { return world_; }
+    uint64_t local_length() const { return uint64_t(1) << n_local_; }
+    uint64_t alloc_length() const { return uint64_t(1) << n_eff_; }
+    size_t amp_bytes() const { return dtype_ == 1 ? 16 : 8; }
+    void *data() const { return d_state_; }
+    cudaStream_t stream() const { return stream_; }
+    void sync() const;
+
+    // ---- initialisation / copies
+    void reset();
+    void init_zeros();
+    void set_basis_state(uint64_t index);
+    void set_state_vector(const uint64_t *indices, const cplx *values, size_t n);
+    void h2d(const void *host, size_t length);
+    void d2h(void *host, size_t length) const;
+    void copy_from(const State &other);
+    std::unique_ptr<State> clone() const;
+    void swap_buffer(void *&other_buffer); // exchange the device buffer with a scratch buffer
+    void *acquire_scratch() const;         // a buffer of alloc_length() amplitudes
+    void release_scratch(void *p) const;
+
+    // ---- gates
+    void apply_gate(const GateOp &op);
+    void apply_ops(const std::vector<GateOp> &ops, bool adjoint);
+    double apply_generator(const std::string &name, const std::vector<int64_t> &wires);
+    void apply_prims(std::vector<Prim> prims);
+    void lower(const GateOp &op, bool flip_inverse, std::vector<Prim> &out) const;
+    void set_fusion(bool f) { fuse_ = f; }
+    bool fusion() const { return fuse_; }
+
+    // ---- reductions (all return after synchronising; sharded states all-reduce)
+    double norm2() const;
+    void inner_product(const State &other, double *re, double *im) const; // <this|other>
+    void inner_product_buf(const void *x, const void *y, double *re, double *im) const;
+    double expval_named(const std::string &name, const std::vector<int64_t> &wires) const;
+    double expval_matrix(const std::vector<int64_t> &wires, const std::vector<cplx> &m) const;
+    double expval_csr(const CsrDevice &m) const;
+    double expval_pauli(uint64_t x, uint64_t z, cplx ph) const;
+    void axpy(cplx alpha, const State &x);
+
+    // ---- probabilities / sampling
+    void probs(const std::vector<int64_t> &wires, double *out) const;
+    void generate_samples(size_t shots, uint64_t seed, uint64_t *out) const;
+
+    // ---- bookkeeping
+    uint64_t sweeps = 0, launches = 0;
+    mutable uint64_t reduce_launches = 0;
+
+    int tile_bits() const { return B_; }
+
+  private:
+    void finish_reduce(int nv, double *out) const;
+    void upload_and_run(const std::vector<Pass> &passes);
+
+    int n_, n_local_, n_eff_, dtype_, device_;
+    int rank_, world_, gbits_;
+    int B_, R_;
+    bool fuse_ = true;
+    void *d_state_ = nullptr;
+    cudaStream_t stream_ = nullptr;
+    // pass descriptors: pinned staging + device copy
+    unsigned char *h_blob_ = nullptr, *d_blob_ = nullptr;
+    size_t blob_cap_ = 0;
+    cudaEvent_t blob_evt_ = nullptr;
+    // reductions
+    double *d_partials_ = nullptr, *d_out_ = nullptr, *h_out_ = nullptr;
+    mutable std::vector<void *> scratch_;
+    Comm *comm_ = nullptr;
+};
+
+} // namespace b2sv

@@ -1,0 +1,344 @@
+// b2sv: the tile executor -- ONE kernel applies every gate of a fused pass in a single HBM sweep.
+//
+// Replaces the reference's one-gate-per-sweep functor dispatch
+// (reference StateVectorKokkos.hpp:807-824 applyGateFunctor -> GateFunctors.hpp, one
+// Kokkos::parallel_for over 2^(n-k) per gate).
+//
+// Data flow per CTA (one tile of 2^B amplitudes, B = 12 for complex128 -> 64 KiB of shared memory):
+//   HBM --coalesced 16 B/lane loads, 2^low-amplitude contiguous runs--> shared memory (XOR-swizzled)
+//   for each round: every thread gathers 2^R amplitudes whose indices differ only in the round's R
+//     "register bits", applies all ops of the round in registers, scatters back in place
+//   shared memory --> HBM (same addresses: the update is in place)
+// HBM traffic is exactly one read + one write of the state per pass, whatever the number of gates.
+//
+// Shared-memory layout: amplitude i of the tile lives at slot phys(i) = i ^ fold(i) where fold XORs
+// the higher SW-bit groups of i into its low SW bits (SW = log2(128 B / sizeof(amp))). phys is
+// GF(2)-linear, so phys(base | off) = phys(base) ^ phys(off), and any 8 (c128) / 16 (c64) consecutive
+// lanes hit distinct 16 B / 8 B bank groups for every choice of register bits.
+#include "schedule.hpp"
+
+#include <cuda_runtime.h>
+
+namespace b2sv {
+
+template <typename real> struct AmpT;
+template <> struct AmpT<double> {
+    using type = double2;
+};
+template <> struct AmpT<float> {
+    using type = float2;
+};
+
+template <int B, int SW> __device__ __forceinline__ uint32_t phys(uint32_t i) {
+    uint32_t f = 0;
+#pragma unroll
+    for (int s = SW; s < B; s += SW)
+        f ^= (i >> s);
+    return i ^ (f & ((1u << SW) - 1u));
+}
+
+// ---- register-level op bodies -------------------------------------------------------------------
+template <int TS, int NS, typename amp_t, typename real>
+__device__ __forceinline__ void op_general(amp_t (&a)[NS], const real (&m)[8], uint32_t act,
+                                           bool pred) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        if (s & (1 << TS))
+            continue;
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int s1 = s | (1 << TS);
+        if (pred && ((act >> s) & 1u)) {
+            const amp_t v0 = a[s], v1 = a[s1];
+            amp_t r0, r1;
+            r0.x = m[0] * v0.x - m[1] * v0.y + m[2] * v1.x - m[3] * v1.y;
+            r0.y = m[0] * v0.y + m[1] * v0.x + m[2] * v1.y + m[3] * v1.x;
+            r1.x = m[4] * v0.x - m[5] * v0.y + m[6] * v1.x - m[7] * v1.y;
+            r1.y = m[4] * v0.y + m[5] * v0.x + m[6] * v1.y + m[7] * v1.x;
+            a[s] = r0;
+            a[s1] = r1;
+        }
+    }
+}
+template <int TS, int NS, typename amp_t, typename real>
+__device__ __forceinline__ void op_real(amp_t (&a)[NS], const real (&m)[8], uint32_t act,
+                                        bool pred) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        if (s & (1 << TS))
+            continue;
+        const int s1 = s | (1 << TS);
+        if (pred && ((act >> s) & 1u)) {
+            const amp_t v0 = a[s], v1 = a[s1];
+            amp_t r0, r1;
+            r0.x = m[0] * v0.x + m[2] * v1.x;
+            r0.y = m[0] * v0.y + m[2] * v1.y;
+            r1.x = m[4] * v0.x + m[6] * v1.x;
+            r1.y = m[4] * v0.y + m[6] * v1.y;
+            a[s] = r0;
+            a[s1] = r1;
+        }
+    }
+}
+template <int TS, int NS, typename amp_t>
+__device__ __forceinline__ void op_perm(amp_t (&a)[NS], uint32_t act, bool pred) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        if (s & (1 << TS))
+            continue;
+        const int s1 = s | (1 << TS);
+        if (pred && ((act >> s) & 1u)) {
+            const amp_t t = a[s];
+            a[s] = a[s1];
+            a[s1] = t;
+        }
+    }
+}
+template <int NS, typename amp_t, typename real>
+__device__ __forceinline__ void op_diag(amp_t (&a)[NS], const real (&m)[8], uint32_t act,
+                                        uint32_t par, bool odd_base, bool pred) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        if (pred && ((act >> s) & 1u)) {
+            const bool odd = odd_base ^ (((par >> s) & 1u) != 0);
+            const real pr = odd ? m[2] : m[0];
+            const real pi = odd ? m[3] : m[1];
+            const amp_t v = a[s];
+            amp_t r;
+            r.x = pr * v.x - pi * v.y;
+            r.y = pr * v.y + pi * v.x;
+            a[s] = r;
+        }
+    }
+}
+
+template <int R, int NS, typename amp_t, typename real>
+__device__ __forceinline__ void run_op(amp_t (&a)[NS], const DevOp &op, uint64_t tile_base,
+                                       uint32_t base_local) {
+    if ((tile_base & op.gcm) != op.gcv)
+        return; // CTA-uniform: the whole tile fails the control
+    const bool pred = (base_local & op.lcm) == op.lcv;
+    real m[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        m[i] = static_cast<real>(op.m[i]);
+    const uint32_t act = op.slot_act;
+    const int kind = op.kind;
+    if (kind == KIND_DIAG) {
+        const bool odd =
+            ((__popcll(tile_base & op.gpm) + __popc(base_local & op.lpm)) & 1) != 0;
+        op_diag<NS>(a, m, act, op.slot_par, odd, pred);
+        return;
+    }
+    const int ts = op.tslot;
+#define B2_CASE(TS)                                                                             \
+    case TS:                                                                                    \
+        if (kind == KIND_GENERAL)                                                               \
+            op_general<TS, NS>(a, m, act, pred);                                                \
+        else if (kind == KIND_REAL)                                                             \
+            op_real<TS, NS>(a, m, act, pred);                                                   \
+        else                                                                                    \
+            op_perm<TS, NS>(a, act, pred);                                                      \
+        break;
+    switch (ts) {
+        B2_CASE(0)
+        B2_CASE(1)
+        B2_CASE(2)
+        default:
+            if constexpr (R >= 4) {
+                if (ts == 3) {
+                    if (kind == KIND_GENERAL)
+                        op_general<3, NS>(a, m, act, pred);
+                    else if (kind == KIND_REAL)
+                        op_real<3, NS>(a, m, act, pred);
+                    else
+                        op_perm<3, NS>(a, act, pred);
+                }
+            }
+            if constexpr (R >= 5) {
+                if (ts == 4) {
+                    if (kind == KIND_GENERAL)
+                        op_general<4, NS>(a, m, act, pred);
+                    else if (kind == KIND_REAL)
+                        op_real<4, NS>(a, m, act, pred);
+                    else
+                        op_perm<4, NS>(a, act, pred);
+                }
+            }
+            break;
+    }
+#undef B2_CASE
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+template <typename real, int B, int R, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    tile_exec_kernel(typename AmpT<real>::type *__restrict__ state,
+                     const unsigned char *__restrict__ blob, uint64_t rank_bits) {
+    using amp_t = typename AmpT<real>::type;
+    constexpr int SW = (sizeof(amp_t) == 16) ? 3 : 4;
+    constexpr int NS = 1 << R;
+    constexpr int TILE = 1 << B;
+    constexpr int GROUPS = TILE / NS;
+    static_assert(GROUPS % THREADS == 0, "thread count must divide the number of register groups");
+    constexpr int GPT = GROUPS / THREADS;
+    constexpr int EPT = TILE / THREADS; // amplitudes per thread in the load / store phases
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    amp_t *tile = reinterpret_cast<amp_t *>(smem_raw);
+    DevOp *sops = reinterpret_cast<DevOp *>(smem_raw + sizeof(amp_t) * TILE);
+    uint64_t *rowoff = reinterpret_cast<uint64_t *>(sops + kMaxOpsPerPass);
+    __shared__ DevPassHeader hdr;
+
+    const int tid = threadIdx.x;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(blob);
+        uint4 *dst = reinterpret_cast<uint4 *>(&hdr);
+        for (int i = tid; i < static_cast<int>(sizeof(DevPassHeader) / 16); i += THREADS)
+            dst[i] = src[i];
+        const int n_ops = reinterpret_cast<const DevPassHeader *>(blob)->n_ops;
+        const uint4 *osrc = reinterpret_cast<const uint4 *>(blob + sizeof(DevPassHeader));
+        uint4 *odst = reinterpret_cast<uint4 *>(sops);
+        for (int i = tid; i < n_ops * static_cast<int>(sizeof(DevOp) / 16); i += THREADS)
+            odst[i] = osrc[i];
+    }
+    __syncthreads();
+
+    const int low = hdr.low_bits;
+    // tile id -> index with the tile bits cleared (deposit into the non-tile positions)
+    uint64_t tb = blockIdx.x;
+#pragma unroll 1
+    for (int j = 0; j < B; j++) {
+        const int p = hdr.tile_bits[j];
+        tb = ((tb >> p) << (p + 1)) | (tb & ((uint64_t(1) << p) - 1));
+    }
+    for (int r = tid; r < (1 << (B - low)); r += THREADS) {
+        uint64_t off = 0;
+        for (int j = low; j < B; j++)
+            if ((r >> (j - low)) & 1)
+                off |= uint64_t(1) << hdr.tile_bits[j];
+        rowoff[r] = off;
+    }
+    __syncthreads();
+
+    // ---- HBM -> shared
+    const uint32_t lowmask = (1u << low) - 1u;
+    {
+        amp_t v[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const uint32_t i = e * THREADS + tid;
+            v[e] = state[tb | rowoff[i >> low] | (i & lowmask)];
+        }
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const uint32_t i = e * THREADS + tid;
+            tile[phys<B, SW>(i)] = v[e];
+        }
+    }
+    __syncthreads();
+
+    const uint64_t tbr = tb | rank_bits;
+    const int n_rounds = hdr.n_rounds;
+#pragma unroll 1
+    for (int rd = 0; rd < n_rounds; rd++) {
+        uint32_t poff[R];
+        int rbit[R];
+#pragma unroll
+        for (int s = 0; s < R; s++) {
+            rbit[s] = hdr.round_regbits[rd][s];
+            poff[s] = phys<B, SW>(1u << rbit[s]);
+        }
+        const int o_begin = hdr.round_begin[rd], o_end = hdr.round_begin[rd + 1];
+#pragma unroll 1
+        for (int gi = 0; gi < GPT; gi++) {
+            uint32_t base = gi * THREADS + tid;
+#pragma unroll
+            for (int s = 0; s < R; s++)
+                base = ((base >> rbit[s]) << (rbit[s] + 1)) | (base & ((1u << rbit[s]) - 1u));
+            const uint32_t pb = phys<B, SW>(base);
+            amp_t a[NS];
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                uint32_t x = pb;
+#pragma unroll
+                for (int k = 0; k < R; k++)
+                    if (s & (1 << k))
+                        x ^= poff[k];
+                a[s] = tile[x];
+            }
+#pragma unroll 1
+            for (int oi = o_begin; oi < o_end; oi++)
+                run_op<R, NS, amp_t, real>(a, sops[oi], tbr, base);
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                uint32_t x = pb;
+#pragma unroll
+                for (int k = 0; k < R; k++)
+                    if (s & (1 << k))
+                        x ^= poff[k];
+                tile[x] = a[s];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- shared -> HBM
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+        const uint32_t i = e * THREADS + tid;
+        state[tb | rowoff[i >> low] | (i & lowmask)] = tile[phys<B, SW>(i)];
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+namespace {
+constexpr int kMinLow = 4;
+template <typename real, int B> constexpr size_t tile_smem_bytes() {
+    return sizeof(typename AmpT<real>::type) * (size_t(1) << B) + sizeof(DevOp) * kMaxOpsPerPass +
+           sizeof(uint64_t) * (size_t(1) << (B - kMinLow));
+}
+} // namespace
+
+// Tile geometry per dtype: complex128 -> 2^12 amps (64 KiB), complex64 -> 2^13 amps (64 KiB).
+void tile_config(int dtype, int *B, int *R) {
+    if (dtype == 1) {
+        *B = 12;
+        *R = 4;
+    } else {
+        *B = 13;
+        *R = 4;
+    }
+}
+
+void launch_tile_pass(int dtype, void *state, const unsigned char *dev_blob, int n_eff,
+                      uint64_t rank_bits, cudaStream_t stream) {
+    if (dtype == 1) {
+        constexpr int B = 12;
+        auto kern = tile_exec_kernel<double, B, 4, 256, 2>;
+        constexpr size_t smem = tile_smem_bytes<double, B>();
+        static bool configured = false;
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem)));
+            configured = true;
+        }
+        const unsigned grid = 1u << (n_eff - B);
+        kern<<<grid, 256, smem, stream>>>(static_cast<double2 *>(state), dev_blob, rank_bits);
+    } else {
+        constexpr int B = 13;
+        auto kern = tile_exec_kernel<float, B, 4, 512, 2>;
+        constexpr size_t smem = tile_smem_bytes<float, B>();
+        static bool configured = false;
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem)));
+            configured = true;
+        }
+        const unsigned grid = 1u << (n_eff - B);
+        kern<<<grid, 512, smem, stream>>>(static_cast<float2 *>(state), dev_blob, rank_bits);
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace b2sv

@@ -1,0 +1,516 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) vs the reference oracle
+(oracle/_ref = unmodified reference headers over the Kokkos stand-in) on identical inputs.
+
+Tolerances are BASELINE.json's: 1e-12 relative (complex128) / 1e-5 (complex64) on amplitudes,
+expectation values and gradients (relative to the infinity norm of the reference result).
+"""
+import numpy as np
+import pytest
+
+from cases import (GATES, GENERATORS, gate_cases, layered_circuit, random_circuit,
+                   random_pauli_hamiltonian, random_state, sel_circuit)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.complex128: 1e-12, np.complex64: 1e-5}
+DTYPES = [np.complex128, np.complex64]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pennylane_lightning_kokkos_b200 import lightning_kokkos_qubit_ops as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref as r
+    if not r.available():
+        pytest.skip("oracle/_ref/libref_oracle.so not built")
+    return r
+
+
+def sv_class(ops, dtype):
+    return ops.LightningKokkos_C128 if dtype == np.complex128 else ops.LightningKokkos_C64
+
+
+def suffix(dtype):
+    return "C128" if dtype == np.complex128 else "C64"
+
+
+def to_host(sv, n, dtype):
+    out = np.zeros(1 << n, dtype=dtype)
+    sv.DeviceToHost(out)
+    return out
+
+
+def rel_err(a, b):
+    scale = max(np.max(np.abs(b)), 1e-300)
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / scale
+
+
+def apply_gpu(sv, op):
+    name, wires, inv, params = op
+    getattr(sv, name)(wires, inv, params)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 13, 15])
+def test_init_and_basis_state(ops, ref, dtype, n):
+    sv = sv_class(ops, dtype)(n)
+    r = ref.RefStateVector(n, dtype)
+    assert sv.numQubits() == n and sv.dataLength() == 1 << n
+    np.testing.assert_array_equal(to_host(sv, n, dtype), r.d2h())
+    idx = (1 << n) - 1 if n < 3 else 5
+    sv.setBasisState(idx)
+    r.set_basis_state(idx)
+    np.testing.assert_array_equal(to_host(sv, n, dtype), r.d2h())
+    sv.resetKokkos()
+    r.reset()
+    np.testing.assert_array_equal(to_host(sv, n, dtype), r.d2h())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_set_state_vector_and_ctor_from_array(ops, ref, dtype):
+    n = 4
+    idx = [1, 7, 12]
+    vals = np.array([0.5 + 0.5j, -0.5j, 0.5], dtype=np.complex128)
+    sv = sv_class(ops, dtype)(n)
+    sv.setStateVector(idx, vals)
+    r = ref.RefStateVector(n, dtype)
+    r.set_state_vector(idx, vals)
+    np.testing.assert_array_equal(to_host(sv, n, dtype), r.d2h())
+    st = random_state(n, 3, dtype)
+    sv2 = sv_class(ops, dtype)(st)
+    np.testing.assert_array_equal(to_host(sv2, n, dtype), st)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [4, 6, 14])
+def test_every_gate_every_pattern(ops, ref, dtype, n):
+    """Each named gate x wire pattern x inverse on a random state (reference GateFunctors.hpp)."""
+    st = random_state(n, 11 + n, dtype)
+    sv = sv_class(ops, dtype)(n)
+    r = ref.RefStateVector(n, dtype)
+    worst = 0.0
+    for case in gate_cases(n, seed=n, per_gate=4 if n < 14 else 3):
+        sv.HostToDevice(st)
+        r.h2d(st)
+        apply_gpu(sv, case)
+        r.apply(*case)
+        e = rel_err(to_host(sv, n, dtype), r.d2h())
+        worst = max(worst, e)
+        assert e < TOL[dtype], f"{case}: rel err {e:.3e}"
+    assert worst < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_matrix_ops_1q_2q_and_sorted_kq(ops, ref, dtype):
+    """Matrix path. For >=3 wires the reference is only right for ascending wires,
+    so those are compared with the reference on ascending wires and with NumPy otherwise."""
+    n = 6
+    rng = np.random.default_rng(5)
+    st = random_state(n, 21, dtype)
+    sv = sv_class(ops, dtype)(n)
+    r = ref.RefStateVector(n, dtype)
+    for wires in ([3], [0], [5], [1, 4], [4, 1], [0, 5], [0, 1, 2], [1, 3, 4], [2, 3, 4, 5]):
+        k = len(wires)
+        m = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+        q, _ = np.linalg.qr(m)
+        for inv in (False, True):
+            sv.HostToDevice(st)
+            r.h2d(st)
+            sv.apply("QubitUnitary", wires, inv, [], q.ravel())
+            r.apply_matrix(q, wires, inv)
+            assert rel_err(to_host(sv, n, dtype), r.d2h()) < TOL[dtype], (wires, inv)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_matrix_unsorted_wires_vs_numpy(ops, dtype):
+    from oracle import np_oracle
+    n = 5
+    rng = np.random.default_rng(6)
+    st = random_state(n, 22, dtype)
+    sv = sv_class(ops, dtype)(n)
+    for wires in ([2, 1, 0], [4, 0, 2], [3, 1, 4, 0]):
+        k = len(wires)
+        m = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+        q, _ = np.linalg.qr(m)
+        sv.HostToDevice(st)
+        sv.apply("QubitUnitary", wires, False, [], q.ravel())
+        want = np_oracle.apply_matrix(st.astype(np.complex128), n, q, wires)
+        assert rel_err(to_host(sv, n, dtype), want) < (1e-12 if dtype == np.complex128 else 2e-6)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,depth,seed", [(3, 40, 1), (8, 200, 2), (13, 150, 3), (16, 300, 4)])
+def test_random_circuits_fused_and_unfused(ops, ref, dtype, n, depth, seed):
+    """The fusion scheduler (one list call) and the per-gate path must both equal the reference."""
+    circ = random_circuit(n, depth, seed)
+    st = random_state(n, seed, dtype)
+    r = ref.RefStateVector(n, dtype)
+    r.h2d(st)
+    r.apply_ops(circ)
+    want = r.d2h()
+    tol = TOL[dtype] * (10 if dtype == np.complex64 else 1)
+    sv = sv_class(ops, dtype)(n)
+    sv.HostToDevice(st)
+    sv.apply([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ],
+             [c[3] for c in circ])
+    assert rel_err(to_host(sv, n, dtype), want) < tol
+    fused_sweeps = sv.stats()["sweeps"]
+    sv.set_fusion(False)
+    sv.reset_stats()
+    sv.HostToDevice(st)
+    sv.apply([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ],
+             [c[3] for c in circ])
+    assert rel_err(to_host(sv, n, dtype), want) < tol
+    assert sv.stats()["sweeps"] >= fused_sweeps
+    # per-gate method calls
+    sv.HostToDevice(st)
+    for c in circ:
+        apply_gpu(sv, c)
+    assert rel_err(to_host(sv, n, dtype), want) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_config1_sel_circuit_and_expvals(ops, ref, dtype):
+    """BASELINE config 1 (20q StronglyEntanglingLayers x4, <Z_i>) at 16 qubits vs the reference."""
+    n = 16
+    circ = sel_circuit(n, 4)
+    r = ref.RefStateVector(n, dtype)
+    r.apply_ops(circ)
+    sv = sv_class(ops, dtype)(n)
+    sv.apply([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ],
+             [c[3] for c in circ])
+    assert rel_err(to_host(sv, n, dtype), r.d2h()) < TOL[dtype] * (10 if dtype == np.complex64 else 1)
+    ez = [sv.ExpectationValue("PauliZ", [w], [], np.zeros(0)) for w in range(n)]
+    rz = [r.expval_named("PauliZ", [w]) for w in range(n)]
+    assert rel_err(ez, rz) < (1e-12 if dtype == np.complex128 else 1e-5)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_generators_vs_reference(ops, ref, dtype):
+    n = 6
+    rng = np.random.default_rng(9)
+    st = random_state(n, 31, dtype)
+    sv = sv_class(ops, dtype)(n)
+    r = ref.RefStateVector(n, dtype)
+    for name in GENERATORS:
+        nw = GATES[name][0] or 3
+        for _ in range(3):
+            wires = [int(x) for x in rng.choice(n, size=nw, replace=False)]
+            sv.HostToDevice(st)
+            r.h2d(st)
+            s1 = sv.applyGenerator(name, wires, False, [])
+            s2 = r.apply_generator(name, wires, False)
+            assert s1 == s2, name
+            assert rel_err(to_host(sv, n, dtype), r.d2h()) < TOL[dtype], (name, wires)
+    with pytest.raises(ops.PLException, match="Generator does not exist"):
+        sv.applyGenerator("Hadamard", [0], False, [])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [3, 7, 14])
+def test_expvals(ops, ref, dtype, n):
+    tol = 1e-12 if dtype == np.complex128 else 1e-5
+    st = random_state(n, 41, dtype)
+    sv = sv_class(ops, dtype)(st)
+    r = ref.RefStateVector(n, dtype)
+    r.h2d(st)
+    for name in ("Identity", "PauliX", "PauliY", "PauliZ", "Hadamard"):
+        for w in sorted({0, n // 2, n - 1}):
+            got = sv.ExpectationValue(name, [w], [], np.zeros(0))
+            want = r.expval_named(name, [w])
+            assert abs(got - want) < tol, (name, w)
+    rng = np.random.default_rng(3)
+    for wires in ([0], [n - 1], [0, n - 1], [n - 1, 0], [1, 0, 2]):
+        if max(wires) >= n or len(set(wires)) != len(wires):
+            continue
+        k = len(wires)
+        a = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+        h = a + a.conj().T
+        got = sv.ExpectationValue(wires, h.ravel())
+        if k >= 3 and wires != sorted(wires):
+            continue
+        want = r.expval_matrix(h, wires)
+        assert abs(got - want) < tol * max(1, abs(want)), wires
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_reference_test_literals(ops, dtype):
+    """The reference's own expval / var literals (Test_StateVectorKokkos_Expval.cpp:396-491,
+    Test_StateVectorKokkos_Var.cpp:124-144) through the observable classes."""
+    S = suffix(dtype)
+    init = np.array([0.0, 0.1j, 0.1 + 0.1j, 0.1 + 0.2j, 0.2 + 0.2j, 0.3 + 0.3j, 0.3 + 0.4j, 0.4 + 0.5j],
+                    dtype=dtype)
+    sv = sv_class(ops, dtype)(init)
+    X0 = getattr(ops, f"NamedObsKokkos_{S}")("PauliX", [0])
+    Z1 = getattr(ops, f"NamedObsKokkos_{S}")("PauliZ", [1])
+    ham = getattr(ops, f"HamiltonianKokkos_{S}")([0.3, 0.5], [X0, Z1])
+    ten = getattr(ops, f"TensorProdObsKokkos_{S}")([X0, Z1])
+    assert sv.expval(ham) == pytest.approx(-0.086, rel=1e-5)
+    assert sv.expval(ten) == pytest.approx(-0.36, rel=1e-5)
+    assert sv.var(ham) == pytest.approx(0.224604, rel=1e-5)
+    # sparse literal (Expval.cpp:417-446)
+    index_ptr = [0, 2, 4, 6, 8, 10, 12, 14, 16]
+    indices = [0, 3, 1, 2, 1, 2, 0, 3, 4, 7, 5, 6, 5, 6, 4, 7]
+    p = 3.1415
+    values = [p, -1j * p, p, 1j * p, -1j * p, p, 1j * p, p, p, -1j * p, p, 1j * p, -1j * p, p, 1j * p, p]
+    assert sv.ExpectationValue(np.array(values), indices, index_ptr) == pytest.approx(3.1415, rel=1e-6)
+    sp = getattr(ops, f"SparseHamiltonianKokkos_{S}")(values, indices, index_ptr, [0, 1, 2])
+    assert sv.expval(sp) == pytest.approx(3.1415, rel=1e-6)
+    # 3-qubit Hermitian literal (Expval.cpp:394-415): Re = 1.263
+    blk = np.array([[0.5, 0.2 + 0.5j], [0.2 - 0.5j, 0.3]])
+    rowa = [0.5, 0.2 + 0.5j] + [0.2 - 0.5j, 0.3] * 3
+    rowb = [0.2 - 0.5j, 0.3] * 4
+    mat = np.array([rowa, rowb] * 4, dtype=np.complex128)
+    herm = getattr(ops, f"HermitianObsKokkos_{S}")(mat.ravel(), [0, 1, 2])
+    assert sv.expval(herm) == pytest.approx(1.263, rel=1e-5)
+    assert sv.ExpectationValue([0, 1, 2], mat.ravel()) == pytest.approx(1.263, rel=1e-5)
+    del blk
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_observables_vs_reference(ops, ref, dtype):
+    n = 8
+    S = suffix(dtype)
+    prec = 1 if dtype == np.complex128 else 0
+    tol = 1e-12 if dtype == np.complex128 else 2e-5
+    st = random_state(n, 51, dtype)
+    sv = sv_class(ops, dtype)(st)
+    r = ref.RefStateVector(n, dtype)
+    r.h2d(st)
+    terms = random_pauli_hamiltonian(n, 12, seed=4)
+
+    def build(mod_named, mod_tensor, mod_ham):
+        obs = []
+        for _, word in terms:
+            fac = [mod_named(nm, [w]) for nm, w in word]
+            obs.append(fac[0] if len(fac) == 1 else mod_tensor(fac))
+        return mod_ham([c for c, _ in terms], obs), obs
+
+    gh, gobs = build(getattr(ops, f"NamedObsKokkos_{S}"), getattr(ops, f"TensorProdObsKokkos_{S}"),
+                     getattr(ops, f"HamiltonianKokkos_{S}"))
+    rh, robs = build(lambda nm, w: ref.RefObs.named(nm, w, prec),
+                     lambda f: ref.RefObs.tensor(f, prec),
+                     lambda c, o: ref.RefObs.hamiltonian(c, o, prec))
+    assert abs(sv.expval(gh) - r.expval_obs(rh)) < tol * 10
+    assert abs(sv.var(gh) - r.var_obs(rh)) < tol * 10
+    for g, o in zip(gobs, robs):
+        assert abs(sv.expval(g) - r.expval_obs(o)) < tol
+        assert repr(g) == o.name()
+    assert repr(gh).split("'observables'")[1] == rh.name().split("'observables'")[1]
+    # Hadamard / Hermitian terms take the generic (copy + apply + axpy) path
+    Hd = getattr(ops, f"NamedObsKokkos_{S}")("Hadamard", [2])
+    a = np.array([[1.0, 0.5 - 0.2j], [0.5 + 0.2j, -0.3]])
+    He = getattr(ops, f"HermitianObsKokkos_{S}")(a.ravel(), [5])
+    gh2 = getattr(ops, f"HamiltonianKokkos_{S}")([0.7, -0.4, 0.2], [Hd, He, gobs[0]])
+    rh2 = ref.RefObs.hamiltonian([0.7, -0.4, 0.2], [ref.RefObs.named("Hadamard", [2], prec),
+                                                    ref.RefObs.hermitian(a, [5], prec), robs[0]], prec)
+    assert abs(sv.expval(gh2) - r.expval_obs(rh2)) < tol * 10
+    assert abs(sv.var(gh2) - r.var_obs(rh2)) < tol * 10
+    with pytest.raises(ops.PLException, match="disjoint"):
+        getattr(ops, f"TensorProdObsKokkos_{S}")([Hd, getattr(ops, f"NamedObsKokkos_{S}")("PauliX", [2])])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_sparse_hamiltonian_vs_reference(ops, ref, dtype):
+    import scipy.sparse as sp
+    n = 10
+    S = suffix(dtype)
+    prec = 1 if dtype == np.complex128 else 0
+    rng = np.random.default_rng(8)
+    dim = 1 << n
+    a = sp.random(dim, dim, density=0.01, random_state=7, format="csr", dtype=np.float64)
+    b = sp.random(dim, dim, density=0.01, random_state=8, format="csr", dtype=np.float64)
+    h = (a + 1j * b)
+    h = (h + h.conj().T).tocsr()
+    h.sort_indices()
+    st = random_state(n, 61, dtype)
+    sv = sv_class(ops, dtype)(st)
+    r = ref.RefStateVector(n, dtype)
+    r.h2d(st)
+    tol = 1e-11 if dtype == np.complex128 else 1e-4
+    got = sv.ExpectationValue(h.data, h.indices, h.indptr)
+    want = r.expval_csr(h.data, h.indices, h.indptr)
+    assert abs(got - want) < tol * max(1.0, abs(want))
+    gs = getattr(ops, f"SparseHamiltonianKokkos_{S}")(h.data, h.indices, h.indptr, list(range(n)))
+    rs = ref.RefObs.sparse(h.data, h.indices, h.indptr, list(range(n)), prec)
+    assert abs(sv.expval(gs) - r.expval_obs(rs)) < tol * max(1.0, abs(want))
+    assert abs(sv.var(gs) - r.var_obs(rs)) < 50 * tol * max(1.0, abs(r.var_obs(rs)))
+    del rng
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [3, 9, 14])
+def test_probs(ops, ref, dtype, n):
+    tol = 1e-12 if dtype == np.complex128 else 1e-6
+    st = random_state(n, 71, dtype)
+    sv = sv_class(ops, dtype)(st)
+    r = ref.RefStateVector(n, dtype)
+    r.h2d(st)
+    np.testing.assert_allclose(sv.probs([]), r.probs(), atol=tol)
+    np.testing.assert_allclose(sv.probs(list(range(n))), r.probs(), atol=tol)
+    rng = np.random.default_rng(2)
+    pats = [[0], [n - 1], [0, 1], [1, 0], [2, 0], [0, 1, 2], [2, 1, 0], [1, 2, 0]]
+    pats += [[int(x) for x in rng.choice(n, size=min(n, k), replace=False)] for k in (2, 3, 5, 13)]
+    for wires in pats:
+        if max(wires) >= n:
+            continue
+        got = sv.probs(wires)
+        want = r.probs(wires)
+        np.testing.assert_allclose(got, want, atol=tol, err_msg=str(wires))
+
+
+def test_probs_reference_literals(ops):
+    """Test_StateVectorKokkos_Measure.cpp:21-46 (computed with default.qubit)."""
+    sv = ops.LightningKokkos_C128(3)
+    ph = 0.7
+    for q in range(3):
+        sv.RX([q], False, [ph])
+        sv.RY([q], False, [ph])
+        ph -= 0.2
+    lit = {
+        (0, 1, 2): [0.67078706, 0.03062806, 0.0870997, 0.00397696, 0.17564072, 0.00801973, 0.02280642, 0.00104134],
+        (2, 0): [0.75788676, 0.19844714, 0.03460502, 0.00906107],
+        (1, 2): [0.84642778, 0.0386478, 0.10990612, 0.0050183],
+        (1,): [0.88507558, 0.11492442],
+    }
+    for wires, want in lit.items():
+        np.testing.assert_allclose(sv.probs(list(wires)), want, atol=1e-7)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_sampling_distribution(ops, dtype):
+    """Reference test: 100 000 shots histogram within 0.05 of the exact probabilities
+    (Test_StateVectorKokkos_Param.cpp:1325-1394). The RNG stream itself is unpinned."""
+    n = 4
+    sv = sv_class(ops, dtype)(n)
+    ph = 0.7
+    for q in range(n):
+        sv.RX([q], False, [ph])
+        sv.RY([q], False, [ph])
+        ph -= 0.2
+    p = sv.probs([])
+    shots = 100000
+    s = sv.GenerateSamples(n, shots)
+    assert s.shape == (shots, n) and s.dtype == np.uint64
+    idx = (s * (1 << np.arange(n - 1, -1, -1, dtype=np.uint64))).sum(axis=1)
+    hist = np.bincount(idx.astype(np.int64), minlength=1 << n) / shots
+    assert np.max(np.abs(hist - p)) < 0.01
+    s2 = sv.GenerateSamples(n, shots)  # same seed every call, like the reference (MK.hpp:551)
+    np.testing.assert_array_equal(s, s2)
+    # a basis state samples itself; big state exercises the two-level search
+    big = sv_class(ops, dtype)(15)
+    big.setBasisState(12345)
+    sb = big.GenerateSamples(15, 64)
+    want = [(12345 >> (14 - j)) & 1 for j in range(15)]
+    assert (sb == np.array(want, dtype=np.uint64)).all()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_adjoint_reference_literals(ops, dtype):
+    """Test_AdjointDiffKokkos.cpp:213-259: decomposed Rot, <X x X x X>."""
+    S = suffix(dtype)
+    p = [-np.pi / 7, np.pi / 5, 2 * np.pi / 3]
+    names = ["RZ", "RY", "RZ", "CNOT", "CNOT", "RZ", "RY", "RZ"]
+    params = [[p[0]], [p[1]], [p[2]], [], [], [p[0]], [p[1]], [p[2]]]
+    wires = [[0], [0], [0], [0, 1], [1, 2], [1], [1], [1]]
+    sv = sv_class(ops, dtype)(3)
+    sv.apply(names, wires, [False] * 8, params)
+    N = getattr(ops, f"NamedObsKokkos_{S}")
+    obs = getattr(ops, f"TensorProdObsKokkos_{S}")([N("PauliX", [i]) for i in range(3)])
+    adj = getattr(ops, f"AdjointJacobianKokkos_{S}")()
+    ol = adj.create_ops_list(names, [np.array(x) for x in params], wires, [False] * 8,
+                             [np.zeros(0)] * 8)
+    jac = adj.adjoint_jacobian(sv, [obs], ol, list(range(6)))
+    want = [0.0, -0.674214427, 0.275139672, 0.275139672, -0.0129093062, 0.323846156]
+    np.testing.assert_allclose(jac[0], want, atol=1e-7 if dtype == np.complex128 else 1e-5)
+    with pytest.raises(ops.PLException, match="No trainable parameters"):
+        adj.adjoint_jacobian(sv, [obs], ol, [])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,layers", [(4, 2), (13, 2)])
+def test_adjoint_vs_reference(ops, ref, dtype, n, layers):
+    """All parametrised gate families, permuted wires, Hamiltonian + tensor + named observables,
+    a trainable subset -- against the reference's AdjointJacobianKokkos."""
+    S = suffix(dtype)
+    prec = 1 if dtype == np.complex128 else 0
+    rng = np.random.default_rng(77)
+    par_gates = [g for g, (nw, npar) in GATES.items() if npar == 1]
+    circ = []
+    for _ in range(layers):
+        for g in par_gates:
+            nw = GATES[g][0] or 3
+            if nw > n:
+                continue
+            wires = [int(x) for x in rng.choice(n, size=nw, replace=False)]
+            circ.append((g, wires, bool(rng.integers(2)), [float(rng.uniform(-1, 1))]))
+            if rng.integers(2):
+                a, b = [int(x) for x in rng.choice(n, size=2, replace=False)]
+                circ.append(("CNOT", [a, b], False, []))
+    names, wires = [c[0] for c in circ], [c[1] for c in circ]
+    invs, params = [c[2] for c in circ], [c[3] for c in circ]
+    n_par = sum(1 for c in circ if c[3])
+    tp = sorted(int(x) for x in rng.choice(n_par, size=max(1, (2 * n_par) // 3), replace=False))
+
+    terms = random_pauli_hamiltonian(n, 6, seed=12)
+    N, T = getattr(ops, f"NamedObsKokkos_{S}"), getattr(ops, f"TensorProdObsKokkos_{S}")
+    H = getattr(ops, f"HamiltonianKokkos_{S}")
+    gobs, robs = [], []
+    for _, word in terms:
+        f = [N(nm, [w]) for nm, w in word]
+        rf = [ref.RefObs.named(nm, [w], prec) for nm, w in word]
+        gobs.append(f[0] if len(f) == 1 else T(f))
+        robs.append(rf[0] if len(rf) == 1 else ref.RefObs.tensor(rf, prec))
+    coeffs = [c for c, _ in terms]
+    g_all = [H(coeffs, gobs), gobs[0], N("Hadamard", [0])]
+    r_all = [ref.RefObs.hamiltonian(coeffs, robs, prec), robs[0], ref.RefObs.named("Hadamard", [0], prec)]
+
+    sv = sv_class(ops, dtype)(n)
+    sv.apply(names, wires, invs, params)
+    r = ref.RefStateVector(n, dtype)
+    r.apply_ops(circ)
+    adj = getattr(ops, f"AdjointJacobianKokkos_{S}")()
+    ol = adj.create_ops_list(names, [np.array(x) for x in params], wires, invs,
+                             [np.zeros(0)] * len(names))
+    jac = adj.adjoint_jacobian(sv, g_all, ol, tp)
+    want = r.adjoint_jacobian(r_all, circ, tp)
+    assert jac.shape == want.shape == (3, len(tp))
+    tol = 1e-12 if dtype == np.complex128 else 2e-5
+    assert rel_err(jac, want) < tol
+
+
+def test_config2_layer_properties_at_scale(ops):
+    """BASELINE config 2 shape at 26 qubits (1 GiB state): norm preserved, U^dagger U = identity,
+    sampled amplitudes equal the per-gate (unfused) path."""
+    n = 26
+    circ = layered_circuit(n, 1, seed=42)
+    names, wires = [c[0] for c in circ], [c[1] for c in circ]
+    invs, params = [c[2] for c in circ], [c[3] for c in circ]
+    sv = ops.LightningKokkos_C128(n)
+    for w in range(n):
+        sv.Hadamard([w], False, [])
+    sv.reset_stats()
+    sv.apply(names, wires, invs, params)
+    fused = sv.stats()["sweeps"]
+    assert fused <= 8, f"fusion regressed: {fused} sweeps for one layer"
+    assert abs(sv.ExpectationValue("Identity", [0], [], np.zeros(0)) - 1.0) < 1e-12
+    probe = ops.LightningKokkos_C128(n)
+    for w in range(n):
+        probe.Hadamard([w], False, [])
+    probe.set_fusion(False)
+    probe.apply(names, wires, invs, params)
+    ol = ops.OpsStructKokkos_C128(names, params, wires, invs)
+    a = np.zeros(1 << n, dtype=np.complex128)
+    b = np.zeros(1 << n, dtype=np.complex128)
+    sv.DeviceToHost(a)
+    probe.DeviceToHost(b)
+    idx = np.random.default_rng(0).integers(0, 1 << n, size=4096)
+    assert np.max(np.abs(a[idx] - b[idx])) < 1e-12 * np.max(np.abs(b))
+    sv.apply_ops(ol, adjoint=True)  # undo the layer
+    sv.DeviceToHost(a)
+    assert np.max(np.abs(a - 2.0 ** (-n / 2))) < 1e-12
