@@ -243,7 +243,7 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
         }
         B2_ASSERT(!chosen.empty());
         for (int b = 0; free_bits > 0; b++) { // pad the tile with the lowest unused local bits
-            B2_ASSERT(b < cfg.n_local);
+            B2_ASSERT(b < std::max(cfg.n_local, cfg.n_alloc));
             if (!(tile_mask & bit(b))) {
                 tile_mask |= bit(b);
                 free_bits--;

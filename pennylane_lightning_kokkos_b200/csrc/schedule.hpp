@@ -56,6 +56,7 @@ struct SchedConfig {
     int R = 4;         // register bits
     int low = 5;       // contiguous low bits forced into every tile
     int n_local = 0;   // bits >= n_local cannot be targets (rank bits when sharded)
+    int n_alloc = 0;   // index bits of the allocation (>= B; small states are zero-padded)
     bool fuse = true;  // false: one pass per primitive group (reference schedule)
 };
 
