@@ -182,6 +182,8 @@ DevOp make_devop(const Prim &p, const uint8_t *tile_bits, int B, const uint8_t *
         if (__builtin_popcount(s & rpm) & 1)
             o.slot_par |= 1u << s;
     }
+    if (p.cmask == 0)
+        o.kind |= OPF_UNCOND;
     return o;
 }
 
@@ -258,10 +260,62 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                     ps.hdr.tile_bits[j++] = static_cast<uint8_t>(b);
             B2_ASSERT(j == B);
         }
-        // ---- rounds
+        // ---- rounds, with permutation primitives folded into the address map at round boundaries
+        uint32_t Mcol[kMaxTileBits]; // storage index (before the swizzle) of logical basis vector e_j
+        for (int j = 0; j < B; j++)
+            Mcol[j] = 1u << j;
+        int n_cx = 0;
+        auto tile_pos = [&](int b) {
+            int j = 0;
+            while (ps.hdr.tile_bits[j] != b)
+                j++;
+            return j;
+        };
+        // 0 = not absorbable, 1 = CNOT inside the tile, 2 = X toggled by CTA-uniform bits
+        auto perm_class = [&](const Prim &p) {
+            if (!cfg.free_perms || p.type != Prim::C1Q || p.tag >= 0 || classify(p) != KIND_PERM)
+                return 0;
+            const uint64_t in_tile = p.cmask & tile_mask;
+            if (in_tile == 0)
+                return n_cx < kMaxCx ? 2 : 0;
+            if (in_tile == p.cmask && popc(p.cmask) == 1 && p.cval == p.cmask)
+                return 1;
+            return 0;
+        };
+        auto absorb = [&](const Prim &p, int cls, int round_idx) {
+            const int jt = tile_pos(p.target);
+            if (cls == 1) {
+                const int jc = tile_pos(ctz(p.cmask));
+                Mcol[jc] ^= Mcol[jt];
+            } else {
+                DevCx &c = ps.hdr.cx[n_cx++];
+                c.gcm = p.cmask;
+                c.gcv = p.cval;
+                c.vec = static_cast<uint16_t>(phys_slot(Mcol[jt], B, cfg.SW));
+                c.round = static_cast<uint16_t>(round_idx);
+            }
+            ps.n_absorbed++;
+        };
         std::vector<int> remaining = chosen;
         int n_rounds = 0;
-        while (!remaining.empty()) {
+        while (true) {
+            { // boundary: absorb every permutation that commutes back to here
+                Blocker lb;
+                std::vector<int> rest;
+                for (int i : remaining) {
+                    const Prim &p = prims[i];
+                    const int cls = lb.blocked(p) ? 0 : perm_class(p);
+                    if (cls) {
+                        absorb(p, cls, n_rounds);
+                    } else {
+                        lb.skip(p);
+                        rest.push_back(i);
+                    }
+                }
+                remaining.swap(rest);
+            }
+            if (remaining.empty())
+                break;
             B2_ABORT_IF(n_rounds >= kMaxRounds, "internal: too many rounds in a pass");
             uint32_t reg_mask = 0; // over tile-local positions
             int reg_free = R;
@@ -271,9 +325,7 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                 const Prim &p = prims[i];
                 bool fits = !rb.blocked(p);
                 if (fits && p.type == Prim::C1Q) {
-                    int j = 0;
-                    while (ps.hdr.tile_bits[j] != p.target)
-                        j++;
+                    const int j = tile_pos(p.target);
                     if (!(reg_mask & (1u << j))) {
                         if (reg_free > 0) {
                             reg_mask |= 1u << j;
@@ -290,6 +342,7 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                     later.push_back(i);
                 }
             }
+            B2_ASSERT(!now.empty());
             for (int j = B - 1; reg_free > 0; j--) { // pad with the highest unused tile bits
                 B2_ASSERT(j >= 0);
                 if (!(reg_mask & (1u << j))) {
@@ -299,10 +352,17 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
             }
             uint8_t *rbits = ps.hdr.round_regbits[n_rounds];
             {
-                int s = 0;
-                for (int j = 0; j < B; j++)
-                    if (reg_mask & (1u << j))
+                int s = 0, k = 0;
+                for (int j = 0; j < B; j++) {
+                    const uint32_t col = phys_slot(Mcol[j], B, cfg.SW);
+                    if (reg_mask & (1u << j)) {
+                        ps.hdr.round_poff[n_rounds][s] = static_cast<uint16_t>(col);
                         rbits[s++] = static_cast<uint8_t>(j);
+                    } else {
+                        ps.hdr.round_col[n_rounds][k++] = ((1u << j) << 16) | col;
+                    }
+                }
+                B2_ASSERT(k <= kMaxFreeBits);
             }
             ps.hdr.round_begin[n_rounds] = static_cast<uint16_t>(ps.ops.size());
             for (int i : now) {
@@ -312,6 +372,9 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
             n_rounds++;
             remaining.swap(later);
         }
+        for (int j = 0; j < B; j++)
+            ps.hdr.final_col[j] = static_cast<uint16_t>(phys_slot(Mcol[j], B, cfg.SW));
+        ps.hdr.n_cx = n_cx;
         ps.hdr.round_begin[n_rounds] = static_cast<uint16_t>(ps.ops.size());
         ps.hdr.n_rounds = n_rounds;
         ps.hdr.n_ops = static_cast<int32_t>(ps.ops.size());

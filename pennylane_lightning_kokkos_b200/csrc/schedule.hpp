@@ -5,6 +5,13 @@
 // chosen bits. Every C1Q in the pass has its target among the tile bits; controls and DIAG masks may
 // touch any bit (bits outside the tile are CTA-uniform predicates). Inside a pass each thread keeps
 // 2^R amplitudes in registers; a round fixes which R tile bits are register-resident.
+//
+// Permutation gates are FREE inside a pass: the tile in shared memory carries a GF(2)-affine
+// address map  slot(j) = phys(M j ^ o)  from the logical tile-local index j to the storage slot.
+// A CNOT whose control and target are both tile bits multiplies M by an elementary matrix, an X
+// (uncontrolled, or controlled only by bits outside the tile = CTA-uniform) toggles o; neither
+// moves data. The scheduler folds them into the per-round address columns below; SWAP, CSWAP's
+// and the CNOT conjugations of the Ising / excitation gates (gates.cpp) all vanish this way.
 #pragma once
 #include "ir.hpp"
 
@@ -14,34 +21,53 @@ constexpr int kMaxRounds = 24;
 constexpr int kMaxOpsPerPass = 80;
 constexpr int kMaxTileBits = 16;
 constexpr int kMaxRegBits = 5;
+constexpr int kMaxFreeBits = 12; // tile bits that are not register bits (= log2 threads)
+constexpr int kMaxCx = 24;       // conditional address toggles per pass
 
 enum OpKind : uint8_t { KIND_GENERAL = 0, KIND_REAL = 1, KIND_PERM = 2, KIND_DIAG = 3 };
+// flag bits stored in DevOp::kind above the OpKind
+enum : uint8_t { OPF_UNCOND = 0x10, OPF_KIND_MASK = 0x0f }; // UNCOND: no control of any sort
 
 // Device-side op record (read from shared memory by every thread; 16-byte aligned).
 struct alignas(16) DevOp {
     double m[8];        // C1Q: m00,m01,m10,m11 as (re,im); DIAG: p0,p1 as (re,im)
     uint64_t gcm, gcv;  // control over bits outside the tile (CTA-uniform, tested on tile_base)
     uint64_t gpm;       // DIAG parity over bits outside the tile
-    uint32_t lcm, lcv;  // control over tile-local, non-register bits (per thread)
-    uint32_t lpm;       // DIAG parity over tile-local, non-register bits
+    uint32_t lcm, lcv;  // control over tile-local, non-register LOGICAL bits (per thread)
+    uint32_t lpm;       // DIAG parity over tile-local, non-register logical bits
     uint32_t slot_act;  // bit s: register slot s satisfies the register part of the control
     uint32_t slot_par;  // DIAG: parity contribution of register slot s
-    uint8_t kind;       // OpKind
+    uint8_t kind;       // OpKind | OPF_* flags
     uint8_t tslot;      // C1Q: which register bit (0..R-1) is the target
     int16_t jac;        // adjoint: Jacobian accumulator slot fed by this op, -1 = none
 };
 static_assert(sizeof(DevOp) == 112, "DevOp layout");
 
+struct DevCx { // address toggle: from round `round` on, slot ^= vec when (tile_base & gcm) == gcv
+    uint64_t gcm, gcv;
+    uint16_t vec;   // phys(M e_t) at the time the X was absorbed
+    uint16_t round; // first round (or n_rounds = the store phase) that sees it
+    uint32_t pad_;
+};
+
 struct alignas(16) DevPassHeader {
     int32_t n_ops;
     int32_t n_rounds;
     int32_t low_bits;                 // number of contiguous low bits in the tile
-    int32_t reserved;
+    int32_t n_cx;
     uint8_t tile_bits[kMaxTileBits];  // ascending bit positions; tile_bits[j]=j for j<low_bits
-    uint8_t round_regbits[kMaxRounds][8]; // tile-local positions held in registers, ascending
+    uint8_t round_regbits[kMaxRounds][8]; // logical tile-local positions held in registers, ascending
     uint16_t round_begin[kMaxRounds + 1]; // op index ranges per round
     uint16_t pad_[3];
+    // storage offset phys(M e_r) of register bit s in round rd
+    uint16_t round_poff[kMaxRounds][8];
+    // thread-id bit k <-> k-th non-register logical bit f_k: (1 << f_k) << 16 | phys(M e_{f_k})
+    uint32_t round_col[kMaxRounds][kMaxFreeBits];
+    // store phase: phys(M_final e_j) per logical tile-local bit j
+    uint16_t final_col[kMaxTileBits];
+    DevCx cx[kMaxCx];
 };
+static_assert(sizeof(DevPassHeader) % 16 == 0, "header must be copyable in 16-byte words");
 
 struct Pass {
     bool is_matk = false;
@@ -49,16 +75,28 @@ struct Pass {
     DevPassHeader hdr{};    // otherwise
     std::vector<DevOp> ops;
     std::vector<int> tags;  // per op: Prim::tag
+    int n_absorbed = 0;     // permutation primitives folded into the address map
 };
 
 struct SchedConfig {
     int B = 12;        // tile bits
     int R = 4;         // register bits
+    int SW = 3;        // log2(amplitudes per 128 B): the shared-memory swizzle width
     int low = 5;       // contiguous low bits forced into every tile
     int n_local = 0;   // bits >= n_local cannot be targets (rank bits when sharded)
     int n_alloc = 0;   // index bits of the allocation (>= B; small states are zero-padded)
     bool fuse = true;  // false: one pass per primitive group (reference schedule)
+    bool free_perms = true; // fold CNOT / X into the address map
 };
+
+// Shared-memory swizzle (same function as tile_kernel.cu phys<B,SW>): XOR-folds every higher
+// SW-bit group of the index into its low SW bits. GF(2)-linear.
+inline uint32_t phys_slot(uint32_t i, int B, int SW) {
+    uint32_t f = 0;
+    for (int s = SW; s < B; s += SW)
+        f ^= (i >> s);
+    return i ^ (f & ((1u << SW) - 1u));
+}
 
 // Pre-pass: merge runs of uncontrolled single-bit primitives on the same bit into one 2x2.
 std::vector<Prim> fuse_single_qubit(const std::vector<Prim> &prims);

@@ -276,6 +276,7 @@ void State::apply_prims(std::vector<Prim> prims) {
     cfg.B = B_;
     cfg.R = R_;
     cfg.low = 5;
+    cfg.SW = dtype_ == 1 ? 3 : 4;
     cfg.n_local = n_local_;
     cfg.n_alloc = n_eff_;
     upload_and_run(build_schedule(prims, cfg));

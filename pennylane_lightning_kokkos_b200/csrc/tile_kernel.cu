@@ -112,62 +112,111 @@ __device__ __forceinline__ void op_diag(amp_t (&a)[NS], const real (&m)[8], uint
     }
 }
 
+// ---- fast paths: no control of any kind, so no predicate and full instruction-level parallelism
+template <int TS, int NS, typename amp_t, typename real>
+__device__ __forceinline__ void fast_general(amp_t (&a)[NS], const real (&m)[8]) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        if (s & (1 << TS))
+            continue;
+        const int s1 = s | (1 << TS);
+        const amp_t v0 = a[s], v1 = a[s1];
+        amp_t r0, r1;
+        r0.x = m[0] * v0.x - m[1] * v0.y + m[2] * v1.x - m[3] * v1.y;
+        r0.y = m[0] * v0.y + m[1] * v0.x + m[2] * v1.y + m[3] * v1.x;
+        r1.x = m[4] * v0.x - m[5] * v0.y + m[6] * v1.x - m[7] * v1.y;
+        r1.y = m[4] * v0.y + m[5] * v0.x + m[6] * v1.y + m[7] * v1.x;
+        a[s] = r0;
+        a[s1] = r1;
+    }
+}
+template <int TS, int NS, typename amp_t, typename real>
+__device__ __forceinline__ void fast_real(amp_t (&a)[NS], const real (&m)[8]) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        if (s & (1 << TS))
+            continue;
+        const int s1 = s | (1 << TS);
+        const amp_t v0 = a[s], v1 = a[s1];
+        amp_t r0, r1;
+        r0.x = m[0] * v0.x + m[2] * v1.x;
+        r0.y = m[0] * v0.y + m[2] * v1.y;
+        r1.x = m[4] * v0.x + m[6] * v1.x;
+        r1.y = m[4] * v0.y + m[6] * v1.y;
+        a[s] = r0;
+        a[s1] = r1;
+    }
+}
+
 template <int R, int NS, typename amp_t, typename real>
 __device__ __forceinline__ void run_op(amp_t (&a)[NS], const DevOp &op, uint64_t tile_base,
                                        uint32_t base_local) {
+    real m[8];
+    {
+        const double2 *mp = reinterpret_cast<const double2 *>(op.m);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const double2 t = mp[i];
+            m[2 * i] = static_cast<real>(t.x);
+            m[2 * i + 1] = static_cast<real>(t.y);
+        }
+    }
+    const int kind = op.kind & OPF_KIND_MASK;
+    const int ts = op.tslot;
+    if ((op.kind & OPF_UNCOND) && kind <= KIND_REAL) {
+        // code = kind * 8 + ts; one flat switch keeps the hot bodies contiguous
+        switch (kind * 8 + ts) {
+#define B2_FAST(TS)                                                                             \
+    case TS:                                                                                    \
+        if constexpr (TS < R)                                                                   \
+            fast_general<TS, NS>(a, m);                                                         \
+        break;                                                                                  \
+    case 8 + TS:                                                                                \
+        if constexpr (TS < R)                                                                   \
+            fast_real<TS, NS>(a, m);                                                            \
+        break;
+            B2_FAST(0)
+            B2_FAST(1)
+            B2_FAST(2)
+            B2_FAST(3)
+            B2_FAST(4)
+#undef B2_FAST
+        default:
+            break;
+        }
+        return;
+    }
     if ((tile_base & op.gcm) != op.gcv)
         return; // CTA-uniform: the whole tile fails the control
     const bool pred = (base_local & op.lcm) == op.lcv;
-    real m[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-        m[i] = static_cast<real>(op.m[i]);
     const uint32_t act = op.slot_act;
-    const int kind = op.kind;
     if (kind == KIND_DIAG) {
         const bool odd =
             ((__popcll(tile_base & op.gpm) + __popc(base_local & op.lpm)) & 1) != 0;
         op_diag<NS>(a, m, act, op.slot_par, odd, pred);
         return;
     }
-    const int ts = op.tslot;
+    switch (ts) {
 #define B2_CASE(TS)                                                                             \
     case TS:                                                                                    \
-        if (kind == KIND_GENERAL)                                                               \
-            op_general<TS, NS>(a, m, act, pred);                                                \
-        else if (kind == KIND_REAL)                                                             \
-            op_real<TS, NS>(a, m, act, pred);                                                   \
-        else                                                                                    \
-            op_perm<TS, NS>(a, act, pred);                                                      \
+        if constexpr (TS < R) {                                                                 \
+            if (kind == KIND_GENERAL)                                                           \
+                op_general<TS, NS>(a, m, act, pred);                                            \
+            else if (kind == KIND_REAL)                                                         \
+                op_real<TS, NS>(a, m, act, pred);                                               \
+            else                                                                                \
+                op_perm<TS, NS>(a, act, pred);                                                  \
+        }                                                                                       \
         break;
-    switch (ts) {
         B2_CASE(0)
         B2_CASE(1)
         B2_CASE(2)
-        default:
-            if constexpr (R >= 4) {
-                if (ts == 3) {
-                    if (kind == KIND_GENERAL)
-                        op_general<3, NS>(a, m, act, pred);
-                    else if (kind == KIND_REAL)
-                        op_real<3, NS>(a, m, act, pred);
-                    else
-                        op_perm<3, NS>(a, act, pred);
-                }
-            }
-            if constexpr (R >= 5) {
-                if (ts == 4) {
-                    if (kind == KIND_GENERAL)
-                        op_general<4, NS>(a, m, act, pred);
-                    else if (kind == KIND_REAL)
-                        op_real<4, NS>(a, m, act, pred);
-                    else
-                        op_perm<4, NS>(a, act, pred);
-                }
-            }
-            break;
-    }
+        B2_CASE(3)
+        B2_CASE(4)
 #undef B2_CASE
+    default:
+        break;
+    }
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------
@@ -179,16 +228,17 @@ __global__ void __launch_bounds__(THREADS, MINB)
     constexpr int SW = (sizeof(amp_t) == 16) ? 3 : 4;
     constexpr int NS = 1 << R;
     constexpr int TILE = 1 << B;
-    constexpr int GROUPS = TILE / NS;
-    static_assert(GROUPS % THREADS == 0, "thread count must divide the number of register groups");
-    constexpr int GPT = GROUPS / THREADS;
-    constexpr int EPT = TILE / THREADS; // amplitudes per thread in the load / store phases
+    constexpr int NF = B - R; // non-register tile bits = thread-id bits
+    static_assert((1 << NF) == THREADS, "one register group per thread");
+    static_assert(NF <= kMaxFreeBits, "too many thread-id bits");
+    constexpr int EPT = TILE / THREADS; // amplitudes per thread in the load / store phases (= NS)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     amp_t *tile = reinterpret_cast<amp_t *>(smem_raw);
     DevOp *sops = reinterpret_cast<DevOp *>(smem_raw + sizeof(amp_t) * TILE);
     uint64_t *rowoff = reinterpret_cast<uint64_t *>(sops + kMaxOpsPerPass);
     __shared__ DevPassHeader hdr;
+    __shared__ uint32_t xoff[kMaxRounds + 1];
 
     const int tid = threadIdx.x;
     {
@@ -219,9 +269,18 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 off |= uint64_t(1) << hdr.tile_bits[j];
         rowoff[r] = off;
     }
+    const uint64_t tbr = tb | rank_bits;
+    const int n_rounds = hdr.n_rounds;
+    if (tid <= n_rounds) { // CTA-uniform address toggles visible from round `tid` on
+        uint32_t x = 0;
+        for (int k = 0; k < hdr.n_cx; k++)
+            if (hdr.cx[k].round <= tid && (tbr & hdr.cx[k].gcm) == hdr.cx[k].gcv)
+                x ^= hdr.cx[k].vec;
+        xoff[tid] = x;
+    }
     __syncthreads();
 
-    // ---- HBM -> shared
+    // ---- HBM -> shared (identity address map)
     const uint32_t lowmask = (1u << low) - 1u;
     {
         amp_t v[EPT];
@@ -238,56 +297,66 @@ __global__ void __launch_bounds__(THREADS, MINB)
     }
     __syncthreads();
 
-    const uint64_t tbr = tb | rank_bits;
-    const int n_rounds = hdr.n_rounds;
 #pragma unroll 1
     for (int rd = 0; rd < n_rounds; rd++) {
+        // this thread's register group: logical base index (high half) and storage slot (low half)
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < NF; k++)
+            acc ^= (0u - ((static_cast<uint32_t>(tid) >> k) & 1u)) & hdr.round_col[rd][k];
+        const uint32_t base = acc >> 16;
+        const uint32_t pb = (acc & 0xffffu) ^ xoff[rd];
         uint32_t poff[R];
-        int rbit[R];
 #pragma unroll
-        for (int s = 0; s < R; s++) {
-            rbit[s] = hdr.round_regbits[rd][s];
-            poff[s] = phys<B, SW>(1u << rbit[s]);
-        }
+        for (int s = 0; s < R; s++)
+            poff[s] = hdr.round_poff[rd][s];
         const int o_begin = hdr.round_begin[rd], o_end = hdr.round_begin[rd + 1];
+        amp_t a[NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            uint32_t x = pb;
+#pragma unroll
+            for (int k = 0; k < R; k++)
+                if (s & (1 << k))
+                    x ^= poff[k];
+            a[s] = tile[x];
+        }
 #pragma unroll 1
-        for (int gi = 0; gi < GPT; gi++) {
-            uint32_t base = gi * THREADS + tid;
+        for (int oi = o_begin; oi < o_end; oi++)
+            run_op<R, NS, amp_t, real>(a, sops[oi], tbr, base);
 #pragma unroll
-            for (int s = 0; s < R; s++)
-                base = ((base >> rbit[s]) << (rbit[s] + 1)) | (base & ((1u << rbit[s]) - 1u));
-            const uint32_t pb = phys<B, SW>(base);
-            amp_t a[NS];
+        for (int s = 0; s < NS; s++) {
+            uint32_t x = pb;
 #pragma unroll
-            for (int s = 0; s < NS; s++) {
-                uint32_t x = pb;
-#pragma unroll
-                for (int k = 0; k < R; k++)
-                    if (s & (1 << k))
-                        x ^= poff[k];
-                a[s] = tile[x];
-            }
-#pragma unroll 1
-            for (int oi = o_begin; oi < o_end; oi++)
-                run_op<R, NS, amp_t, real>(a, sops[oi], tbr, base);
-#pragma unroll
-            for (int s = 0; s < NS; s++) {
-                uint32_t x = pb;
-#pragma unroll
-                for (int k = 0; k < R; k++)
-                    if (s & (1 << k))
-                        x ^= poff[k];
-                tile[x] = a[s];
-            }
+            for (int k = 0; k < R; k++)
+                if (s & (1 << k))
+                    x ^= poff[k];
+            tile[x] = a[s];
         }
         __syncthreads();
     }
 
-    // ---- shared -> HBM
+    // ---- shared -> HBM through the final address map
+    {
+        constexpr int NT = NF; // log2(THREADS)
+        uint32_t sl = xoff[n_rounds];
 #pragma unroll
-    for (int e = 0; e < EPT; e++) {
-        const uint32_t i = e * THREADS + tid;
-        state[tb | rowoff[i >> low] | (i & lowmask)] = tile[phys<B, SW>(i)];
+        for (int k = 0; k < NT; k++)
+            sl ^= (0u - ((static_cast<uint32_t>(tid) >> k) & 1u)) & hdr.final_col[k];
+        uint32_t ecol[B - NT];
+#pragma unroll
+        for (int k = 0; k < B - NT; k++)
+            ecol[k] = hdr.final_col[NT + k];
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const uint32_t i = e * THREADS + tid;
+            uint32_t x = sl;
+#pragma unroll
+            for (int k = 0; k < B - NT; k++)
+                if (e & (1 << k))
+                    x ^= ecol[k];
+            state[tb | rowoff[i >> low] | (i & lowmask)] = tile[x];
+        }
     }
 }
 

@@ -346,7 +346,8 @@ def test_sparse_hamiltonian_vs_reference(ops, ref, dtype):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", [3, 9, 14])
 def test_probs(ops, ref, dtype, n):
-    tol = 1e-12 if dtype == np.complex128 else 1e-6
+    # c64: the reference accumulates marginals in float with atomics; north_star tolerance is 1e-5
+    tol = 1e-12 if dtype == np.complex128 else 5e-6
     st = random_state(n, 71, dtype)
     sv = sv_class(ops, dtype)(st)
     r = ref.RefStateVector(n, dtype)
