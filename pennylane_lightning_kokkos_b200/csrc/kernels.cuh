@@ -13,7 +13,8 @@ constexpr int kMaxReduceVals = 8;
 
 // ---- tile executor (tile_kernel.cu)
 void tile_config(int dtype, int *B, int *R);
-void launch_tile_pass(int dtype, void *state, const unsigned char *dev_blob, int n_eff,
+struct PassParams;
+void launch_tile_pass(int dtype, void *state, const PassParams &pass, int n_eff,
                       uint64_t rank_bits, cudaStream_t stream);
 
 // ---- state management

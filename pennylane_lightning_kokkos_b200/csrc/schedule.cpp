@@ -217,13 +217,18 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
         int free_bits = B - low;
         Blocker blk;
         std::vector<int> chosen;
+        int heavy = 0; // arithmetic ops taken so far (permutations are free: address-map updates)
         for (int i = first; i < N && static_cast<int>(chosen.size()) < kMaxOpsPerPass; i++) {
             if (done[i])
                 continue;
             const Prim &p = prims[i];
             if (p.type == Prim::MATK)
                 break; // full barrier
-            bool fits = !blk.blocked(p);
+            const bool light = cfg.free_perms && p.type == Prim::C1Q && p.tag < 0 &&
+                               classify(p) == KIND_PERM;
+            // balance: a pass is HBM-bound up to ~max_heavy gates; beyond that the FP64 pipe is the
+            // limit, so later passes (which stream the state anyway) should take the rest
+            bool fits = !blk.blocked(p) && (light || heavy < cfg.max_heavy);
             if (fits && p.type == Prim::C1Q) {
                 B2_ABORT_IF(p.target >= cfg.n_local,
                             "internal: non-diagonal target on a global (rank) qubit");
@@ -239,6 +244,7 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
             if (fits) {
                 chosen.push_back(i);
                 done[i] = 1;
+                heavy += light ? 0 : 1;
             } else {
                 blk.skip(p);
             }
@@ -323,7 +329,8 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
             std::vector<int> now, later;
             for (int i : remaining) {
                 const Prim &p = prims[i];
-                bool fits = !rb.blocked(p);
+                // an absorbable permutation waits for the next round boundary, where it is free
+                bool fits = !rb.blocked(p) && perm_class(p) == 0;
                 if (fits && p.type == Prim::C1Q) {
                     const int j = tile_pos(p.target);
                     if (!(reg_mask & (1u << j))) {
@@ -343,26 +350,66 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                 }
             }
             B2_ASSERT(!now.empty());
+            // register slots in order of first use by the round's ops, then the padding bits
+            std::vector<int> slot_bits;
+            for (int i : now) {
+                const Prim &p = prims[i];
+                if (p.type != Prim::C1Q)
+                    continue;
+                const int j = tile_pos(p.target);
+                if (std::find(slot_bits.begin(), slot_bits.end(), j) == slot_bits.end())
+                    slot_bits.push_back(j);
+            }
             for (int j = B - 1; reg_free > 0; j--) { // pad with the highest unused tile bits
                 B2_ASSERT(j >= 0);
                 if (!(reg_mask & (1u << j))) {
                     reg_mask |= 1u << j;
                     reg_free--;
+                    slot_bits.push_back(j);
                 }
             }
+            B2_ASSERT(static_cast<int>(slot_bits.size()) == R);
+            // dense round: every op is an uncontrolled, untagged 2x2 on its own register slot
+            bool dense = static_cast<int>(now.size()) <= R;
+            for (size_t k = 0; dense && k < now.size(); k++) {
+                const Prim &p = prims[now[k]];
+                dense = p.type == Prim::C1Q && p.cmask == 0 && p.tag < 0 &&
+                        tile_pos(p.target) == slot_bits[k];
+            }
+            ps.hdr.round_kind[n_rounds] = dense ? static_cast<uint8_t>(now.size()) : 0;
             uint8_t *rbits = ps.hdr.round_regbits[n_rounds];
             {
-                int s = 0, k = 0;
-                for (int j = 0; j < B; j++) {
-                    const uint32_t col = phys_slot(Mcol[j], B, cfg.SW);
-                    if (reg_mask & (1u << j)) {
-                        ps.hdr.round_poff[n_rounds][s] = static_cast<uint16_t>(col);
-                        rbits[s++] = static_cast<uint8_t>(j);
+                std::vector<uint32_t> free_cols; // ((1 << j) << 16) | storage column of free bit j
+                for (int s = 0; s < R; s++) {
+                    rbits[s] = static_cast<uint8_t>(slot_bits[s]);
+                    ps.hdr.round_poff[n_rounds][s] =
+                        static_cast<uint16_t>(phys_slot(Mcol[slot_bits[s]], B, cfg.SW));
+                }
+                for (int j = 0; j < B; j++)
+                    if (!(reg_mask & (1u << j)))
+                        free_cols.push_back(((1u << j) << 16) | phys_slot(Mcol[j], B, cfg.SW));
+                B2_ASSERT(free_cols.size() <= static_cast<size_t>(kMaxFreeBits));
+                // Bank-conflict-free gathers: the lanes that share one shared-memory wavefront
+                // (8 x 16 B or 16 x 8 B) differ in the lowest SW thread-id bits, so give those
+                // bits free tile bits whose storage columns are linearly independent (over GF(2))
+                // in their low SW bits = they enumerate all 2^SW bank groups.
+                const uint32_t bank_mask = (1u << cfg.SW) - 1u;
+                std::vector<uint32_t> order, rest, basis;
+                for (uint32_t fc : free_cols) {
+                    uint32_t v = fc & bank_mask;
+                    for (uint32_t b : basis)
+                        v = std::min(v, v ^ b);
+                    if (v != 0 && static_cast<int>(order.size()) < cfg.SW) {
+                        basis.push_back(v);
+                        std::sort(basis.rbegin(), basis.rend());
+                        order.push_back(fc);
                     } else {
-                        ps.hdr.round_col[n_rounds][k++] = ((1u << j) << 16) | col;
+                        rest.push_back(fc);
                     }
                 }
-                B2_ASSERT(k <= kMaxFreeBits);
+                order.insert(order.end(), rest.begin(), rest.end());
+                for (size_t k = 0; k < order.size(); k++)
+                    ps.hdr.round_col[n_rounds][k] = order[k];
             }
             ps.hdr.round_begin[n_rounds] = static_cast<uint16_t>(ps.ops.size());
             for (int i : now) {

@@ -56,7 +56,10 @@ struct alignas(16) DevPassHeader {
     int32_t low_bits;                 // number of contiguous low bits in the tile
     int32_t n_cx;
     uint8_t tile_bits[kMaxTileBits];  // ascending bit positions; tile_bits[j]=j for j<low_bits
-    uint8_t round_regbits[kMaxRounds][8]; // logical tile-local positions held in registers, ascending
+    uint8_t round_regbits[kMaxRounds][8]; // logical tile-local positions held in registers, by slot
+    // 0: generic round (op interpreter); g >= 1: "dense" round = exactly g uncontrolled 2x2 gates,
+    // the k-th one on register slot k (straight-line code, no per-op dispatch)
+    uint8_t round_kind[kMaxRounds];
     uint16_t round_begin[kMaxRounds + 1]; // op index ranges per round
     uint16_t pad_[3];
     // storage offset phys(M e_r) of register bit s in round rd
@@ -68,6 +71,13 @@ struct alignas(16) DevPassHeader {
     DevCx cx[kMaxCx];
 };
 static_assert(sizeof(DevPassHeader) % 16 == 0, "header must be copyable in 16-byte words");
+
+// What one tile-kernel launch receives as its __grid_constant__ parameter.
+struct PassParams {
+    DevPassHeader hdr;
+    DevOp ops[kMaxOpsPerPass];
+};
+static_assert(sizeof(PassParams) <= 32000, "kernel parameter space is 32764 bytes");
 
 struct Pass {
     bool is_matk = false;
@@ -87,6 +97,7 @@ struct SchedConfig {
     int n_alloc = 0;   // index bits of the allocation (>= B; small states are zero-padded)
     bool fuse = true;  // false: one pass per primitive group (reference schedule)
     bool free_perms = true; // fold CNOT / X into the address map
+    int max_heavy = 8;      // arithmetic ops per pass before the pass turns FP64-bound
 };
 
 // Shared-memory swizzle (same function as tile_kernel.cu phys<B,SW>): XOR-folds every higher

@@ -3,6 +3,7 @@
 #include "comm.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace b2sv {
@@ -16,6 +17,15 @@ void order_after(cudaStream_t waiter, cudaStream_t signaler) {
     CUDA_CHECK(cudaEventRecord(ev, signaler));
     CUDA_CHECK(cudaStreamWaitEvent(waiter, ev, 0));
     CUDA_CHECK(cudaEventDestroy(ev));
+}
+// contiguous low index bits kept in every tile (2^low amplitudes per HBM run); B2SV_TILE_LOW overrides
+int tile_low_bits() {
+    static int low = 0;
+    if (!low) {
+        const char *e = getenv("B2SV_TILE_LOW");
+        low = e ? std::max(4, std::min(6, atoi(e))) : 5;
+    }
+    return low;
 }
 int log2_exact(int x) {
     int g = 0;
@@ -84,7 +94,6 @@ State::State(int num_qubits, int dtype, int device, int rank, int world, const v
     e = cudaMalloc(&d_state_, alloc_length() * amp_bytes());
     B2_ABORT_IF(e != cudaSuccess, std::string("cannot allocate the state vector: ") +
                                       cudaGetErrorString(e));
-    CUDA_CHECK(cudaEventCreateWithFlags(&blob_evt_, cudaEventDisableTiming));
     CUDA_CHECK(cudaMalloc(&d_partials_, sizeof(double) * kReduceBlocks * kMaxReduceVals));
     CUDA_CHECK(cudaMalloc(&d_out_, sizeof(double) * 64));
     CUDA_CHECK(cudaMallocHost(&h_out_, sizeof(double) * 64));
@@ -102,15 +111,10 @@ State::~State() {
     for (void *p : scratch_)
         cudaFree(p);
     cudaFree(d_state_);
-    cudaFree(d_blob_);
-    if (h_blob_)
-        cudaFreeHost(h_blob_);
     cudaFree(d_partials_);
     cudaFree(d_out_);
     if (h_out_)
         cudaFreeHost(h_out_);
-    if (blob_evt_)
-        cudaEventDestroy(blob_evt_);
     if (stream_)
         cudaStreamDestroy(stream_);
 }
@@ -275,7 +279,9 @@ void State::apply_prims(std::vector<Prim> prims) {
     SchedConfig cfg;
     cfg.B = B_;
     cfg.R = R_;
-    cfg.low = 5;
+    cfg.low = tile_low_bits();
+    if (const char *e = getenv("B2SV_MAX_HEAVY"))
+        cfg.max_heavy = std::max(1, atoi(e));
     cfg.SW = dtype_ == 1 ? 3 : 4;
     cfg.n_local = n_local_;
     cfg.n_alloc = n_eff_;
@@ -283,37 +289,11 @@ void State::apply_prims(std::vector<Prim> prims) {
 }
 
 void State::upload_and_run(const std::vector<Pass> &passes) {
-    size_t total = 0;
-    std::vector<size_t> offs(passes.size(), 0);
-    for (size_t i = 0; i < passes.size(); i++) {
-        if (passes[i].is_matk)
-            continue;
-        offs[i] = total;
-        total += sizeof(DevPassHeader) + sizeof(DevOp) * passes[i].ops.size();
-        total = (total + 255) & ~size_t(255);
-    }
-    if (total > blob_cap_) {
-        CUDA_CHECK(cudaStreamSynchronize(stream_));
-        cudaFree(d_blob_);
-        if (h_blob_)
-            cudaFreeHost(h_blob_);
-        blob_cap_ = std::max<size_t>(total * 2, 1 << 16);
-        CUDA_CHECK(cudaMalloc(&d_blob_, blob_cap_));
-        CUDA_CHECK(cudaMallocHost(&h_blob_, blob_cap_));
-    }
-    if (total) {
-        CUDA_CHECK(cudaEventSynchronize(blob_evt_)); // previous upload has left the staging buffer
-        for (size_t i = 0; i < passes.size(); i++) {
-            if (passes[i].is_matk)
-                continue;
-            std::memcpy(h_blob_ + offs[i], &passes[i].hdr, sizeof(DevPassHeader));
-            std::memcpy(h_blob_ + offs[i] + sizeof(DevPassHeader), passes[i].ops.data(),
-                        sizeof(DevOp) * passes[i].ops.size());
-        }
-        CUDA_CHECK(cudaMemcpyAsync(d_blob_, h_blob_, total, cudaMemcpyHostToDevice, stream_));
-        CUDA_CHECK(cudaEventRecord(blob_evt_, stream_));
-    }
+    // Pass descriptors travel as kernel parameters (copied by the runtime at launch), so there is
+    // no staging buffer, no H2D copy and nothing to keep alive after the launch call returns.
     const uint64_t rank_bits = uint64_t(rank_) << n_local_;
+    auto params = std::make_unique<PassParams>();
+    last_upload_bytes_ = 0;
     for (size_t i = 0; i < passes.size(); i++) {
         const Pass &ps = passes[i];
         if (ps.is_matk) {
@@ -327,8 +307,13 @@ void State::upload_and_run(const std::vector<Pass> &passes) {
             launch_matk(dtype_, d_state_, n_eff_, d_mat, ps.matk.bits.data(), k, stream_);
             CUDA_CHECK(cudaFreeAsync(d_mat, stream_));
             CUDA_CHECK(cudaStreamSynchronize(stream_)); // the host matrix lives in `passes`
+            last_upload_bytes_ += bytes;
         } else {
-            launch_tile_pass(dtype_, d_state_, d_blob_ + offs[i], n_eff_, rank_bits, stream_);
+            B2_ASSERT(ps.ops.size() <= static_cast<size_t>(kMaxOpsPerPass));
+            params->hdr = ps.hdr;
+            std::memcpy(params->ops, ps.ops.data(), sizeof(DevOp) * ps.ops.size());
+            launch_tile_pass(dtype_, d_state_, *params, n_eff_, rank_bits, stream_);
+            last_upload_bytes_ += sizeof(DevPassHeader) + sizeof(DevOp) * ps.ops.size();
         }
         sweeps++;
         launches++;

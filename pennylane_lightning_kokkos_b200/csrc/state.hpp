@@ -98,6 +98,7 @@ class State {
     mutable uint64_t reduce_launches = 0;
 
     int tile_bits() const { return B_; }
+    size_t last_upload_bytes() const { return last_upload_bytes_; }
 
   private:
     void finish_reduce(int nv, double *out) const;
@@ -109,10 +110,7 @@ class State {
     bool fuse_ = true;
     void *d_state_ = nullptr;
     cudaStream_t stream_ = nullptr;
-    // pass descriptors: pinned staging + device copy
-    unsigned char *h_blob_ = nullptr, *d_blob_ = nullptr;
-    size_t blob_cap_ = 0;
-    cudaEvent_t blob_evt_ = nullptr;
+    size_t last_upload_bytes_ = 0; // descriptor bytes handed to the device by the last apply
     // reductions
     double *d_partials_ = nullptr, *d_out_ = nullptr, *h_out_ = nullptr;
     mutable std::vector<void *> scratch_;

@@ -4,11 +4,17 @@
 // (reference StateVectorKokkos.hpp:807-824 applyGateFunctor -> GateFunctors.hpp, one
 // Kokkos::parallel_for over 2^(n-k) per gate).
 //
-// Data flow per CTA (one tile of 2^B amplitudes, B = 12 for complex128 -> 64 KiB of shared memory):
-//   HBM --coalesced 16 B/lane loads, 2^low-amplitude contiguous runs--> shared memory (XOR-swizzled)
-//   for each round: every thread gathers 2^R amplitudes whose indices differ only in the round's R
-//     "register bits", applies all ops of the round in registers, scatters back in place
-//   shared memory --> HBM (same addresses: the update is in place)
+// Execution model (one persistent CTA per SM, two worker groups, three rotating tile buffers):
+//   * a tile = 2^B amplitudes (B = 12 for complex128 -> 64 KiB) whose indices differ in the pass's
+//     B tile bits; the CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+//   * each worker group (GT threads) owns every second tile of the CTA: it waits for the tile to
+//     land in shared memory, runs all rounds of the pass on it in registers, streams it back to
+//     HBM in place, and then refills the buffer it just freed with the tile three steps ahead
+//     (cp.async = LDGSTS with a per-amplitude XOR-swizzled destination; completion is handed to the
+//     other group through an mbarrier). So while two tiles are being computed a third is always
+//     in flight, and the HBM stream and the FP64 pipe overlap inside every SM.
+//   * a round: every thread gathers the 2^R amplitudes whose indices differ only in the round's R
+//     "register bits", applies all ops of the round in registers, scatters back in place.
 // HBM traffic is exactly one read + one write of the state per pass, whatever the number of gates.
 //
 // Shared-memory layout: amplitude i of the tile lives at slot phys(i) = i ^ fold(i) where fold XORs
@@ -17,6 +23,8 @@
 // lanes hit distinct 16 B / 8 B bank groups for every choice of register bits.
 #include "schedule.hpp"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 namespace b2sv {
@@ -35,6 +43,51 @@ template <int B, int SW> __device__ __forceinline__ uint32_t phys(uint32_t i) {
     for (int s = SW; s < B; s += SW)
         f ^= (i >> s);
     return i ^ (f & ((1u << SW) - 1u));
+}
+
+// ---- async-copy / mbarrier / named-barrier primitives ----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cp_async_amp(double2 *dst, const double2 *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_amp(float2 *dst, const float2 *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(dst)), "l"(src)
+                 : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its cp.async issued so far have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t *mbar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t *mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(
+                     smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
+    const uint32_t a = smem_u32(mbar);
+    uint32_t ok;
+    uint32_t spins = 0;
+    do {
+        if (++spins == (1u << 26))
+            __trap(); // a lost hand-off must surface as a CUDA error, never as a hung GPU
+        asm volatile("{\n .reg .pred p;\n"
+                     " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     " selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok)
+                     : "r"(a), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ---- register-level op bodies -------------------------------------------------------------------
@@ -219,144 +272,251 @@ __device__ __forceinline__ void run_op(amp_t (&a)[NS], const DevOp &op, uint64_t
     }
 }
 
+// G uncontrolled 2x2 gates, gate k on register slot k (k < R), fully unrolled.
+template <int G, int R, int NS, typename amp_t, typename real>
+__device__ __forceinline__ void dense_round(amp_t (&a)[NS], const DevOp *ops) {
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+        if constexpr (true) {
+            if (k >= R)
+                break;
+        }
+        real m[8];
+        const double2 *mp = reinterpret_cast<const double2 *>(ops[k].m);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const double2 t = mp[i];
+            m[2 * i] = static_cast<real>(t.x);
+            m[2 * i + 1] = static_cast<real>(t.y);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            if (s & (1 << k))
+                continue;
+            const int s1 = s | (1 << k);
+            const amp_t v0 = a[s], v1 = a[s1];
+            amp_t r0, r1;
+            r0.x = m[0] * v0.x - m[1] * v0.y + m[2] * v1.x - m[3] * v1.y;
+            r0.y = m[0] * v0.y + m[1] * v0.x + m[2] * v1.y + m[3] * v1.x;
+            r1.x = m[4] * v0.x - m[5] * v0.y + m[6] * v1.x - m[7] * v1.y;
+            r1.y = m[4] * v0.y + m[5] * v0.x + m[6] * v1.y + m[7] * v1.x;
+            a[s] = r0;
+            a[s1] = r1;
+        }
+    }
+}
+template <int R, int NS, typename amp_t>
+__device__ __forceinline__ void scatter_round(amp_t *tile, const amp_t (&a)[NS], uint32_t pb,
+                                              const uint32_t (&poff)[R]) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        uint32_t x = pb;
+#pragma unroll
+        for (int c = 0; c < R; c++)
+            if (s & (1 << c))
+                x ^= poff[c];
+        tile[x] = a[s];
+    }
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------
-template <typename real, int B, int R, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
+// The pass descriptor travels as a __grid_constant__ kernel parameter (constant bank): no upload,
+// and the dense rounds read their gate matrices through uniform constant loads instead of holding
+// them in 16 vector registers per thread.
+constexpr int kTileBuffers = 3;
+constexpr int kProducerThreads = 128; // one warpgroup that does nothing but stream tiles into shared memory
+
+template <typename real, int B, int R, int GT>
+__global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
     tile_exec_kernel(typename AmpT<real>::type *__restrict__ state,
-                     const unsigned char *__restrict__ blob, uint64_t rank_bits) {
+                     const __grid_constant__ PassParams pp, uint64_t rank_bits,
+                     uint32_t n_tiles) {
     using amp_t = typename AmpT<real>::type;
     constexpr int SW = (sizeof(amp_t) == 16) ? 3 : 4;
     constexpr int NS = 1 << R;
     constexpr int TILE = 1 << B;
-    constexpr int NF = B - R; // non-register tile bits = thread-id bits
-    static_assert((1 << NF) == THREADS, "one register group per thread");
+    constexpr int NF = B - R; // non-register tile bits = thread-id bits within a group
+    constexpr int NTHREADS = 2 * GT + kProducerThreads;
+    static_assert((1 << NF) == GT, "one register group per thread");
     static_assert(NF <= kMaxFreeBits, "too many thread-id bits");
-    constexpr int EPT = TILE / THREADS; // amplitudes per thread in the load / store phases (= NS)
+    constexpr int EPT = TILE / GT; // amplitudes per thread in the store phase (= NS)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    amp_t *tile = reinterpret_cast<amp_t *>(smem_raw);
-    DevOp *sops = reinterpret_cast<DevOp *>(smem_raw + sizeof(amp_t) * TILE);
+    amp_t *tiles = reinterpret_cast<amp_t *>(smem_raw); // kTileBuffers buffers of TILE amplitudes
+    DevOp *sops = reinterpret_cast<DevOp *>(smem_raw + kTileBuffers * sizeof(amp_t) * TILE);
     uint64_t *rowoff = reinterpret_cast<uint64_t *>(sops + kMaxOpsPerPass);
     __shared__ DevPassHeader hdr;
-    __shared__ uint32_t xoff[kMaxRounds + 1];
+    __shared__ uint32_t xoff_all[2][kMaxRounds + 1];
+    __shared__ __align__(8) uint64_t full[kTileBuffers], empty[kTileBuffers];
 
-    const int tid = threadIdx.x;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(blob);
+        const uint4 *src = reinterpret_cast<const uint4 *>(&pp.hdr);
         uint4 *dst = reinterpret_cast<uint4 *>(&hdr);
-        for (int i = tid; i < static_cast<int>(sizeof(DevPassHeader) / 16); i += THREADS)
+        for (int i = threadIdx.x; i < static_cast<int>(sizeof(DevPassHeader) / 16); i += NTHREADS)
             dst[i] = src[i];
-        const int n_ops = reinterpret_cast<const DevPassHeader *>(blob)->n_ops;
-        const uint4 *osrc = reinterpret_cast<const uint4 *>(blob + sizeof(DevPassHeader));
+        const int n_ops = pp.hdr.n_ops;
+        const uint4 *osrc = reinterpret_cast<const uint4 *>(pp.ops);
         uint4 *odst = reinterpret_cast<uint4 *>(sops);
-        for (int i = tid; i < n_ops * static_cast<int>(sizeof(DevOp) / 16); i += THREADS)
+        for (int i = threadIdx.x; i < n_ops * static_cast<int>(sizeof(DevOp) / 16); i += NTHREADS)
             odst[i] = osrc[i];
+        if (threadIdx.x < kTileBuffers) {
+            mbar_init(&full[threadIdx.x], kProducerThreads);
+            mbar_init(&empty[threadIdx.x], 1);
+        }
     }
     __syncthreads();
 
     const int low = hdr.low_bits;
-    // tile id -> index with the tile bits cleared (deposit into the non-tile positions)
-    uint64_t tb = blockIdx.x;
-#pragma unroll 1
-    for (int j = 0; j < B; j++) {
-        const int p = hdr.tile_bits[j];
-        tb = ((tb >> p) << (p + 1)) | (tb & ((uint64_t(1) << p) - 1));
-    }
-    for (int r = tid; r < (1 << (B - low)); r += THREADS) {
+    for (int r = threadIdx.x; r < (1 << (B - low)); r += NTHREADS) {
         uint64_t off = 0;
         for (int j = low; j < B; j++)
             if ((r >> (j - low)) & 1)
                 off |= uint64_t(1) << hdr.tile_bits[j];
         rowoff[r] = off;
     }
-    const uint64_t tbr = tb | rank_bits;
-    const int n_rounds = hdr.n_rounds;
-    if (tid <= n_rounds) { // CTA-uniform address toggles visible from round `tid` on
-        uint32_t x = 0;
-        for (int k = 0; k < hdr.n_cx; k++)
-            if (hdr.cx[k].round <= tid && (tbr & hdr.cx[k].gcm) == hdr.cx[k].gcv)
-                x ^= hdr.cx[k].vec;
-        xoff[tid] = x;
-    }
-    __syncthreads();
-
-    // ---- HBM -> shared (identity address map)
+    const int n_rounds = pp.hdr.n_rounds;
     const uint32_t lowmask = (1u << low) - 1u;
-    {
-        amp_t v[EPT];
-#pragma unroll
-        for (int e = 0; e < EPT; e++) {
-            const uint32_t i = e * THREADS + tid;
-            v[e] = state[tb | rowoff[i >> low] | (i & lowmask)];
-        }
-#pragma unroll
-        for (int e = 0; e < EPT; e++) {
-            const uint32_t i = e * THREADS + tid;
-            tile[phys<B, SW>(i)] = v[e];
-        }
-    }
     __syncthreads();
 
+    // tiles of this CTA: k = 0 .. n_mine-1  <->  global tile blockIdx.x + k * gridDim.x
+    const uint32_t n_mine = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    auto tile_base_of = [&](uint32_t k) { // deposit the tile id into the non-tile index bits
+        uint64_t tb = blockIdx.x + static_cast<uint64_t>(k) * gridDim.x;
 #pragma unroll 1
-    for (int rd = 0; rd < n_rounds; rd++) {
-        // this thread's register group: logical base index (high half) and storage slot (low half)
-        uint32_t acc = 0;
-#pragma unroll
-        for (int k = 0; k < NF; k++)
-            acc ^= (0u - ((static_cast<uint32_t>(tid) >> k) & 1u)) & hdr.round_col[rd][k];
-        const uint32_t base = acc >> 16;
-        const uint32_t pb = (acc & 0xffffu) ^ xoff[rd];
-        uint32_t poff[R];
-#pragma unroll
-        for (int s = 0; s < R; s++)
-            poff[s] = hdr.round_poff[rd][s];
-        const int o_begin = hdr.round_begin[rd], o_end = hdr.round_begin[rd + 1];
-        amp_t a[NS];
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-            uint32_t x = pb;
-#pragma unroll
-            for (int k = 0; k < R; k++)
-                if (s & (1 << k))
-                    x ^= poff[k];
-            a[s] = tile[x];
+        for (int j = 0; j < B; j++) {
+            const int p = hdr.tile_bits[j];
+            tb = ((tb >> p) << (p + 1)) | (tb & ((uint64_t(1) << p) - 1));
         }
-#pragma unroll 1
-        for (int oi = o_begin; oi < o_end; oi++)
-            run_op<R, NS, amp_t, real>(a, sops[oi], tbr, base);
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-            uint32_t x = pb;
-#pragma unroll
-            for (int k = 0; k < R; k++)
-                if (s & (1 << k))
-                    x ^= poff[k];
-            tile[x] = a[s];
+        return tb;
+    };
+
+    if (threadIdx.x >= 2 * GT) {
+        // ---- producer warps: HBM -> shared (identity address map), one tile ahead of the workers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n");
+        const int ptid = threadIdx.x - 2 * GT;
+        for (uint32_t k = 0; k < n_mine; k++) {
+            const int bi = k % kTileBuffers;
+            if (k >= kTileBuffers)
+                mbar_wait(&empty[bi], ((k / kTileBuffers) - 1) & 1u);
+            const uint64_t tb = tile_base_of(k);
+            amp_t *buf = tiles + bi * TILE;
+#pragma unroll 8
+            for (int e = 0; e < TILE / kProducerThreads; e++) {
+                const uint32_t i = e * kProducerThreads + ptid;
+                cp_async_amp(&buf[phys<B, SW>(i)], &state[tb | rowoff[i >> low] | (i & lowmask)]);
+            }
+            cp_async_arrive(&full[bi]);
         }
-        __syncthreads();
+        return;
     }
 
-    // ---- shared -> HBM through the final address map
-    {
-        constexpr int NT = NF; // log2(THREADS)
-        uint32_t sl = xoff[n_rounds];
-#pragma unroll
-        for (int k = 0; k < NT; k++)
-            sl ^= (0u - ((static_cast<uint32_t>(tid) >> k) & 1u)) & hdr.final_col[k];
-        uint32_t ecol[B - NT];
-#pragma unroll
-        for (int k = 0; k < B - NT; k++)
-            ecol[k] = hdr.final_col[NT + k];
-#pragma unroll
-        for (int e = 0; e < EPT; e++) {
-            const uint32_t i = e * THREADS + tid;
-            uint32_t x = sl;
-#pragma unroll
-            for (int k = 0; k < B - NT; k++)
-                if (e & (1 << k))
-                    x ^= ecol[k];
-            state[tb | rowoff[i >> low] | (i & lowmask)] = tile[x];
+    // ---- worker groups: tile k is computed by group k & 1
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
+    const int grp = threadIdx.x / GT;
+    const int tid = threadIdx.x % GT;
+    uint32_t *xoff = xoff_all[grp];
+    for (uint32_t k = grp; k < n_mine; k += 2) {
+        const int bi = k % kTileBuffers;
+        amp_t *tile = tiles + bi * TILE;
+        const uint64_t tb = tile_base_of(k);
+        const uint64_t tbr = tb | rank_bits;
+        if (tid <= n_rounds) { // CTA-uniform address toggles visible from round `tid` on
+            uint32_t x = 0;
+            for (int c = 0; c < hdr.n_cx; c++)
+                if (hdr.cx[c].round <= tid && (tbr & hdr.cx[c].gcm) == hdr.cx[c].gcv)
+                    x ^= hdr.cx[c].vec;
+            xoff[tid] = x;
         }
+        mbar_wait(&full[bi], (k / kTileBuffers) & 1u);
+        group_sync(1 + grp, GT);
+
+#pragma unroll 1
+        for (int rd = 0; rd < n_rounds; rd++) {
+            // this thread's register group: logical base index (high half), storage slot (low half)
+            uint32_t acc = 0;
+#pragma unroll
+            for (int c = 0; c < NF; c++)
+                acc ^= (0u - ((static_cast<uint32_t>(tid) >> c) & 1u)) & hdr.round_col[rd][c];
+            const uint32_t base = acc >> 16;
+            const uint32_t pb = (acc & 0xffffu) ^ xoff[rd];
+            uint32_t poff[R];
+#pragma unroll
+            for (int s = 0; s < R; s++)
+                poff[s] = hdr.round_poff[rd][s];
+            const int o_begin = pp.hdr.round_begin[rd], o_end = pp.hdr.round_begin[rd + 1];
+            amp_t a[NS];
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                uint32_t x = pb;
+#pragma unroll
+                for (int c = 0; c < R; c++)
+                    if (s & (1 << c))
+                        x ^= poff[c];
+                a[s] = tile[x];
+            }
+            // a zero the compiler cannot see through: the 2^R scatter addresses are recomputed
+            // after the arithmetic instead of being kept alive -- and spilled -- across the round
+            const uint32_t opaque_zero = pp.hdr.pad_[0];
+            const int kind = pp.hdr.round_kind[rd];
+            if (kind == 0) {
+#pragma unroll 1
+                for (int oi = o_begin; oi < o_end; oi++)
+                    run_op<R, NS, amp_t, real>(a, sops[oi], tbr, base);
+                scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+            } else {
+                // dense round: gate k acts on register slot k; each case is straight-line code from
+                // the gathered registers to the scatter, so ptxas renames freely (no moves)
+                switch (kind) {
+                case 1:
+                    dense_round<1, R, NS, amp_t, real>(a, pp.ops + o_begin);
+                    scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+                    break;
+                case 2:
+                    dense_round<2, R, NS, amp_t, real>(a, pp.ops + o_begin);
+                    scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+                    break;
+                case 3:
+                    dense_round<3, R, NS, amp_t, real>(a, pp.ops + o_begin);
+                    scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+                    break;
+                case 4:
+                    dense_round<4, R, NS, amp_t, real>(a, pp.ops + o_begin);
+                    scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+                    break;
+                default:
+                    dense_round<5, R, NS, amp_t, real>(a, pp.ops + o_begin);
+                    scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+                    break;
+                }
+            }
+            group_sync(1 + grp, GT);
+        }
+
+        // ---- shared -> HBM through the final address map
+        {
+            constexpr int NT = NF; // log2(GT)
+            uint32_t sl = xoff[n_rounds];
+#pragma unroll
+            for (int c = 0; c < NT; c++)
+                sl ^= (0u - ((static_cast<uint32_t>(tid) >> c) & 1u)) & hdr.final_col[c];
+            uint32_t ecol[B - NT];
+#pragma unroll
+            for (int c = 0; c < B - NT; c++)
+                ecol[c] = hdr.final_col[NT + c];
+#pragma unroll
+            for (int e = 0; e < EPT; e++) {
+                const uint32_t i = e * GT + tid;
+                uint32_t x = sl;
+#pragma unroll
+                for (int c = 0; c < B - NT; c++)
+                    if (e & (1 << c))
+                        x ^= ecol[c];
+                state[tb | rowoff[i >> low] | (i & lowmask)] = tile[x];
+            }
+        }
+        group_sync(1 + grp, GT); // every thread of the group is done with this buffer (and xoff)
+        if (tid == 0)
+            mbar_arrive(&empty[bi]);
     }
 }
 
@@ -364,50 +524,53 @@ __global__ void __launch_bounds__(THREADS, MINB)
 namespace {
 constexpr int kMinLow = 4;
 template <typename real, int B> constexpr size_t tile_smem_bytes() {
-    return sizeof(typename AmpT<real>::type) * (size_t(1) << B) + sizeof(DevOp) * kMaxOpsPerPass +
-           sizeof(uint64_t) * (size_t(1) << (B - kMinLow));
+    return kTileBuffers * sizeof(typename AmpT<real>::type) * (size_t(1) << B) +
+           sizeof(DevOp) * kMaxOpsPerPass + sizeof(uint64_t) * (size_t(1) << (B - kMinLow));
+}
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return n;
+}
+template <typename real, int B, int R, int GT>
+void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
+                    cudaStream_t stream) {
+    using amp_t = typename AmpT<real>::type;
+    auto kern = tile_exec_kernel<real, B, R, GT>;
+    constexpr size_t smem = tile_smem_bytes<real, B>();
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+        configured = true;
+    }
+    const uint32_t n_tiles = 1u << (n_eff - B);
+    // one persistent CTA per SM; with fewer than 2 tiles per SM spread them one per CTA
+    const unsigned grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(sm_count()));
+    // the descriptor is copied into the launch's parameter buffer by the runtime at this call
+    kern<<<grid, 2 * GT + kProducerThreads, smem, stream>>>(static_cast<amp_t *>(state), pp,
+                                                            rank_bits, n_tiles);
+    CUDA_CHECK(cudaGetLastError());
 }
 } // namespace
 
-// Tile geometry per dtype: complex128 -> 2^12 amps (64 KiB), complex64 -> 2^13 amps (64 KiB).
+// Tile geometry per dtype: complex128 -> 2^12 amps (64 KiB), complex64 -> 2^13 amps (64 KiB);
+// three buffers per CTA (192 KiB of the 227 KiB an sm_100 CTA may use).
 void tile_config(int dtype, int *B, int *R) {
-    if (dtype == 1) {
-        *B = 12;
-        *R = 4;
-    } else {
-        *B = 13;
-        *R = 4;
-    }
+    *B = dtype == 1 ? 12 : 13;
+    *R = dtype == 1 ? 4 : 5; // 16 double2 / 32 float2 amplitudes per thread = 64 registers
 }
 
-void launch_tile_pass(int dtype, void *state, const unsigned char *dev_blob, int n_eff,
+void launch_tile_pass(int dtype, void *state, const PassParams &pp, int n_eff,
                       uint64_t rank_bits, cudaStream_t stream) {
-    if (dtype == 1) {
-        constexpr int B = 12;
-        auto kern = tile_exec_kernel<double, B, 4, 256, 2>;
-        constexpr size_t smem = tile_smem_bytes<double, B>();
-        static bool configured = false;
-        if (!configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(smem)));
-            configured = true;
-        }
-        const unsigned grid = 1u << (n_eff - B);
-        kern<<<grid, 256, smem, stream>>>(static_cast<double2 *>(state), dev_blob, rank_bits);
-    } else {
-        constexpr int B = 13;
-        auto kern = tile_exec_kernel<float, B, 4, 512, 2>;
-        constexpr size_t smem = tile_smem_bytes<float, B>();
-        static bool configured = false;
-        if (!configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(smem)));
-            configured = true;
-        }
-        const unsigned grid = 1u << (n_eff - B);
-        kern<<<grid, 512, smem, stream>>>(static_cast<float2 *>(state), dev_blob, rank_bits);
-    }
-    CUDA_CHECK(cudaGetLastError());
+    if (dtype == 1)
+        launch_variant<double, 12, 4, 256>(state, pp, n_eff, rank_bits, stream);
+    else
+        launch_variant<float, 13, 5, 256>(state, pp, n_eff, rank_bits, stream);
 }
 
 } // namespace b2sv
