@@ -266,8 +266,31 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                     ps.hdr.tile_bits[j++] = static_cast<uint8_t>(b);
             B2_ASSERT(j == B);
         }
+        { // tile-id deposit segments: runs of consecutive non-tile bits
+            int n_seg = 0, id_bit = 0, below = 0; // below = tile bits under the current position
+            const int top = std::max(cfg.n_alloc, cfg.n_local);
+            int b = 0;
+            while (b < top) {
+                if (tile_mask & bit(b)) {
+                    below++;
+                    b++;
+                    continue;
+                }
+                int len = 0;
+                while (b + len < top && !(tile_mask & bit(b + len)))
+                    len++;
+                B2_ASSERT(n_seg <= kMaxTileBits);
+                ps.hdr.seg_mask[n_seg] = static_cast<uint32_t>(((uint64_t(1) << len) - 1) << id_bit);
+                ps.hdr.seg_shift[n_seg] = static_cast<uint8_t>(below);
+                n_seg++;
+                id_bit += len;
+                b += len;
+            }
+            ps.hdr.n_seg = static_cast<uint8_t>(n_seg);
+        }
         // ---- rounds, with permutation primitives folded into the address map at round boundaries
         uint32_t Mcol[kMaxTileBits]; // storage index (before the swizzle) of logical basis vector e_j
+        uint32_t McolLast[kMaxTileBits] = {0}; // Mcol as the most recent round saw it
         for (int j = 0; j < B; j++)
             Mcol[j] = 1u << j;
         int n_cx = 0;
@@ -288,12 +311,30 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                 return 1;
             return 0;
         };
+        // logical-space image of the permutations absorbed since the last round was built:
+        // index j (as the last round's threads know it) ends up at Lmap(j) ^ (toggles that fire)
+        uint32_t Lcol[kMaxTileBits];
+        uint32_t cx_logical[kMaxCx];
+        auto reset_logical = [&]() {
+            for (int j = 0; j < B; j++)
+                Lcol[j] = 1u << j;
+            for (int c = 0; c < kMaxCx; c++)
+                cx_logical[c] = 0;
+        };
+        reset_logical();
         auto absorb = [&](const Prim &p, int cls, int round_idx) {
             const int jt = tile_pos(p.target);
             if (cls == 1) {
                 const int jc = tile_pos(ctz(p.cmask));
                 Mcol[jc] ^= Mcol[jt];
+                for (int j = 0; j < B; j++)
+                    if ((Lcol[j] >> jc) & 1u)
+                        Lcol[j] ^= 1u << jt;
+                for (int c = 0; c < n_cx; c++)
+                    if ((cx_logical[c] >> jc) & 1u)
+                        cx_logical[c] ^= 1u << jt;
             } else {
+                cx_logical[n_cx] = 1u << jt;
                 DevCx &c = ps.hdr.cx[n_cx++];
                 c.gcm = p.cmask;
                 c.gcv = p.cval;
@@ -411,6 +452,8 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                 for (size_t k = 0; k < order.size(); k++)
                     ps.hdr.round_col[n_rounds][k] = order[k];
             }
+            for (int j = 0; j < B; j++)
+                McolLast[j] = Mcol[j];
             ps.hdr.round_begin[n_rounds] = static_cast<uint16_t>(ps.ops.size());
             for (int i : now) {
                 ps.ops.push_back(make_devop(prims[i], ps.hdr.tile_bits, B, rbits, R, -1));
@@ -418,6 +461,57 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
             }
             n_rounds++;
             remaining.swap(later);
+            reset_logical();
+        }
+        if (n_rounds >= 1 && cfg.fuse_store) {
+            // Fused store: possible when five thread-id bits of the last round can be given free
+            // tile bits whose images under the trailing permutations stay inside logical bits 0..4
+            // and span them -- then every warp-wide store covers whole contiguous runs.
+            const int last = n_rounds - 1;
+            uint32_t reg_mask = 0;
+            for (int k = 0; k < R; k++)
+                reg_mask |= 1u << ps.hdr.round_regbits[last][k];
+            std::vector<int> lanes, others;
+            std::vector<uint32_t> basis;
+            for (int j = 0; j < B; j++) {
+                if (reg_mask & (1u << j))
+                    continue;
+                uint32_t v = Lcol[j];
+                bool ok = v < 32u && lanes.size() < 5;
+                if (ok) {
+                    for (uint32_t b : basis)
+                        v = std::min(v, v ^ b);
+                    ok = v != 0;
+                }
+                if (ok) {
+                    basis.push_back(v);
+                    std::sort(basis.rbegin(), basis.rend());
+                    lanes.push_back(j);
+                } else {
+                    others.push_back(j);
+                }
+            }
+            if (lanes.size() == 5) {
+                auto spread = [&](uint32_t v) {
+                    uint64_t g = 0;
+                    for (int j = 0; j < B; j++)
+                        if ((v >> j) & 1u)
+                            g |= bit(ps.hdr.tile_bits[j]);
+                    return g;
+                };
+                lanes.insert(lanes.end(), others.begin(), others.end());
+                for (size_t k = 0; k < lanes.size(); k++) {
+                    const int j = lanes[k];
+                    ps.hdr.round_col[last][k] =
+                        ((1u << j) << 16) | phys_slot(McolLast[j], B, cfg.SW);
+                    ps.hdr.store_free[k] = spread(Lcol[j]);
+                }
+                for (int k = 0; k < R; k++)
+                    ps.hdr.store_reg[k] = spread(Lcol[ps.hdr.round_regbits[last][k]]);
+                for (int c = 0; c < n_cx; c++)
+                    ps.hdr.store_cx[c] = ps.hdr.cx[c].round == n_rounds ? spread(cx_logical[c]) : 0;
+                ps.hdr.fused_store = 1;
+            }
         }
         for (int j = 0; j < B; j++)
             ps.hdr.final_col[j] = static_cast<uint16_t>(phys_slot(Mcol[j], B, cfg.SW));

@@ -60,6 +60,19 @@ struct alignas(16) DevPassHeader {
     // 0: generic round (op interpreter); g >= 1: "dense" round = exactly g uncontrolled 2x2 gates,
     // the k-th one on register slot k (straight-line code, no per-op dispatch)
     uint8_t round_kind[kMaxRounds];
+    // tile id -> index with the tile bits cleared: base = OR_k ((id & seg_mask[k]) << seg_shift[k]),
+    // one segment per run of consecutive non-tile index bits
+    uint32_t seg_mask[kMaxTileBits + 1];
+    uint8_t seg_shift[kMaxTileBits + 1];
+    uint8_t n_seg;
+    // fused store: the last round writes its registers straight to HBM (no scatter, no store phase)
+    uint8_t fused_store;
+    uint8_t pad2_[13];
+    // global index offsets (already pushed through the permutations absorbed after the last round):
+    // of thread-id bit k of the last round, of register slot s, and of conditional toggle c
+    uint64_t store_free[kMaxFreeBits];
+    uint64_t store_reg[8];
+    uint64_t store_cx[kMaxCx];
     uint16_t round_begin[kMaxRounds + 1]; // op index ranges per round
     uint16_t pad_[3];
     // storage offset phys(M e_r) of register bit s in round rd
@@ -97,6 +110,7 @@ struct SchedConfig {
     int n_alloc = 0;   // index bits of the allocation (>= B; small states are zero-padded)
     bool fuse = true;  // false: one pass per primitive group (reference schedule)
     bool free_perms = true; // fold CNOT / X into the address map
+    bool fuse_store = true; // let the last round of a pass write straight to HBM when coalescing allows
     int max_heavy = 8;      // arithmetic ops per pass before the pass turns FP64-bound
 };
 

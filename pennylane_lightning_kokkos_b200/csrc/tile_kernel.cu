@@ -86,6 +86,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
                      : "memory");
     } while (!ok);
 }
+// one lane polls, the rest of the warp parks at the warp barrier (no 32-wide spinning)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *mbar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0)
+        mbar_wait(mbar, parity);
+    __syncwarp();
+}
 __device__ __forceinline__ void group_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -319,6 +325,41 @@ __device__ __forceinline__ void scatter_round(amp_t *tile, const amp_t (&a)[NS],
     }
 }
 
+// last round of a pass: registers -> HBM directly. Addresses are XOR-combinations of global index
+// offsets read from the (uniform) pass descriptor; computed here, after the arithmetic, so nothing
+// extra stays live across the round.
+template <int R, int NS, int NF, typename amp_t>
+__device__ __forceinline__ void store_round(amp_t *__restrict__ state, const amp_t (&a)[NS],
+                                            const DevPassHeader &ph, uint64_t tb, uint64_t tbr,
+                                            int tid) {
+    uint64_t addr0 = tb;
+#pragma unroll
+    for (int c = 0; c < NF; c++)
+        addr0 ^= (uint64_t(0) - ((static_cast<uint64_t>(tid) >> c) & 1u)) & ph.store_free[c];
+    for (int c = 0; c < ph.n_cx; c++)
+        if ((tbr & ph.cx[c].gcm) == ph.cx[c].gcv)
+            addr0 ^= ph.store_cx[c];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        uint64_t x = addr0;
+#pragma unroll
+        for (int c = 0; c < R; c++)
+            if (s & (1 << c))
+                x ^= ph.store_reg[c];
+        state[x] = a[s];
+    }
+}
+template <int R, int NS, int NF, typename amp_t>
+__device__ __forceinline__ void finish_round(bool fused, amp_t *__restrict__ state, amp_t *tile,
+                                             const amp_t (&a)[NS], uint32_t pb,
+                                             const uint32_t (&poff)[R], const DevPassHeader &ph,
+                                             uint64_t tb, uint64_t tbr, int tid) {
+    if (fused)
+        store_round<R, NS, NF>(state, a, ph, tb, tbr, tid);
+    else
+        scatter_round<R, NS>(tile, a, pb, poff);
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------
 // The pass descriptor travels as a __grid_constant__ kernel parameter (constant bank): no upload,
 // and the dense rounds read their gate matrices through uniform constant loads instead of holding
@@ -381,12 +422,12 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
     // tiles of this CTA: k = 0 .. n_mine-1  <->  global tile blockIdx.x + k * gridDim.x
     const uint32_t n_mine = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     auto tile_base_of = [&](uint32_t k) { // deposit the tile id into the non-tile index bits
-        uint64_t tb = blockIdx.x + static_cast<uint64_t>(k) * gridDim.x;
+        const uint32_t t = blockIdx.x + k * gridDim.x;
+        uint64_t tb = 0;
+        const int n_seg = pp.hdr.n_seg;
 #pragma unroll 1
-        for (int j = 0; j < B; j++) {
-            const int p = hdr.tile_bits[j];
-            tb = ((tb >> p) << (p + 1)) | (tb & ((uint64_t(1) << p) - 1));
-        }
+        for (int j = 0; j < n_seg; j++)
+            tb |= static_cast<uint64_t>(t & pp.hdr.seg_mask[j]) << pp.hdr.seg_shift[j];
         return tb;
     };
 
@@ -397,7 +438,7 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
         for (uint32_t k = 0; k < n_mine; k++) {
             const int bi = k % kTileBuffers;
             if (k >= kTileBuffers)
-                mbar_wait(&empty[bi], ((k / kTileBuffers) - 1) & 1u);
+                mbar_wait_warp(&empty[bi], ((k / kTileBuffers) - 1) & 1u);
             const uint64_t tb = tile_base_of(k);
             amp_t *buf = tiles + bi * TILE;
 #pragma unroll 8
@@ -427,7 +468,7 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
                     x ^= hdr.cx[c].vec;
             xoff[tid] = x;
         }
-        mbar_wait(&full[bi], (k / kTileBuffers) & 1u);
+        mbar_wait_warp(&full[bi], (k / kTileBuffers) & 1u);
         group_sync(1 + grp, GT);
 
 #pragma unroll 1
@@ -458,39 +499,50 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
             // after the arithmetic instead of being kept alive -- and spilled -- across the round
             const uint32_t opaque_zero = pp.hdr.pad_[0];
             const int kind = pp.hdr.round_kind[rd];
+            // fused store: the last round's registers go straight to HBM; the tile buffer is free
+            // as soon as every thread of the group has gathered from it
+            const bool fused = pp.hdr.fused_store && rd == n_rounds - 1;
+            if (fused) {
+                group_sync(1 + grp, GT);
+                if (tid == 0)
+                    mbar_arrive(&empty[bi]);
+            }
             if (kind == 0) {
 #pragma unroll 1
                 for (int oi = o_begin; oi < o_end; oi++)
                     run_op<R, NS, amp_t, real>(a, sops[oi], tbr, base);
-                scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+                finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
             } else {
                 // dense round: gate k acts on register slot k; each case is straight-line code from
                 // the gathered registers to the scatter, so ptxas renames freely (no moves)
                 switch (kind) {
                 case 1:
                     dense_round<1, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
                     break;
                 case 2:
                     dense_round<2, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
                     break;
                 case 3:
                     dense_round<3, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
                     break;
                 case 4:
                     dense_round<4, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
                     break;
                 default:
                     dense_round<5, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    scatter_round<R, NS>(tile, a, pb ^ opaque_zero, poff);
+                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
                     break;
                 }
             }
-            group_sync(1 + grp, GT);
+            if (!fused)
+                group_sync(1 + grp, GT);
         }
+        if (pp.hdr.fused_store && n_rounds > 0)
+            continue; // stored from registers, buffer already released
 
         // ---- shared -> HBM through the final address map
         {
