@@ -83,6 +83,14 @@ int b2sv_set_fusion(b2sv_state *s, int fuse);
 /* counters since the last reset: full-state sweeps executed, kernels launched */
 int b2sv_get_stats(const b2sv_state *s, uint64_t *sweeps, uint64_t *launches);
 int b2sv_reset_stats(b2sv_state *s);
+/* sharded states: global<->local qubit swaps done so far, bytes each rank sent, and whether the
+ * NVLink peer-memory swap kernel (1) or NCCL send/recv (0) carries them */
+int b2sv_comm_stats(const b2sv_state *s, uint64_t *swaps, uint64_t *swap_bytes, int *peer_path);
+/* bytes of pass descriptors / matrices the last apply call handed to the device */
+int b2sv_last_upload_bytes(const b2sv_state *s, uint64_t *bytes);
+/* sharded states keep swapped-in qubits where they are (lazy layout); this restores the identity
+ * layout (wire w <-> bit n-1-w, top bits = rank). d2h does it implicitly. */
+int b2sv_normalize_layout(b2sv_state *s);
 
 /* ---- op lists (OpsData ADJ.hpp:40-56; create_ops_list Bindings.cpp:772-805) ---------- */
 /* params / wires are concatenated; nparams[i] / nwires[i] give the split. matrices may be NULL;

@@ -229,6 +229,25 @@ int b2sv_reset_stats(b2sv_state *s) {
         st(s).reduce_launches = 0;
     });
 }
+int b2sv_comm_stats(const b2sv_state *s, uint64_t *swaps, uint64_t *swap_bytes, int *peer_path) {
+    return guard([&] {
+        uint64_t a = 0, b = 0;
+        int p = 0;
+        st(s).comm_stats(&a, &b, &p);
+        if (swaps)
+            *swaps = a;
+        if (swap_bytes)
+            *swap_bytes = b;
+        if (peer_path)
+            *peer_path = p;
+    });
+}
+int b2sv_last_upload_bytes(const b2sv_state *s, uint64_t *bytes) {
+    return guard([&] { *bytes = st(s).last_upload_bytes(); });
+}
+int b2sv_normalize_layout(b2sv_state *s) {
+    return guard([&] { st(s).normalize_layout(); });
+}
 
 int b2sv_ops_create(int nops, const char *const *names, const double *params, const int *nparams,
                     const int64_t *wires, const int *nwires, const int *inverses,

@@ -1,9 +1,12 @@
 // b2sv: multi-GPU plumbing (see comm.hpp). NCCL is resolved at run time with dlopen.
 #include "comm.hpp"
+#include "kernels.cuh"
 #include "state.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <dlfcn.h>
 
 namespace b2sv {
@@ -21,6 +24,7 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t *, int, NcclId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -51,6 +55,7 @@ NcclApi &nccl() {
     LOAD(CommInitRank);
     LOAD(CommDestroy);
     LOAD(AllReduce);
+    LOAD(AllGather);
     LOAD(Send);
     LOAD(Recv);
     LOAD(GroupStart);
@@ -72,6 +77,9 @@ struct Comm {
     ncclComm_t comm = nullptr;
     void *staging = nullptr;
     size_t staging_bytes = 0;
+    double *d_token = nullptr; // one double used for stream-ordered barriers
+    bool use_peer = true;      // NVLink peer-memory swap kernel (CUDA IPC); else NCCL send/recv
+    uint64_t swaps = 0, swap_bytes = 0;
 };
 
 void comm_unique_id(void *out128) {
@@ -90,6 +98,10 @@ Comm *comm_create(int rank, int world, const void *unique_id, int device) {
     std::memcpy(&id, unique_id, sizeof(id));
     CUDA_CHECK(cudaSetDevice(device));
     NCCL_CHECK(nccl().CommInitRank(&c->comm, world, id, rank));
+    CUDA_CHECK(cudaMalloc(&c->d_token, sizeof(double) * 2));
+    CUDA_CHECK(cudaMemset(c->d_token, 0, sizeof(double) * 2));
+    if (const char *e = getenv("B2SV_SWAP"))
+        c->use_peer = std::string(e) != "nccl";
     return c;
 }
 void comm_destroy(Comm *c) {
@@ -98,6 +110,8 @@ void comm_destroy(Comm *c) {
     cudaSetDevice(c->device);
     if (c->staging)
         cudaFree(c->staging);
+    if (c->d_token)
+        cudaFree(c->d_token);
     if (c->comm)
         nccl().CommDestroy(c->comm);
     delete c;
@@ -106,28 +120,110 @@ void comm_allreduce_sum(Comm *c, double *d_buf, int n, cudaStream_t stream) {
     NCCL_CHECK(nccl().AllReduce(d_buf, d_buf, static_cast<size_t>(n), kNcclFloat64, kNcclSum,
                                 c->comm, stream));
 }
+void comm_barrier(Comm *c, cudaStream_t stream) {
+    NCCL_CHECK(nccl().AllReduce(c->d_token, c->d_token + 1, 1, kNcclFloat64, kNcclSum, c->comm,
+                                stream));
+}
+int comm_rank(const Comm *c) { return c->rank; }
+int comm_world(const Comm *c) { return c->world; }
+void comm_stats(const Comm *c, uint64_t *swaps, uint64_t *bytes) {
+    *swaps = c->swaps;
+    *bytes = c->swap_bytes;
+}
+void comm_reset_stats(Comm *c) { c->swaps = c->swap_bytes = 0; }
+bool comm_uses_peer(const Comm *c) { return c->use_peer; }
 
-// Exchange rank bit j with local index bit l: amplitudes with (rank_bit, local_bit) = (0,1) on the
-// lower rank trade places with (1,0) on the partner rank r ^ (1<<j). The half to send consists of
-// 2^(n_local-1-l) contiguous runs of 2^l amplitudes; it goes through a bounded staging buffer in
-// chunks (the shard may fill most of HBM, so there is no room for a second copy).
-static void swap_global_local(Comm *c, State &s, int j, int l) {
+// Maps every rank's buffer into this process (CUDA IPC): out[r] = pointer usable in kernels here.
+// Collective: every rank calls it with its own buffer, in the same order.
+void comm_map_peers(Comm *c, void *my_buffer, std::vector<void *> &out, cudaStream_t stream) {
+    out.assign(c->world, nullptr);
+    out[c->rank] = my_buffer;
+    if (!c->use_peer)
+        return;
+    CUDA_CHECK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t mine;
+    cudaError_t e = cudaIpcGetMemHandle(&mine, my_buffer);
+    char *d_all = nullptr;
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    CUDA_CHECK(cudaMalloc(&d_all, hs * (c->world + 1)));
+    // slot `world` holds this rank's handle (all zeros on failure, detected by everybody)
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        std::memset(&mine, 0, hs);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(d_all + hs * c->world, &mine, hs, cudaMemcpyHostToDevice, stream));
+    NCCL_CHECK(nccl().AllGather(d_all + hs * c->world, d_all, hs, kNcclInt8, c->comm, stream));
+    std::vector<cudaIpcMemHandle_t> all(c->world);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all, hs * c->world, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    CUDA_CHECK(cudaFree(d_all));
+    bool ok = true;
+    const cudaIpcMemHandle_t zero{};
+    for (int r = 0; r < c->world; r++)
+        ok = ok && std::memcmp(&all[r], &zero, hs) != 0;
+    for (int r = 0; ok && r < c->world; r++) {
+        if (r == c->rank)
+            continue;
+        e = cudaIpcOpenMemHandle(&out[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+        }
+    }
+    // all ranks must agree, otherwise one would wait in a barrier the other never enters
+    double flag = ok ? 0.0 : 1.0, total = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(c->d_token, &flag, sizeof(double), cudaMemcpyHostToDevice, stream));
+    NCCL_CHECK(nccl().AllReduce(c->d_token, c->d_token + 1, 1, kNcclFloat64, kNcclSum, c->comm, stream));
+    CUDA_CHECK(cudaMemcpyAsync(&total, c->d_token + 1, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    flag = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(c->d_token, &flag, sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (total != 0.0) {
+        comm_unmap_peers(c, out);
+        out.assign(c->world, nullptr);
+        out[c->rank] = my_buffer;
+        c->use_peer = false; // every rank takes the NCCL send/recv path from now on
+    }
+}
+void comm_unmap_peers(Comm *c, std::vector<void *> &ptrs) {
+    for (int r = 0; r < static_cast<int>(ptrs.size()); r++)
+        if (r != c->rank && ptrs[r]) {
+            cudaIpcCloseMemHandle(ptrs[r]);
+            ptrs[r] = nullptr;
+        }
+}
+
+// Exchange rank bit j with local bit l: amplitudes with (rank_bit, local_bit) = (0,1) on the lower
+// rank trade places with (1,0) on the partner rank r ^ (1<<j).
+//   peer path : one kernel per rank swaps its half of the pairs in place through the partner's
+//               IPC-mapped shard (NVLink loads + stores), bracketed by stream-ordered barriers;
+//   NCCL path : the half to send consists of 2^(n_local-1-l) contiguous runs of 2^l amplitudes and
+//               goes through a bounded staging buffer in chunks (the shard may fill most of HBM).
+void comm_swap_bits(Comm *c, void *data, const std::vector<void *> &peers, int dtype, int n_local,
+                    int j, int l, cudaStream_t st) {
     CUDA_CHECK(cudaSetDevice(c->device));
     const int partner = c->rank ^ (1 << j);
     const int my_bit = (c->rank >> j) & 1;
-    const size_t ab = s.amp_bytes();
-    const uint64_t run = uint64_t(1) << l;                          // amplitudes per run
-    const uint64_t nruns = uint64_t(1) << (s.num_local() - 1 - l);  // runs in the half
+    const size_t ab = dtype == 1 ? 16 : 8;
+    c->swaps++;
+    c->swap_bytes += (uint64_t(1) << (n_local - 1)) * ab;
+    if (c->use_peer && peers[partner]) {
+        comm_barrier(c, st); // the partner has finished everything queued on its shard
+        launch_peer_swap(dtype, data, peers[partner], n_local, l, my_bit, st);
+        comm_barrier(c, st); // the partner's kernel has finished writing into this shard
+        return;
+    }
+    const uint64_t run = uint64_t(1) << l;                  // amplitudes per run
+    const uint64_t nruns = uint64_t(1) << (n_local - 1 - l); // runs in the half
     const size_t want = size_t(256) << 20;
-    const uint64_t chunk = std::min<uint64_t>(run, want / ab);      // amplitudes per transfer
+    const uint64_t chunk = std::min<uint64_t>(run, want / ab); // amplitudes per transfer
     if (c->staging_bytes < chunk * ab) {
         if (c->staging)
             CUDA_CHECK(cudaFree(c->staging));
         CUDA_CHECK(cudaMalloc(&c->staging, chunk * ab));
         c->staging_bytes = chunk * ab;
     }
-    char *base = static_cast<char *>(s.data());
-    cudaStream_t st = s.stream();
+    char *base = static_cast<char *>(data);
     for (uint64_t r = 0; r < nruns; r++) {
         // run r of the half where local bit l == (1 - my_bit)
         const uint64_t start = (r << (l + 1)) | (uint64_t(1 - my_bit) << l);
@@ -140,24 +236,6 @@ static void swap_global_local(Comm *c, State &s, int j, int l) {
             CUDA_CHECK(cudaMemcpyAsync(p, c->staging, chunk * ab, cudaMemcpyDeviceToDevice, st));
         }
     }
-}
-
-void comm_localize(Comm *c, State &s, std::vector<Prim> &prims) {
-    // v1 policy: find the rank bits that some primitive targets non-diagonally; bring each one in
-    // by swapping it with a high local bit that no primitive of this batch targets (or, failing
-    // that, any high local bit), run the batch with the relabelled bits, and swap back afterwards.
-    const int nl = s.num_local();
-    uint64_t need = 0, targeted = 0;
-    for (const Prim &p : prims) {
-        const uint64_t tm = p.target_mask();
-        targeted |= tm;
-        need |= tm >> nl;
-    }
-    if (!need)
-        return;
-    B2_ABORT("internal: global-qubit targets must be handled by State::apply_prims_sharded");
-    (void)c;
-    (void)swap_global_local;
 }
 
 } // namespace b2sv

@@ -4,19 +4,30 @@
 #include "ir.hpp"
 
 #include <cuda_runtime.h>
+#include <vector>
 
 namespace b2sv {
 
-class State;
 struct Comm;
 
 void comm_unique_id(void *out128);
 Comm *comm_create(int rank, int world, const void *nccl_unique_id, int device);
 void comm_destroy(Comm *c);
+int comm_rank(const Comm *c);
+int comm_world(const Comm *c);
 // sum-all-reduce `n` doubles in place on the device
 void comm_allreduce_sum(Comm *c, double *d_buf, int n, cudaStream_t stream);
-// Rewrites `prims` so that no C1Q / MATK target sits on a rank bit, performing the required
-// global<->local qubit swaps on `state` (pairwise half-shard exchanges over NVLink).
-void comm_localize(Comm *c, State &state, std::vector<Prim> &prims);
+// stream-ordered barrier across ranks
+void comm_barrier(Comm *c, cudaStream_t stream);
+// CUDA-IPC mapping of every rank's shard (collective); falls back to the NCCL path on all ranks
+// together if any mapping fails
+void comm_map_peers(Comm *c, void *my_buffer, std::vector<void *> &out, cudaStream_t stream);
+void comm_unmap_peers(Comm *c, std::vector<void *> &ptrs);
+bool comm_uses_peer(const Comm *c);
+// exchange rank bit j (0 = lowest rank bit) with local index bit l, in place
+void comm_swap_bits(Comm *c, void *data, const std::vector<void *> &peers, int dtype, int n_local,
+                    int j, int l, cudaStream_t stream);
+void comm_stats(const Comm *c, uint64_t *swaps, uint64_t *bytes);
+void comm_reset_stats(Comm *c);
 
 } // namespace b2sv

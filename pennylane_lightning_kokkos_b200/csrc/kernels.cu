@@ -10,6 +10,7 @@
 // All reductions accumulate in double (also for complex64), each block writes its partial sums
 // and a single-block finalize kernel adds them in a fixed order: results are deterministic.
 #include "kernels.cuh"
+#include <algorithm>
 #include "common.hpp"
 
 namespace b2sv {
@@ -540,6 +541,46 @@ int reduce_grid(uint64_t work) {
         }                                                                                       \
         CUDA_CHECK(cudaGetLastError());                                                         \
     } while (0)
+
+// Pairs: local index i with bit l cleared and selector (the top remaining bit) fixed.
+//   rank with bit j = 0 holds (0, x): its half with local bit l = 1 trades with the partner's half
+//   with local bit l = 0.  my_bit = this rank's bit j; it handles the pairs whose selector bit equals
+//   my_bit, so the two kernels touch disjoint pairs and need no synchronisation with each other.
+template <typename amp_t>
+__global__ void __launch_bounds__(256)
+    k_peer_swap(amp_t *__restrict__ mine, amp_t *__restrict__ peer, uint64_t npairs, int lbit,
+                int selbit, int my_bit) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < npairs;
+         k += stride) {
+        // k enumerates local indices with bits {lbit, selbit} removed (lbit != selbit)
+        const int p0 = lbit < selbit ? lbit : selbit, p1 = lbit < selbit ? selbit : lbit;
+        uint64_t i = insert_zero(insert_zero(k, p0), p1);
+        i |= static_cast<uint64_t>(my_bit) << selbit;
+        const uint64_t im = i | (static_cast<uint64_t>(1 - my_bit) << lbit); // my half to give away
+        const uint64_t ip = i | (static_cast<uint64_t>(my_bit) << lbit);     // partner's half
+        const amp_t a = mine[im];
+        const amp_t b = peer[ip];
+        mine[im] = b;
+        peer[ip] = a;
+    }
+}
+void launch_peer_swap(int dtype, void *mine, void *peer, int n_local, int lbit, int my_bit,
+                      cudaStream_t st) {
+    // selector: the highest local bit that is not lbit (keeps each warp on one contiguous run)
+    const int selbit = (lbit == n_local - 1) ? n_local - 2 : n_local - 1;
+    const uint64_t npairs = uint64_t(1) << (n_local - 2);
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((npairs + 255) / 256, 148 * 16));
+    if (dtype == 1)
+        k_peer_swap<double2><<<grid, 256, 0, st>>>(static_cast<double2 *>(mine),
+                                                   static_cast<double2 *>(peer), npairs, lbit,
+                                                   selbit, my_bit);
+    else
+        k_peer_swap<float2><<<grid, 256, 0, st>>>(static_cast<float2 *>(mine),
+                                                  static_cast<float2 *>(peer), npairs, lbit, selbit,
+                                                  my_bit);
+    CUDA_CHECK(cudaGetLastError());
+}
 
 void launch_set_basis(int dtype, void *state, uint64_t len, uint64_t index, cudaStream_t st) {
     const int grid = reduce_grid(len);

@@ -27,6 +27,13 @@ void launch_axpy(int dtype, double ar, double ai, const void *x, void *y, uint64
 void launch_matk(int dtype, void *state, int n_eff, const double2 *d_mat, const int *h_bits, int k,
                  cudaStream_t st);
 
+// ---- multi-GPU: in-place exchange of rank bit j with local bit l through NVLink peer memory.
+// `mine` / `peer` are the two shards (peer = IPC-mapped pointer of rank ^ (1 << j)); this rank
+// swaps the pairs (mine[i | my_half], peer[i | peer_half]) whose selector bit equals `which`, the
+// partner does the other half, so each NVLink direction carries S/4 reads + S/4 writes.
+void launch_peer_swap(int dtype, void *mine, void *peer, int n_local, int lbit, int my_bit,
+                      cudaStream_t st);
+
 // ---- reductions: every kernel writes kReduceBlocks x nv partials; finalize sums them (fixed order)
 void launch_norm2(int dtype, const void *state, uint64_t len, double *d_partials, cudaStream_t st);
 void launch_dot(int dtype, const void *x, const void *y, uint64_t len, double *d_partials,

@@ -314,8 +314,7 @@ double expval_obs(const State &sv, const Obs &ob) {
     if (ob.pauli_terms(sv.num_qubits(), 1.0, terms) && terms.size() == 1) {
         static const cplx ipow[4] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
         const PauliWord &w = terms[0].second;
-        if (!(w.x >> sv.num_local()))
-            return terms[0].first * sv.expval_pauli(w.x, w.z, ipow[w.ny & 3]);
+        return terms[0].first * sv.expval_pauli(w.x, w.z, ipow[w.ny & 3]);
     }
     auto tmp = sv.clone();
     ob.apply_in_place(*tmp);

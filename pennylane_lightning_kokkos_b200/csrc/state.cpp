@@ -73,32 +73,53 @@ std::shared_ptr<CsrDevice> csr_upload(int device, const cplx *data, const uint64
 
 State::State(int num_qubits, int dtype, int device, int rank, int world, const void *nccl_id)
     : n_(num_qubits), dtype_(dtype), device_(device), rank_(rank), world_(world) {
-    B2_ABORT_IF(dtype != 0 && dtype != 1, "dtype must be B2SV_C64 (0) or B2SV_C128 (1)");
-    B2_ABORT_IF(num_qubits < 1 || num_qubits > 60, "number of qubits out of range");
+    init_common(nccl_id);
+}
+
+State::State(const State &like, int)
+    : n_(like.n_), dtype_(like.dtype_), device_(like.device_), rank_(like.rank_),
+      world_(like.world_) {
+    comm_ = like.comm_;
+    if (comm_) { // every state of a communicator lives on one stream, so NCCL calls stay ordered
+        stream_ = like.stream_;
+        owns_stream_ = false;
+    }
+    fuse_ = like.fuse_;
+    init_common(nullptr);
+}
+
+void State::init_common(const void *nccl_id) {
+    B2_ABORT_IF(dtype_ != 0 && dtype_ != 1, "dtype must be B2SV_C64 (0) or B2SV_C128 (1)");
+    B2_ABORT_IF(n_ < 1 || n_ > 60, "number of qubits out of range");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     B2_ABORT_IF(e != cudaSuccess || ndev == 0,
                 "no CUDA device available: b2sv has no CPU fallback (" +
                     std::string(cudaGetErrorString(e)) + ")");
-    B2_ABORT_IF(device < 0 || device >= ndev, "device_id out of range");
+    B2_ABORT_IF(device_ < 0 || device_ >= ndev, "device_id out of range");
     CUDA_CHECK(cudaSetDevice(device_));
-    gbits_ = log2_exact(world);
-    B2_ABORT_IF(rank < 0 || rank >= world, "rank out of range");
-    B2_ABORT_IF(num_qubits - gbits_ < 1, "too few qubits for this many ranks");
+    gbits_ = log2_exact(world_);
+    B2_ABORT_IF(rank_ < 0 || rank_ >= world_, "rank out of range");
+    B2_ABORT_IF(n_ - gbits_ < 1, "too few qubits for this many ranks");
     n_local_ = n_ - gbits_;
     tile_config(dtype_, &B_, &R_);
     n_eff_ = std::max(n_local_, B_);
-    B2_ABORT_IF(world > 1 && n_local_ < B_ + gbits_,
+    B2_ABORT_IF(world_ > 1 && n_local_ < B_ + gbits_,
                 "sharded states need at least tile_bits + log2(world) local qubits");
-    CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    if (!stream_)
+        CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     e = cudaMalloc(&d_state_, alloc_length() * amp_bytes());
     B2_ABORT_IF(e != cudaSuccess, std::string("cannot allocate the state vector: ") +
                                       cudaGetErrorString(e));
     CUDA_CHECK(cudaMalloc(&d_partials_, sizeof(double) * kReduceBlocks * kMaxReduceVals));
     CUDA_CHECK(cudaMalloc(&d_out_, sizeof(double) * 64));
     CUDA_CHECK(cudaMallocHost(&h_out_, sizeof(double) * 64));
-    if (world_ > 1)
-        comm_ = comm_create(rank_, world_, nccl_id, device_);
+    if (world_ > 1) {
+        if (!comm_)
+            comm_ = std::shared_ptr<Comm>(comm_create(rank_, world_, nccl_id, device_), comm_destroy);
+        l2p_.resize(n_);
+        comm_map_peers(comm_.get(), d_state_, peers_, stream_);
+    }
     reset();
 }
 
@@ -106,8 +127,12 @@ State::~State() {
     cudaSetDevice(device_);
     if (stream_)
         cudaStreamSynchronize(stream_);
-    if (comm_)
-        comm_destroy(comm_);
+    if (comm_) {
+        comm_barrier(comm_.get(), stream_); // nobody is still swapping through this shard
+        cudaStreamSynchronize(stream_);
+        comm_unmap_peers(comm_.get(), peers_);
+    }
+    comm_.reset();
     for (void *p : scratch_)
         cudaFree(p);
     cudaFree(d_state_);
@@ -115,7 +140,7 @@ State::~State() {
     cudaFree(d_out_);
     if (h_out_)
         cudaFreeHost(h_out_);
-    if (stream_)
+    if (stream_ && owns_stream_)
         cudaStreamDestroy(stream_);
 }
 
@@ -128,10 +153,12 @@ void State::sync() const {
 void State::reset() { set_basis_state(0); }
 void State::init_zeros() {
     CUDA_CHECK(cudaSetDevice(device_));
+    reset_layout();
     CUDA_CHECK(cudaMemsetAsync(d_state_, 0, alloc_length() * amp_bytes(), stream_));
 }
 void State::set_basis_state(uint64_t index) {
     CUDA_CHECK(cudaSetDevice(device_));
+    reset_layout();
     B2_ABORT_IF(n_ < 64 && index >= (uint64_t(1) << n_), "basis-state index out of range");
     const uint64_t owner = index >> n_local_;
     const uint64_t local = (owner == static_cast<uint64_t>(rank_)) ? (index & (local_length() - 1))
@@ -170,12 +197,14 @@ void State::set_state_vector(const uint64_t *indices, const cplx *values, size_t
 void State::h2d(const void *host, size_t length) {
     CUDA_CHECK(cudaSetDevice(device_));
     B2_ABORT_IF(length != local_length(), "HostToDevice: length does not match the state vector");
+    reset_layout();
     CUDA_CHECK(cudaMemcpyAsync(d_state_, host, length * amp_bytes(), cudaMemcpyHostToDevice, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 void State::d2h(void *host, size_t length) const {
     CUDA_CHECK(cudaSetDevice(device_));
     B2_ABORT_IF(length != local_length(), "DeviceToHost: length does not match the state vector");
+    normalize_layout();
     CUDA_CHECK(cudaMemcpyAsync(host, d_state_, length * amp_bytes(), cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
@@ -187,11 +216,11 @@ void State::copy_from(const State &o) {
     CUDA_CHECK(cudaMemcpyAsync(d_state_, o.d_state_, alloc_length() * amp_bytes(),
                                cudaMemcpyDeviceToDevice, stream_));
     order_after(o.stream_, stream_);
+    l2p_ = o.l2p_;
 }
 std::unique_ptr<State> State::clone() const {
-    B2_ABORT_IF(world_ > 1, "clone of a sharded state must go through b2sv_create_sharded + copy");
-    auto c = std::make_unique<State>(n_, dtype_, device_);
-    c->fuse_ = fuse_;
+    // sharded: collective (every rank clones in the same order); shares communicator and stream
+    auto c = std::make_unique<State>(*this, 0);
     c->copy_from(*this);
     return c;
 }
@@ -215,6 +244,167 @@ void State::release_scratch(void *p) const {
     } else {
         cudaStreamSynchronize(stream_);
         cudaFree(p);
+    }
+}
+
+// ---- sharded layout -------------------------------------------------------------------------------
+void State::reset_layout() const {
+    for (size_t q = 0; q < l2p_.size(); q++)
+        l2p_[q] = static_cast<int>(q);
+}
+uint64_t State::phys_mask(uint64_t m) const {
+    if (l2p_.empty())
+        return m;
+    uint64_t r = 0;
+    while (m) {
+        const int q = __builtin_ctzll(m);
+        r |= bit(l2p_[q]);
+        m &= m - 1;
+    }
+    return r;
+}
+Prim State::to_physical(const Prim &p) const {
+    Prim q = p;
+    if (p.type == Prim::C1Q)
+        q.target = l2p_[p.target];
+    q.cmask = phys_mask(p.cmask);
+    q.cval = phys_mask(p.cval);
+    q.pmask = phys_mask(p.pmask);
+    for (int &b : q.bits)
+        b = l2p_[b];
+    return q;
+}
+void State::swap_phys(int gpos, int lpos) const {
+    B2_ASSERT(comm_ && gpos >= n_local_ && lpos < n_local_);
+    comm_swap_bits(comm_.get(), d_state_, peers_, dtype_, n_local_, gpos - n_local_, lpos, stream_);
+    int qa = -1, qb = -1;
+    for (int q = 0; q < n_; q++) {
+        if (l2p_[q] == gpos)
+            qa = q;
+        if (l2p_[q] == lpos)
+            qb = q;
+    }
+    std::swap(l2p_[qa], l2p_[qb]);
+}
+void State::ensure_local(uint64_t logical_mask) const {
+    if (!comm_)
+        return;
+    CUDA_CHECK(cudaSetDevice(device_));
+    for (int q = 0; q < n_; q++) {
+        if (!((logical_mask >> q) & 1) || l2p_[q] < n_local_)
+            continue;
+        // victim: the highest local position whose logical owner is not wanted
+        int victim = -1;
+        for (int pos = n_local_ - 1; pos >= 0 && victim < 0; pos--)
+            for (int o = 0; o < n_; o++)
+                if (l2p_[o] == pos && !((logical_mask >> o) & 1))
+                    victim = pos;
+        B2_ABORT_IF(victim < 0, "operation acts on more qubits than one shard holds");
+        swap_phys(l2p_[q], victim);
+    }
+}
+void State::normalize_layout() const {
+    if (!comm_)
+        return;
+    CUDA_CHECK(cudaSetDevice(device_));
+    // rank bits first: logical bit P must sit at physical position P for P >= n_local
+    for (int P = n_local_; P < n_; P++) {
+        if (l2p_[P] == P)
+            continue;
+        if (l2p_[P] >= n_local_)
+            ensure_local(bit(P)); // it sits on another rank bit: bring it into the shard first
+        swap_phys(P, l2p_[P]);
+    }
+    // then sort the local positions with SWAPs (free address-map permutations inside tile passes)
+    std::vector<Prim> prims;
+    std::vector<int> cur(l2p_.begin(), l2p_.end());
+    for (int q = 0; q < n_local_; q++) {
+        if (cur[q] == q)
+            continue;
+        int other = -1;
+        for (int o = 0; o < n_local_; o++)
+            if (cur[o] == q)
+                other = o;
+        // exchange the contents of physical positions cur[q] and q
+        const std::vector<int> bits = {cur[q], q};
+        lower_gate("SWAP", bits, false, {}, prims);
+        std::swap(cur[q], cur[other]);
+    }
+    if (!prims.empty())
+        const_cast<State *>(this)->run_local(prims);
+    reset_layout();
+}
+void State::comm_stats(uint64_t *swaps, uint64_t *bytes, int *peer) const {
+    *swaps = *bytes = 0;
+    *peer = 0;
+    if (comm_) {
+        b2sv::comm_stats(comm_.get(), swaps, bytes);
+        *peer = comm_uses_peer(comm_.get()) ? 1 : 0;
+    }
+}
+
+// Sharded gate application. Ops are taken in order as long as their non-diagonal targets are
+// shard-local (controls and phases on rank bits are CTA-uniform predicates, they never move data);
+// when the frontier needs a rank bit, that qubit is swapped with the local qubit whose next use as a
+// target lies farthest in the future, and the walk continues in the new layout.
+void State::apply_prims_sharded(std::vector<Prim> pending) {
+    while (!pending.empty()) {
+        std::vector<Prim> seg, rest;
+        uint64_t T = 0, D = 0; // logical bits touched non-diagonally / diagonally by skipped ops
+        for (const Prim &p : pending) {
+            const uint64_t tm = p.target_mask(), dm = p.support() & ~tm;
+            const bool blocked = (tm & (T | D)) || (dm & T);
+            const bool local = (phys_mask(tm) >> n_local_) == 0;
+            if (!blocked && local) {
+                seg.push_back(to_physical(p));
+            } else {
+                T |= tm;
+                D |= dm;
+                rest.push_back(p);
+            }
+        }
+        if (!seg.empty())
+            run_local(seg);
+        if (rest.empty())
+            break;
+        // rank bits wanted by the frontier, in order of first appearance
+        std::vector<int> need;
+        uint64_t need_mask = 0;
+        for (const Prim &p : rest) {
+            uint64_t tm = p.target_mask();
+            while (tm && static_cast<int>(need.size()) < gbits_) {
+                const int q = __builtin_ctzll(tm);
+                tm &= tm - 1;
+                if (l2p_[q] >= n_local_ && !((need_mask >> q) & 1)) {
+                    need.push_back(q);
+                    need_mask |= bit(q);
+                }
+            }
+            if (static_cast<int>(need.size()) >= gbits_)
+                break;
+        }
+        B2_ASSERT(!need.empty());
+        std::vector<size_t> next_use(n_, rest.size() + 1);
+        for (size_t i = rest.size(); i-- > 0;) {
+            uint64_t tm = rest[i].target_mask();
+            while (tm) {
+                next_use[__builtin_ctzll(tm)] = i;
+                tm &= tm - 1;
+            }
+        }
+        for (int q : need) {
+            int victim = -1;
+            for (int o = 0; o < n_; o++) {
+                if (l2p_[o] >= n_local_ || ((need_mask >> o) & 1))
+                    continue;
+                if (victim < 0 || next_use[o] > next_use[victim] ||
+                    (next_use[o] == next_use[victim] && l2p_[o] > l2p_[victim]))
+                    victim = o;
+            }
+            B2_ASSERT(victim >= 0);
+            swap_phys(l2p_[q], l2p_[victim]);
+        }
+        pending.swap(rest);
     }
 }
 
@@ -275,7 +465,12 @@ void State::apply_prims(std::vector<Prim> prims) {
         return;
     CUDA_CHECK(cudaSetDevice(device_));
     if (comm_)
-        comm_localize(comm_, *this, prims); // global<->local qubit swaps where needed
+        apply_prims_sharded(std::move(prims));
+    else
+        run_local(prims);
+}
+
+void State::run_local(const std::vector<Prim> &prims) {
     SchedConfig cfg;
     cfg.B = B_;
     cfg.R = R_;
@@ -285,6 +480,7 @@ void State::apply_prims(std::vector<Prim> prims) {
     cfg.SW = dtype_ == 1 ? 3 : 4;
     cfg.n_local = n_local_;
     cfg.n_alloc = n_eff_;
+    cfg.fuse = fuse_;
     upload_and_run(build_schedule(prims, cfg));
 }
 
@@ -325,7 +521,7 @@ void State::finish_reduce(int nv, double *out) const {
     launch_finalize(d_partials_, kReduceBlocks, nv, d_out_, stream_);
     reduce_launches += 2;
     if (comm_)
-        comm_allreduce_sum(comm_, d_out_, nv, stream_);
+        comm_allreduce_sum(comm_.get(), d_out_, nv, stream_);
     CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(double) * nv, cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
     for (int i = 0; i < nv; i++)
@@ -351,12 +547,18 @@ void State::inner_product_buf(const void *x, const void *y, double *re, double *
 void State::inner_product(const State &o, double *re, double *im) const {
     B2_ABORT_IF(o.n_ != n_ || o.dtype_ != dtype_ || o.device_ != device_,
                 "state vectors are not compatible");
+    if (!same_layout(o)) {
+        normalize_layout();
+        o.normalize_layout();
+    }
     order_after(stream_, o.stream_);
     inner_product_buf(d_state_, o.d_state_, re, im);
 }
 double State::expval_pauli(uint64_t x, uint64_t z, cplx ph) const {
     CUDA_CHECK(cudaSetDevice(device_));
-    B2_ABORT_IF(x >> n_local_, "Pauli X/Y on a global (rank) qubit needs the apply path");
+    ensure_local(x); // X / Y factors pair amplitudes: those qubits must be shard-local
+    x = phys_mask(x);
+    z = phys_mask(z);
     // Z factors on rank bits contribute a per-rank constant sign
     if (__builtin_popcountll((uint64_t(rank_) << n_local_) & z) & 1)
         ph = -ph;
@@ -371,7 +573,10 @@ double State::expval_named(const std::string &name, const std::vector<int64_t> &
     if (name == "Identity")
         return norm2(); // EVF.hpp:13-28
     B2_ABORT_IF(wires.size() != 1, "named observables act on exactly one wire");
-    const int t = wires_to_bits(wires, n_)[0];
+    const int tq = wires_to_bits(wires, n_)[0];
+    if (name != "PauliZ")
+        ensure_local(bit(tq));
+    const int t = phys_bit(tq);
     const double s = 0.70710678118654752440;
     double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (name == "PauliX") { // EVF.hpp:30-58
@@ -391,10 +596,8 @@ double State::expval_named(const std::string &name, const std::vector<int64_t> &
     } else {
         B2_ABORT("unknown named observable '" + name + "'");
     }
-    if (t >= n_local_) { // global qubit: only diagonal observables are local
-        B2_ABORT_IF(name != "PauliZ", "non-diagonal observable on a global (rank) qubit");
-        return expval_pauli(0, bit(t), 1.0);
-    }
+    if (t >= n_local_) // PauliZ on a rank bit: a per-rank sign
+        return expval_pauli(0, bit(tq), 1.0);
     launch_expval_1q(dtype_, d_state_, local_length(), t, m, d_partials_, stream_);
     double r;
     finish_reduce(1, &r);
@@ -402,12 +605,18 @@ double State::expval_named(const std::string &name, const std::vector<int64_t> &
 }
 double State::expval_matrix(const std::vector<int64_t> &wires, const std::vector<cplx> &mat) const {
     CUDA_CHECK(cudaSetDevice(device_));
-    const std::vector<int> bits = wires_to_bits(wires, n_);
+    std::vector<int> bits = wires_to_bits(wires, n_);
     const size_t k = bits.size();
     B2_ABORT_IF(k == 0, "matrix observable needs at least one wire");
     B2_ABORT_IF(mat.size() != (size_t(1) << (2 * k)), "matrix size does not match the number of wires");
-    for (int b : bits)
-        B2_ABORT_IF(b >= n_local_, "matrix observable on a global (rank) qubit is not supported");
+    {
+        uint64_t m = 0;
+        for (int b : bits)
+            m |= bit(b);
+        ensure_local(m);
+        for (int &b : bits)
+            b = phys_bit(b);
+    }
     double r;
     if (k == 1) { // MK.hpp:283-300
         double m[8];
@@ -446,6 +655,10 @@ double State::expval_csr(const CsrDevice &m) const {
 }
 void State::axpy(cplx alpha, const State &x) {
     CUDA_CHECK(cudaSetDevice(device_));
+    if (!same_layout(x)) {
+        normalize_layout();
+        x.normalize_layout();
+    }
     order_after(stream_, x.stream_);
     launch_axpy(dtype_, alpha.real(), alpha.imag(), x.d_state_, d_state_, local_length(), stream_);
     launches++;

@@ -39,6 +39,8 @@ class State {
   public:
     State(int num_qubits, int dtype, int device, int rank = 0, int world = 1,
           const void *nccl_id = nullptr);
+    // a second state on the communicator and stream of `like` (collective when sharded)
+    explicit State(const State &like, int /*tag*/);
     ~State();
     State(const State &) = delete;
     State &operator=(const State &) = delete;
@@ -76,6 +78,15 @@ class State {
     double apply_generator(const std::string &name, const std::vector<int64_t> &wires);
     void apply_prims(std::vector<Prim> prims);
     void lower(const GateOp &op, bool flip_inverse, std::vector<Prim> &out) const;
+    // ---- sharded layout: logical index bit q lives at physical bit l2p_[q]; physical bits
+    // >= num_local() are the rank bits. Gates that target a rank bit pull it into the shard by a
+    // global<->local qubit swap over NVLink and leave it there (lazy, never undone until needed).
+    int phys_bit(int logical) const { return l2p_.empty() ? logical : l2p_[logical]; }
+    uint64_t phys_mask(uint64_t logical_mask) const;
+    void ensure_local(uint64_t logical_mask) const; // make these logical bits shard-local
+    void normalize_layout() const;                  // back to the identity layout
+    bool same_layout(const State &o) const { return l2p_ == o.l2p_; }
+    void comm_stats(uint64_t *swaps, uint64_t *bytes, int *peer) const;
     void set_fusion(bool f) { fuse_ = f; }
     bool fusion() const { return fuse_; }
 
@@ -103,6 +114,12 @@ class State {
   private:
     void finish_reduce(int nv, double *out) const;
     void upload_and_run(const std::vector<Pass> &passes);
+    void run_local(const std::vector<Prim> &prims);       // prims in PHYSICAL bits, all targets local
+    void apply_prims_sharded(std::vector<Prim> prims);    // prims in logical bits
+    Prim to_physical(const Prim &p) const;
+    void swap_phys(int gpos, int lpos) const;             // rank bit position <-> local position
+    void reset_layout() const;
+    void init_common(const void *nccl_id);
 
     int n_, n_local_, n_eff_, dtype_, device_;
     int rank_, world_, gbits_;
@@ -114,7 +131,10 @@ class State {
     // reductions
     double *d_partials_ = nullptr, *d_out_ = nullptr, *h_out_ = nullptr;
     mutable std::vector<void *> scratch_;
-    Comm *comm_ = nullptr;
+    std::shared_ptr<Comm> comm_;
+    bool owns_stream_ = true;
+    mutable std::vector<int> l2p_;     // empty for single-GPU states
+    mutable std::vector<void *> peers_; // IPC-mapped shards of all ranks (this rank: own buffer)
 };
 
 } // namespace b2sv

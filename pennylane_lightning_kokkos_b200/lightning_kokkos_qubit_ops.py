@@ -264,6 +264,19 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
                 check(lib.b2sv_create(n, dtype_flag, device_id, C.byref(self._h)))
                 self.HostToDevice(arr)
 
+        @classmethod
+        def sharded(cls, num_qubits, device_id, rank, world, nccl_unique_id: bytes):
+            """State of ``num_qubits`` wires sharded over ``world`` GPUs (one process per GPU):
+            rank = top log2(world) index bits = wires 0..g-1.  ``nccl_unique_id`` is the 128-byte
+            id from :func:`pennylane_lightning_kokkos_b200.dist.nccl_unique_id`, identical on all ranks.
+            (New: the reference is single-device)"""
+            self = cls.__new__(cls)
+            self._h = C.c_void_p()
+            buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
+            check(lib.b2sv_create_sharded(int(num_qubits), dtype_flag, int(device_id), int(rank),
+                                          int(world), C.cast(buf, C.c_void_p), C.byref(self._h)))
+            return self
+
         def __del__(self):
             try:
                 if self._h:
@@ -426,6 +439,20 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
 
         def reset_stats(self):
             check(lib.b2sv_reset_stats(self._h))
+
+        def comm_stats(self):
+            sw, by, peer = C.c_uint64(), C.c_uint64(), C.c_int()
+            check(lib.b2sv_comm_stats(self._h, C.byref(sw), C.byref(by), C.byref(peer)))
+            return {"swaps": sw.value, "swap_bytes_per_rank": by.value,
+                    "path": "nvlink-peer-kernel" if peer.value else "nccl-sendrecv"}
+
+        def last_upload_bytes(self):
+            b = C.c_uint64()
+            check(lib.b2sv_last_upload_bytes(self._h, C.byref(b)))
+            return b.value
+
+        def normalize_layout(self):
+            check(lib.b2sv_normalize_layout(self._h))
 
         def sync(self):
             check(lib.b2sv_sync(self._h))

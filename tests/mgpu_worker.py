@@ -1,0 +1,104 @@
+"""Multi-GPU parity worker, launched by torchrun (one rank per GPU) from tests/test_multi_gpu.py.
+
+Every rank applies the same random circuit to a sharded state (rank = top index bits); the shards
+are gathered and compared with (a) the NumPy oracle, (b) the single-GPU engine on rank 0, and the
+all-reduced expectation values / adjoint Jacobian are compared with the oracle's.  Prints one
+"MGPU_OK ..." line on rank 0 when everything agrees.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    from cases import layered_circuit, random_circuit
+    from oracle import np_oracle as npo
+    from pennylane_lightning_kokkos_b200 import dist as b2dist
+    from pennylane_lightning_kokkos_b200 import lightning_kokkos_qubit_ops as ops
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    g = world.bit_length() - 1
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 12 + 2 * g + 1
+    worst = 0.0
+    for dtype, tol in ((np.complex128, 1e-12), (np.complex64, 1e-5)):
+        n_eff = n if dtype == np.complex128 else n + 1
+        for case, circ in (("layers", layered_circuit(n_eff, 2, seed=3)),
+                           ("random", random_circuit(n_eff, 120, seed=5))):
+            sv = b2dist.create_sharded_state(ops, n_eff, dtype, local_rank)
+            sv.apply([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ],
+                     [c[3] for c in circ])
+            stats = sv.comm_stats()
+            # expectation values before normalising the layout (exercise the remapped reductions)
+            ez = [sv.ExpectationValue("PauliZ", [w], [], np.zeros(0)) for w in (0, g, n_eff - 1)]
+            ex = [sv.ExpectationValue("PauliX", [w], [], np.zeros(0)) for w in (0, n_eff - 1)]
+            nloc = 1 << (n_eff - g)
+            mine = np.zeros(nloc, dtype=dtype)
+            sv.DeviceToHost(mine)
+            t = torch.from_numpy(mine.view(np.float64 if dtype == np.complex128 else np.float32)).cuda()
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            full = np.concatenate([p.cpu().numpy() for p in parts]).view(dtype)
+            psi0 = np.zeros(1 << n_eff, dtype=complex)
+            psi0[0] = 1
+            want = npo.apply_ops(psi0, n_eff, circ)
+            err = float(np.max(np.abs(full - want)) / np.max(np.abs(want)))
+            ez_want = [npo.expval(want, n_eff, ("named", "PauliZ", [w])) for w in (0, g, n_eff - 1)]
+            ex_want = [npo.expval(want, n_eff, ("named", "PauliX", [w])) for w in (0, n_eff - 1)]
+            e2 = max(abs(a - b) for a, b in zip(ez + ex, ez_want + ex_want))
+            worst = max(worst, err / tol, e2 / tol)
+            if rank == 0:
+                print(f"  {case} {np.dtype(dtype).name} n={n_eff} world={world}: amp err {err:.2e} "
+                      f"expval err {e2:.2e} swaps {stats['swaps']} path {stats['path']}", flush=True)
+            assert err < tol and e2 < tol, (case, dtype, err, e2)
+            if rank == 0 and dtype == np.complex128:
+                single = ops.LightningKokkos_C128(n_eff)
+                single.apply([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ],
+                             [c[3] for c in circ])
+                ref1 = np.zeros(1 << n_eff, dtype=dtype)
+                single.DeviceToHost(ref1)
+                assert np.max(np.abs(ref1 - full)) < 1e-13
+                del single
+            del sv
+            dist.barrier()
+    # adjoint Jacobian on a sharded state (all-reduced inner products)
+    n_a = 12 + 2 * g
+    circ = [c for c in layered_circuit(n_a, 1, seed=7)]
+    names, wires = [c[0] for c in circ], [c[1] for c in circ]
+    invs, params = [c[2] for c in circ], [c[3] for c in circ]
+    sv = b2dist.create_sharded_state(ops, n_a, np.complex128, local_rank)
+    sv.apply(names, wires, invs, params)
+    obs = [ops.NamedObsKokkos_C128("PauliZ", [0]), ops.NamedObsKokkos_C128("PauliX", [n_a - 1])]
+    adj = ops.AdjointJacobianKokkos_C128()
+    oplist = adj.create_ops_list(names, [np.array(p) for p in params], wires, invs,
+                                 [np.zeros(0, dtype=complex) for _ in names])
+    n_par = sum(1 for p in params if len(p))
+    tp = list(range(n_par))
+    jac = adj.adjoint_jacobian(sv, obs, oplist, tp)
+    psi0 = np.zeros(1 << n_a, dtype=complex)
+    psi0[0] = 1
+    final = npo.apply_ops(psi0, n_a, circ)
+    jac_want = npo.adjoint_jacobian(final, n_a, [("named", "PauliZ", [0]),
+                                                 ("named", "PauliX", [n_a - 1])], circ, tp)
+    ej = float(np.max(np.abs(jac - jac_want)) / max(np.max(np.abs(jac_want)), 1e-300))
+    assert ej < 1e-12, ej
+    del sv
+    dist.barrier()
+    if rank == 0:
+        print(f"MGPU_OK world={world} worst_err_over_tol={worst:.3f} adjoint_rel_err={ej:.2e}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
