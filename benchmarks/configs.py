@@ -1,0 +1,161 @@
+#!/usr/bin/env python
+"""Timings of the other BASELINE.json configs on one B200 (config 2 is bench.py, config 5 is
+bench.py --gpus N).  Prints one JSON line per config; each is checked against the oracle at a
+reduced size in tests/, here only timed at full size (plus cheap invariants).
+
+  config 1: 20-qubit StronglyEntanglingLayers (4 layers) c128, expval(PauliZ) on every wire
+  config 3: 24-qubit hardware-efficient ansatz, 504 params, adjoint Jacobian of a 100-term Pauli H
+  config 4: 20-qubit excitation-gate circuit, CSR sparse-Hamiltonian expval (CSR device resident)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from cases import random_pauli_hamiltonian, sel_circuit  # noqa: E402
+
+
+def split(circ):
+    return ([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ], [c[3] for c in circ])
+
+
+def timed(fn, reps, sync):
+    fn()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = fn()
+    sync()
+    return (time.perf_counter() - t0) / reps, out
+
+
+def config1(ops, reps):
+    n = 20
+    circ = sel_circuit(n, 4, seed=42)
+    names, wires, invs, params = split(circ)
+    sv = ops.LightningKokkos_C128(n)
+
+    def run():
+        sv.resetKokkos() if hasattr(sv, "resetKokkos") else sv.setBasisState(0)
+        sv.apply(names, wires, invs, params)
+        return [sv.ExpectationValue("PauliZ", [w], [], np.zeros(0)) for w in range(n)]
+
+    dt, ez = timed(run, reps, sv.sync)
+    return {"config": 1, "workload": "20q StronglyEntanglingLayers x4 c128 + 20 <Z>", "s_per_circuit": dt,
+            "gates": len(circ), "sweeps": sv.stats()["sweeps"] / (reps + 1), "sum_z": float(np.sum(ez))}
+
+
+def hea_circuit(n, layers, seed=42):
+    rng = np.random.default_rng(seed)
+    ops = []
+    for _ in range(layers):
+        for w in range(n):
+            for g in ("RX", "RY", "RZ"):
+                ops.append((g, [w], False, [float(rng.uniform(0, 2 * np.pi))]))
+        for w in range(n):
+            ops.append(("CNOT", [w, (w + 1) % n], False, []))
+    return ops
+
+
+def config3(ops, reps, n=24, layers=7, terms=100):
+    circ = hea_circuit(n, layers)
+    names, wires, invs, params = split(circ)
+    ham = random_pauli_hamiltonian(n, terms, seed=42)
+    tobs = []
+    for _, word in ham:
+        fac = [ops.NamedObsKokkos_C128(l, [w]) for l, w in word]
+        tobs.append(fac[0] if len(fac) == 1 else ops.TensorProdObsKokkos_C128(fac))
+    H = ops.HamiltonianKokkos_C128(np.array([c for c, _ in ham]), tobs)
+    sv = ops.LightningKokkos_C128(n)
+    t_fwd, _ = timed(lambda: (sv.setBasisState(0), sv.apply(names, wires, invs, params)), reps, sv.sync)
+    adj = ops.AdjointJacobianKokkos_C128()
+    oplist = adj.create_ops_list(names, [np.array(p) for p in params], wires, invs,
+                                 [np.zeros(0, dtype=complex) for _ in names])
+    n_par = sum(1 for p in params if len(p))
+    tp = list(range(n_par))
+    t_adj, jac = timed(lambda: adj.adjoint_jacobian(sv, [H], oplist, tp), reps, sv.sync)
+    S = 16.0 * (1 << n)
+    return {"config": 3, "workload": f"{n}q HEA {layers} layers, {n_par} params, adjoint Jacobian of a "
+            f"{terms}-term Pauli Hamiltonian, c128", "s_per_jacobian": t_adj, "s_forward": t_fwd,
+            "ops": len(circ), "jac_norm": float(np.linalg.norm(jac)),
+            "floor_s_4S_per_op": len(circ) * 4 * S / 6.4562e12}
+
+
+def config4(ops, reps, n=20):
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(42)
+    occ, virt = list(range(n // 2)), list(range(n // 2, n))
+    circ = []
+    for _ in range(50):
+        circ.append(("SingleExcitation", [int(rng.choice(occ)), int(rng.choice(virt))], False,
+                     [float(rng.uniform(-0.5, 0.5))]))
+    for _ in range(100):
+        o = [int(x) for x in rng.choice(occ, size=2, replace=False)]
+        v = [int(x) for x in rng.choice(virt, size=2, replace=False)]
+        circ.append(("DoubleExcitation", o + v, False, [float(rng.uniform(-0.5, 0.5))]))
+    names, wires, invs, params = split(circ)
+    # synthetic "molecular" Hamiltonian: 64 real-weighted Pauli words of weight <= 4 -> CSR
+    ham = random_pauli_hamiltonian(n, 64, seed=7)
+    dim = 1 << n
+    idx = np.arange(dim, dtype=np.int64)
+    mat = sp.csr_matrix((dim, dim), dtype=np.complex128)
+    for c, word in ham:
+        x = z = 0
+        ny = 0
+        for l, w in word:
+            b = 1 << (n - 1 - w)
+            if l in ("PauliX", "PauliY"):
+                x |= b
+            if l in ("PauliZ", "PauliY"):
+                z |= b
+            ny += l == "PauliY"
+        # P|j> = i^ny (-1)^popc(j&z) |j^x>  -> column j, row j^x
+        par = np.zeros(dim, dtype=np.int64)
+        zz = z
+        while zz:
+            bpos = (zz & -zz).bit_length() - 1
+            par ^= (idx >> bpos) & 1
+            zz &= zz - 1
+        vals = c * (1j ** ny) * (1 - 2 * par)
+        mat = mat + sp.csr_matrix((vals, (idx ^ x, idx)), shape=(dim, dim))
+    mat = ((mat + mat.getH()) * 0.5).tocsr()
+    mat.sort_indices()
+    sv = ops.LightningKokkos_C128(n)
+    hf = int("1" * (n // 2) + "0" * (n - n // 2), 2)
+    sv.setBasisState(hf)
+    t_circ, _ = timed(lambda: (sv.setBasisState(hf), sv.apply(names, wires, invs, params)), reps, sv.sync)
+    t_up0 = time.perf_counter()
+    e_cold = sv.ExpectationValue(mat.data, mat.indices.astype(np.uint64), mat.indptr.astype(np.uint64))
+    t_cold = time.perf_counter() - t_up0
+    Hs = ops.SparseHamiltonianKokkos_C128(mat.data, mat.indices.astype(np.uint64),
+                                         mat.indptr.astype(np.uint64), list(range(n)))
+    t_res, e_res = timed(lambda: sv.expval(Hs), reps, sv.sync)
+    nnz = mat.nnz
+    byts = nnz * (16 + 4) + dim * (16 + 8)
+    return {"config": 4, "workload": f"{n}q 50 SingleExcitation + 100 DoubleExcitation, CSR expval "
+            f"(nnz {nnz}), c128", "s_circuit": t_circ, "s_expval_csr_resident": t_res,
+            "s_expval_with_upload": t_cold, "expval": e_res, "expval_upload_path": e_cold,
+            "csr_stream_GBps": byts / t_res / 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,3,4")
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    from pennylane_lightning_kokkos_b200 import lightning_kokkos_qubit_ops as ops
+    fns = {"1": config1, "3": config3, "4": config4}
+    for c in args.configs.split(","):
+        print(json.dumps(fns[c](ops, args.reps)), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -281,6 +281,39 @@ bool lower_gate(const std::string &name, const std::vector<int> &q, bool inv,
     return true;
 }
 
+bool generator_pauli(const std::string &name, const std::vector<int> &q, uint64_t *x, uint64_t *z,
+                     int *ny, double *scale) {
+    *x = *z = 0;
+    *ny = 0;
+    *scale = -0.5;
+    auto all = [&]() {
+        uint64_t m = 0;
+        for (int b : q)
+            m |= bit(b);
+        return m;
+    };
+    if (name == "RX" && q.size() == 1) {
+        *x = bit(q[0]);
+    } else if (name == "RY" && q.size() == 1) {
+        *x = *z = bit(q[0]);
+        *ny = 1;
+    } else if (name == "RZ" && q.size() == 1) {
+        *z = bit(q[0]);
+    } else if (name == "IsingXX" && q.size() == 2) {
+        *x = all();
+    } else if (name == "IsingYY" && q.size() == 2) {
+        *x = *z = all();
+        *ny = 2;
+    } else if (name == "IsingZZ" && q.size() == 2) {
+        *z = all();
+    } else if (name == "MultiRZ" && !q.empty()) {
+        *z = all();
+    } else {
+        return false;
+    }
+    return true;
+}
+
 bool lower_generator(const std::string &name, const std::vector<int> &q, std::vector<Prim> &out,
                      double *scale) {
     auto need = [&](size_t n) {

@@ -66,6 +66,11 @@ bool lower_gate(const std::string &name, const std::vector<int> &bits, bool inve
 // Returns false when no generator exists; *scale receives the reference's scaling factor.
 bool lower_generator(const std::string &name, const std::vector<int> &bits, std::vector<Prim> &out,
                      double *scale);
+// Generators that are plain Pauli words (RX, RY, RZ, IsingXX/YY/ZZ, MultiRZ): x / z masks over
+// index bits and the number of Y factors, G|j> = i^ny (-1)^popc(j & z) |j ^ x>; scale as above.
+// Lets the adjoint sweep take <H_lambda| G |lambda> in one read pass, without forming G|lambda>.
+bool generator_pauli(const std::string &name, const std::vector<int> &bits, uint64_t *x,
+                     uint64_t *z, int *ny, double *scale);
 // Arbitrary matrix on `bits` (bits[0] = MSB of the local index), row-major; inverse = conj-transpose
 // (reference GateFunctors.hpp:15-300, applyMultiQubitOp StateVectorKokkos.hpp:757-796).
 void lower_matrix(const std::vector<int> &bits, bool inverse, const std::vector<cplx> &matrix,

@@ -276,6 +276,42 @@ __global__ void __launch_bounds__(kReduceThreads)
     block_reduce_store<1>(acc, partials);
 }
 
+// <bra| P |ket> with P a Pauli word: one read pass over both vectors, nothing written.
+template <typename amp_t>
+__global__ void __launch_bounds__(kReduceThreads)
+    k_pauli_dot(const amp_t *__restrict__ bra, const amp_t *__restrict__ ket, uint64_t len,
+                uint64_t x, uint64_t z, double phr, double phi, double *__restrict__ partials) {
+    double acc[2] = {0.0, 0.0};
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const uint64_t j = i ^ x;
+        const amp_t a = bra[i], b = ket[j];
+        // (P ket)_i = ph * (-1)^popc(j & z) * ket_j
+        const double sg = (__popcll(j & z) & 1) ? -1.0 : 1.0;
+        const double wr = sg * (phr * b.x - phi * b.y);
+        const double wi = sg * (phr * b.y + phi * b.x);
+        acc[0] += double(a.x) * wr + double(a.y) * wi; // Re conj(a) w
+        acc[1] += double(a.x) * wi - double(a.y) * wr; // Im conj(a) w
+    }
+    block_reduce_store<2>(acc, partials);
+}
+__global__ void k_finalize_scaled(const double *__restrict__ partials, int nblocks, int nv, int which,
+                                  double scale, double *__restrict__ dst) {
+    __shared__ double red[kReduceThreads];
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+        s += partials[b * nv + which];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (static_cast<int>(threadIdx.x) < o)
+            red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        *dst = scale * red[0];
+}
+
 template <typename amp_t>
 __global__ void __launch_bounds__(256)
     k_pauli_sum_apply(const amp_t *__restrict__ in, amp_t *__restrict__ out, uint64_t len,
@@ -660,6 +696,17 @@ void launch_pauli_expval(int dtype, const void *state, uint64_t len, uint64_t x,
     DISPATCH_DTYPE(dtype,
                    (k_pauli_expval<float2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), len, x, z, phr, phi, d_partials)),
                    (k_pauli_expval<double2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), len, x, z, phr, phi, d_partials)));
+}
+void launch_pauli_dot(int dtype, const void *bra, const void *ket, uint64_t len, uint64_t x,
+                      uint64_t z, double phr, double phi, double *d_partials, cudaStream_t st) {
+    DISPATCH_DTYPE(dtype,
+                   (k_pauli_dot<float2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(bra), static_cast<const float2 *>(ket), len, x, z, phr, phi, d_partials)),
+                   (k_pauli_dot<double2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(bra), static_cast<const double2 *>(ket), len, x, z, phr, phi, d_partials)));
+}
+void launch_finalize_scaled(const double *d_partials, int nblocks, int nv, int which, double scale,
+                            double *d_dst, cudaStream_t st) {
+    k_finalize_scaled<<<1, kReduceThreads, 0, st>>>(d_partials, nblocks, nv, which, scale, d_dst);
+    CUDA_CHECK(cudaGetLastError());
 }
 void launch_finalize(const double *d_partials, int nblocks, int nv, double *d_out,
                      cudaStream_t st) {

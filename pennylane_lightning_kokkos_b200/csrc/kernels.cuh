@@ -47,6 +47,12 @@ void launch_pauli_expval(int dtype, const void *state, uint64_t len, uint64_t x,
                          double phr, double phi, double *d_partials, cudaStream_t st);
 void launch_finalize(const double *d_partials, int nblocks, int nv, double *d_out,
                      cudaStream_t st);
+// 2 values: Re, Im of <bra| P |ket>, P|j> = ph * (-1)^popc(j & z) |j ^ x>
+void launch_pauli_dot(int dtype, const void *bra, const void *ket, uint64_t len, uint64_t x,
+                      uint64_t z, double phr, double phi, double *d_partials, cudaStream_t st);
+// *d_dst = scale * sum_b partials[b * nv + which]   (device-resident Jacobian entries)
+void launch_finalize_scaled(const double *d_partials, int nblocks, int nv, int which, double scale,
+                            double *d_dst, cudaStream_t st);
 
 struct PauliTerm {
     uint64_t x, z;

@@ -76,11 +76,11 @@ State::State(int num_qubits, int dtype, int device, int rank, int world, const v
     init_common(nccl_id);
 }
 
-State::State(const State &like, int)
+State::State(const State &like, int share_stream)
     : n_(like.n_), dtype_(like.dtype_), device_(like.device_), rank_(like.rank_),
       world_(like.world_) {
     comm_ = like.comm_;
-    if (comm_) { // every state of a communicator lives on one stream, so NCCL calls stay ordered
+    if (comm_ || share_stream) { // every state of a communicator lives on one stream, so NCCL calls stay ordered
         stream_ = like.stream_;
         owns_stream_ = false;
     }
@@ -221,6 +221,11 @@ void State::copy_from(const State &o) {
 std::unique_ptr<State> State::clone() const {
     // sharded: collective (every rank clones in the same order); shares communicator and stream
     auto c = std::make_unique<State>(*this, 0);
+    c->copy_from(*this);
+    return c;
+}
+std::unique_ptr<State> State::clone_on_stream() const {
+    auto c = std::make_unique<State>(*this, 1);
     c->copy_from(*this);
     return c;
 }
@@ -652,6 +657,45 @@ double State::expval_csr(const CsrDevice &m) const {
     double r;
     finish_reduce(1, &r);
     return r;
+}
+void State::pauli_dot_im_to(const State &bra, uint64_t x, uint64_t z, cplx ph, double factor,
+                            double *d_dst) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(bra.n_ != n_ || bra.dtype_ != dtype_ || bra.device_ != device_,
+                "state vectors are not compatible");
+    if (!same_layout(bra)) {
+        normalize_layout();
+        bra.normalize_layout();
+    }
+    ensure_local(x); // identical layouts -> identical swap decisions on both states
+    bra.ensure_local(x);
+    const uint64_t xp = phys_mask(x), zp = phys_mask(z);
+    if (__builtin_popcountll((uint64_t(rank_) << n_local_) & zp) & 1)
+        ph = -ph;
+    order_after(stream_, bra.stream_);
+    launch_pauli_dot(dtype_, bra.d_state_, d_state_, local_length(), xp, zp & (local_length() - 1),
+                     ph.real(), ph.imag(), d_partials_, stream_);
+    launch_finalize_scaled(d_partials_, kReduceBlocks, 2, 1, factor, d_dst, stream_);
+    order_after(bra.stream_, stream_);
+    reduce_launches += 2;
+}
+void State::dot_im_to(const State &bra, double factor, double *d_dst) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(bra.n_ != n_ || bra.dtype_ != dtype_ || bra.device_ != device_,
+                "state vectors are not compatible");
+    if (!same_layout(bra)) {
+        normalize_layout();
+        bra.normalize_layout();
+    }
+    order_after(stream_, bra.stream_);
+    launch_dot(dtype_, bra.d_state_, d_state_, local_length(), d_partials_, stream_);
+    launch_finalize_scaled(d_partials_, kReduceBlocks, 2, 1, factor, d_dst, stream_);
+    order_after(bra.stream_, stream_);
+    reduce_launches += 2;
+}
+void State::allreduce_device(double *d_buf, int n) const {
+    if (comm_)
+        comm_allreduce_sum(comm_.get(), d_buf, n, stream_);
 }
 void State::axpy(cplx alpha, const State &x) {
     CUDA_CHECK(cudaSetDevice(device_));

@@ -40,7 +40,7 @@ class State {
     State(int num_qubits, int dtype, int device, int rank = 0, int world = 1,
           const void *nccl_id = nullptr);
     // a second state on the communicator and stream of `like` (collective when sharded)
-    explicit State(const State &like, int /*tag*/);
+    explicit State(const State &like, int share_stream);
     ~State();
     State(const State &) = delete;
     State &operator=(const State &) = delete;
@@ -99,6 +99,16 @@ class State {
     double expval_csr(const CsrDevice &m) const;
     double expval_pauli(uint64_t x, uint64_t z, cplx ph) const;
     void axpy(cplx alpha, const State &x);
+    // Adjoint-sweep reductions that stay on the device (no host synchronisation):
+    //   *d_dst = factor * Im <bra| P |this>   with P|j> = ph (-1)^popc(j&z) |j^x>  (logical bits)
+    //   *d_dst = factor * Im <bra|this>
+    // Sharded states write the per-rank partial; the caller all-reduces the whole Jacobian once.
+    void pauli_dot_im_to(const State &bra, uint64_t x, uint64_t z, cplx ph, double factor,
+                         double *d_dst) const;
+    void dot_im_to(const State &bra, double factor, double *d_dst) const;
+    void allreduce_device(double *d_buf, int n) const;
+    // clone that lives on this state's stream (so kernels touching both need no cross-stream events)
+    std::unique_ptr<State> clone_on_stream() const;
 
     // ---- probabilities / sampling
     void probs(const std::vector<int64_t> &wires, double *out) const;
