@@ -348,13 +348,17 @@ def run_b200(args):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                "kernel": "tile_exec_kernel<double,12,4>",
+                "frac": achieved / peaks["hbm_gbs"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                # (profiles/r1_ncu_tile_v11.summary.txt: 17.184 GB + 17.136 GB at n = 30)
+                "traffic": 34.319e9 if args.qubits == 30 else None, "peak_source": which,
+                "kernel": "tile_exec_kernel<double,12,4,256> (persistent, 148 CTAs x 640 threads)",
                 "algorithmic_bytes_per_launch": sweep_bytes,
                 "avg_launch_ms": avg_launch_ms,
                 "note": "achieved = 2*16*2^n bytes per tile-kernel launch / (CUDA-event time of the "
                         "timed region / tile-kernel launches); the region holds only tile-kernel "
-                        "launches and their few-KB descriptor uploads",
+                        "launches (pass descriptors travel as kernel parameters). Sustained figure: "
+                        "the region is ~2 s of back-to-back launches under the 1 kW power cap.",
             },
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": blob_bytes,
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,

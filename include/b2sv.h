@@ -100,6 +100,13 @@ int b2sv_ops_create(int nops, const char *const *names, const double *params, co
                     const double *const *matrices_c128, b2sv_ops **out);
 int b2sv_ops_destroy(b2sv_ops *ops);
 int b2sv_ops_size(const b2sv_ops *ops, int *nops, int *n_par_ops);
+/* Host-only (no device needed): what the fusion scheduler does with `ops` on an n-qubit state --
+ * HBM passes, register rounds, arithmetic ops executed, permutation gates folded into the address
+ * map for free, passes whose last round stores straight to HBM. The reference has no counterpart:
+ * it runs one kernel per gate (StateVectorKokkos.hpp:807-824). */
+int b2sv_plan_ops(const b2sv_ops *ops, int num_qubits, int dtype, uint64_t *passes,
+                  uint64_t *rounds, uint64_t *arithmetic_ops, uint64_t *absorbed_perms,
+                  uint64_t *fused_stores);
 
 /* ---- measurements (MeasuresKokkos.hpp) ----------------------------------------------- */
 int b2sv_expval_named(const b2sv_state *s, const char *name, const int64_t *wires, int nw,

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "b2sv_apply_generator": (C.c_int, [vp, C.c_char_p, i64p, C.c_int, C.c_int, dp]),
     "b2sv_set_fusion": (C.c_int, [vp, C.c_int]),
     "b2sv_get_stats": (C.c_int, [vp, u64p, u64p]),
+    "b2sv_plan_ops": (C.c_int, [vp, C.c_int, C.c_int, u64p, u64p, u64p, u64p, u64p]),
     "b2sv_comm_stats": (C.c_int, [vp, u64p, u64p, ip]),
     "b2sv_last_upload_bytes": (C.c_int, [vp, u64p]),
     "b2sv_normalize_layout": (C.c_int, [vp]),

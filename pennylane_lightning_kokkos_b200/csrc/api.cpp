@@ -249,6 +249,55 @@ int b2sv_normalize_layout(b2sv_state *s) {
     return guard([&] { st(s).normalize_layout(); });
 }
 
+// Host-only: how the fusion scheduler would execute `ops` on an n-qubit state (no device needed).
+int b2sv_plan_ops(const b2sv_ops *ops, int num_qubits, int dtype, uint64_t *passes,
+                  uint64_t *rounds, uint64_t *arithmetic_ops, uint64_t *absorbed_perms,
+                  uint64_t *fused_stores) {
+    return guard([&] {
+        B2_ABORT_IF(!ops, "null op list");
+        B2_ABORT_IF(dtype != 0 && dtype != 1, "dtype must be B2SV_C64 (0) or B2SV_C128 (1)");
+        std::vector<Prim> prims;
+        for (const GateOp &op : ops->d.ops) {
+            if (op.name == "Identity")
+                continue;
+            const std::vector<int> bits = wires_to_bits(op.wires, num_qubits);
+            if (!lower_gate(op.name, bits, op.inverse, op.params, prims)) {
+                B2_ABORT_IF(op.matrix.empty(), "operation '" + op.name +
+                                                   "' is not a named gate and no matrix was provided");
+                lower_matrix(bits, op.inverse, op.matrix, prims);
+            }
+        }
+        SchedConfig cfg;
+        tile_config(dtype, &cfg.B, &cfg.R);
+        cfg.SW = dtype == 1 ? 3 : 4;
+        cfg.n_local = num_qubits;
+        cfg.n_alloc = std::max(num_qubits, cfg.B);
+        uint64_t np = 0, nr = 0, na = 0, nabs = 0, nf = 0;
+        if (!prims.empty())
+            for (const Pass &ps : build_schedule(prims, cfg)) {
+                np++;
+                if (ps.is_matk) {
+                    na++;
+                    continue;
+                }
+                nr += ps.hdr.n_rounds;
+                na += ps.hdr.n_ops;
+                nabs += ps.n_absorbed;
+                nf += ps.hdr.fused_store;
+            }
+        if (passes)
+            *passes = np;
+        if (rounds)
+            *rounds = nr;
+        if (arithmetic_ops)
+            *arithmetic_ops = na;
+        if (absorbed_perms)
+            *absorbed_perms = nabs;
+        if (fused_stores)
+            *fused_stores = nf;
+    });
+}
+
 int b2sv_ops_create(int nops, const char *const *names, const double *params, const int *nparams,
                     const int64_t *wires, const int *nwires, const int *inverses,
                     const double *const *matrices, b2sv_ops **out) {

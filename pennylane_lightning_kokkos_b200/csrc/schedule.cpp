@@ -366,30 +366,46 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
             B2_ABORT_IF(n_rounds >= kMaxRounds, "internal: too many rounds in a pass");
             uint32_t reg_mask = 0; // over tile-local positions
             int reg_free = R;
-            Blocker rb;
+            // Two sweeps over the remaining ops. The first only takes gates on the lane bits
+            // (tile positions 0..4): doing them early keeps those bits out of the LAST round's
+            // register set, which is what allows the fused store (coalesced HBM writes need the
+            // lanes on the low index bits). The second sweep takes whatever else fits. An op taken
+            // in the first sweep was not blocked by anything before it, so it commutes with every
+            // earlier op that is still waiting.
             std::vector<int> now, later;
-            for (int i : remaining) {
-                const Prim &p = prims[i];
-                // an absorbable permutation waits for the next round boundary, where it is free
-                bool fits = !rb.blocked(p) && perm_class(p) == 0;
-                if (fits && p.type == Prim::C1Q) {
-                    const int j = tile_pos(p.target);
-                    if (!(reg_mask & (1u << j))) {
-                        if (reg_free > 0) {
-                            reg_mask |= 1u << j;
-                            reg_free--;
-                        } else {
-                            fits = false;
+            std::vector<char> taken(remaining.size(), 0);
+            for (int sweep = cfg.fuse_store ? 0 : 1; sweep < 2; sweep++) {
+                Blocker rb;
+                for (size_t r = 0; r < remaining.size(); r++) {
+                    if (taken[r])
+                        continue;
+                    const Prim &p = prims[remaining[r]];
+                    // an absorbable permutation waits for the next round boundary, where it is free
+                    bool fits = !rb.blocked(p) && perm_class(p) == 0;
+                    if (fits && sweep == 0)
+                        fits = p.type == Prim::C1Q && tile_pos(p.target) < 5;
+                    if (fits && p.type == Prim::C1Q) {
+                        const int j = tile_pos(p.target);
+                        if (!(reg_mask & (1u << j))) {
+                            if (reg_free > 0) {
+                                reg_mask |= 1u << j;
+                                reg_free--;
+                            } else {
+                                fits = false;
+                            }
                         }
                     }
-                }
-                if (fits) {
-                    now.push_back(i);
-                } else {
-                    rb.skip(p);
-                    later.push_back(i);
+                    if (fits) {
+                        now.push_back(remaining[r]);
+                        taken[r] = 1;
+                    } else {
+                        rb.skip(p);
+                    }
                 }
             }
+            for (size_t r = 0; r < remaining.size(); r++)
+                if (!taken[r])
+                    later.push_back(remaining[r]);
             B2_ASSERT(!now.empty());
             // register slots in order of first use by the round's ops, then the padding bits
             std::vector<int> slot_bits;

@@ -71,25 +71,32 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
                      smem_u32(mbar))
                  : "memory");
 }
+// Polling must not steal issue slots from the arithmetic warps of the same SM sub-partition: the
+// try_wait carries a suspend-time hint and a missed poll backs off with nanosleep.
+template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
     const uint32_t a = smem_u32(mbar);
     uint32_t ok;
     uint32_t spins = 0;
-    do {
-        if (++spins == (1u << 26))
-            __trap(); // a lost hand-off must surface as a CUDA error, never as a hung GPU
+    while (true) {
         asm volatile("{\n .reg .pred p;\n"
-                     " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
                      " selp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(ok)
-                     : "r"(a), "r"(parity)
+                     : "r"(a), "r"(parity), "r"(static_cast<uint32_t>(SLEEP_NS * 4))
                      : "memory");
-    } while (!ok);
+        if (ok)
+            break;
+        __nanosleep(SLEEP_NS);
+        if (++spins == (1u << 24))
+            __trap(); // a lost hand-off must surface as a CUDA error, never as a hung GPU
+    }
 }
 // one lane polls, the rest of the warp parks at the warp barrier (no 32-wide spinning)
+template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait_warp(uint64_t *mbar, uint32_t parity) {
     if ((threadIdx.x & 31) == 0)
-        mbar_wait(mbar, parity);
+        mbar_wait<SLEEP_NS>(mbar, parity);
     __syncwarp();
 }
 __device__ __forceinline__ void group_sync(int id, int nthreads) {
@@ -438,7 +445,7 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
         for (uint32_t k = 0; k < n_mine; k++) {
             const int bi = k % kTileBuffers;
             if (k >= kTileBuffers)
-                mbar_wait_warp(&empty[bi], ((k / kTileBuffers) - 1) & 1u);
+                mbar_wait_warp<400>(&empty[bi], ((k / kTileBuffers) - 1) & 1u);
             const uint64_t tb = tile_base_of(k);
             amp_t *buf = tiles + bi * TILE;
 #pragma unroll 8
@@ -468,7 +475,7 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
                     x ^= hdr.cx[c].vec;
             xoff[tid] = x;
         }
-        mbar_wait_warp(&full[bi], (k / kTileBuffers) & 1u);
+        mbar_wait_warp<40>(&full[bi], (k / kTileBuffers) & 1u);
         group_sync(1 + grp, GT);
 
 #pragma unroll 1

@@ -38,8 +38,8 @@ int main(int argc, char **argv) {
             kinds[o.kind & OPF_KIND_MASK]++;
             uncond += (o.kind & OPF_UNCOND) ? 1 : 0;
         }
-        printf("pass %2zu: ops %2d (gen %d real %d perm %d diag %d; uncond %d) rounds %d absorbed %d cx %d tile:",
-               i, p.hdr.n_ops, kinds[0], kinds[1], kinds[2], kinds[3], uncond, p.hdr.n_rounds,
+        printf("pass %2zu: fused %d ops %2d (gen %d real %d perm %d diag %d; uncond %d) rounds %d absorbed %d cx %d tile:",
+               i, p.hdr.fused_store, p.hdr.n_ops, kinds[0], kinds[1], kinds[2], kinds[3], uncond, p.hdr.n_rounds,
                p.n_absorbed, p.hdr.n_cx);
         for (int j = 0; j < cfg.B; j++)
             printf(" %d", p.hdr.tile_bits[j]);

@@ -239,6 +239,14 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
             except Exception:
                 pass
 
+        def plan(self, num_qubits):
+            """Host-only: what the fusion scheduler does with this op list on ``num_qubits`` wires
+            (b2sv_plan_ops).  Works without a GPU."""
+            v = [C.c_uint64() for _ in range(5)]
+            check(lib.b2sv_plan_ops(self._h, int(num_qubits), dtype_flag, *[C.byref(x) for x in v]))
+            return dict(zip(("passes", "rounds", "arithmetic_ops", "absorbed_perms", "fused_stores"),
+                            (x.value for x in v)))
+
         def __len__(self):
             return len(self.names)
 
