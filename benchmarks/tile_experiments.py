@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Developer experiment driver: times BASELINE config 2 (30 q c128 layers) under different tile
+executor / scheduler knobs, one subprocess per setting (the knobs are read once per process).
+Prints one JSON line per setting: ms per step, sweeps, ms per sweep, achieved GB/s per sweep and,
+with B2SV_TILE_PROF=1, the phase-timer breakdown (fractions of the lead threads' lifetime).
+
+usage: python benchmarks/tile_experiments.py [--qubits 30] [--layers 4] [--steps 3]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SETTINGS = [
+    {},
+    {"B2SV_STORE_MODE": "1"},
+    {"B2SV_TILE_PROF": "1"},
+    {"B2SV_MAX_HEAVY": "4"},
+    {"B2SV_MAX_HEAVY": "4", "B2SV_STORE_MODE": "1"},
+    {"B2SV_MAX_HEAVY": "6"},
+    {"B2SV_MAX_HEAVY": "12"},
+    {"B2SV_MAX_HEAVY": "12", "B2SV_TILE_PROF": "1"},
+    {"B2SV_MAX_HEAVY": "16"},
+    {"B2SV_TILE_LOW": "4", "B2SV_MAX_HEAVY": "12"},
+    {"B2SV_TILE_LOW": "4"},
+]
+
+
+def child(args):
+    import ctypes as C
+
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from bench import layer_circuit
+    from pennylane_lightning_kokkos_b200 import _lib
+    from pennylane_lightning_kokkos_b200 import lightning_kokkos_qubit_ops as ops
+
+    n = args.qubits
+    layers = int(os.environ.get("_layers", args.layers))
+    circ = layer_circuit(n, layers, seed=42)
+    sv = ops.LightningKokkos_C128(n)
+    had = ops.OpsStructKokkos_C128(["Hadamard"] * n, [[] for _ in range(n)], [[w] for w in range(n)],
+                                   [False] * n)
+    sv.apply_ops(had)
+    oplist = ops.OpsStructKokkos_C128([c[0] for c in circ], [c[3] for c in circ], [c[1] for c in circ],
+                                      [c[2] for c in circ])
+    sv.apply_ops(oplist)
+    sv.sync()
+    prof = np.zeros(8, dtype=np.uint64)
+    _lib.lib.b2sv_debug_tile_prof(prof.ctypes.data_as(C.POINTER(C.c_uint64)))
+    sv.reset_stats()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sv.apply_ops(oplist)
+    sv.sync()
+    dt = (time.perf_counter() - t0) / args.steps
+    st = sv.stats()
+    sweeps = st["sweeps"] / args.steps
+    _lib.lib.b2sv_debug_tile_prof(prof.ctypes.data_as(C.POINTER(C.c_uint64)))
+    norm = sv.ExpectationValue("Identity", [0], [], np.zeros(0))
+    out = {"ms_per_step": dt * 1e3, "sweeps": sweeps, "ms_per_sweep": dt * 1e3 / sweeps,
+           "gbs_per_sweep": 2 * 16 * (1 << n) / (dt / sweeps) / 1e9, "norm": norm, "layers": layers}
+    if prof[5]:
+        p = [float(x) for x in prof]
+        out["prof"] = {"worker_wait_frac": p[0] / (p[0] + p[1]), "producer_wait_frac": p[2] / (p[2] + p[3]),
+                       "worker_cycles_per_tile": (p[0] + p[1]) / p[4], "worker_wait_cycles_per_tile": p[0] / p[4],
+                       "cta_cycles_per_sweep": p[5] / (148.0 * st["sweeps"]),
+                       "last_round_cycles_per_tile": p[6] / p[4], "other_rounds_cycles_per_tile": p[7] / p[4]}
+    print("RESULT " + json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--qubits", type=int, default=30)
+    ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--child", action="store_true")
+    ap.add_argument("--only", type=int, default=-1)
+    args = ap.parse_args()
+    if args.child:
+        return child(args)
+    for i, s in enumerate(SETTINGS):
+        if args.only >= 0 and i != args.only:
+            continue
+        env = dict(os.environ)
+        env.update(s)
+        cmd = [sys.executable, os.path.abspath(__file__), "--child", "--qubits", str(args.qubits),
+               "--layers", str(args.layers), "--steps", str(args.steps)]
+        try:
+            r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=180)
+            res = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+            out = json.loads(res[-1][7:]) if res else {"error": (r.stderr or r.stdout)[-400:]}
+        except subprocess.TimeoutExpired:
+            out = {"error": "timeout"}
+        print(json.dumps({"setting": s, **out}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "b2sv_last_upload_bytes": (C.c_int, [vp, u64p]),
     "b2sv_normalize_layout": (C.c_int, [vp]),
     "b2sv_reset_stats": (C.c_int, [vp]),
+    "b2sv_debug_tile_prof": (C.c_int, [u64p]),
     "b2sv_ops_create": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), dp, ip, i64p, ip, ip,
                                   C.POINTER(dp), C.POINTER(vp)]),
     "b2sv_ops_destroy": (C.c_int, [vp]),

@@ -229,6 +229,15 @@ int b2sv_reset_stats(b2sv_state *s) {
         st(s).reduce_launches = 0;
     });
 }
+int b2sv_debug_tile_prof(uint64_t *out8) {
+    return guard([&] {
+        B2_ABORT_IF(!out8, "null output");
+        unsigned long long v[8];
+        tile_prof_read(v);
+        for (int i = 0; i < 8; i++)
+            out8[i] = v[i];
+    });
+}
 int b2sv_comm_stats(const b2sv_state *s, uint64_t *swaps, uint64_t *swap_bytes, int *peer_path) {
     return guard([&] {
         uint64_t a = 0, b = 0;
@@ -270,6 +279,7 @@ int b2sv_plan_ops(const b2sv_ops *ops, int num_qubits, int dtype, uint64_t *pass
         SchedConfig cfg;
         tile_config(dtype, &cfg.B, &cfg.R);
         cfg.SW = dtype == 1 ? 3 : 4;
+        cfg.f32 = dtype != 1;
         cfg.n_local = num_qubits;
         cfg.n_alloc = std::max(num_qubits, cfg.B);
         uint64_t np = 0, nr = 0, na = 0, nabs = 0, nf = 0;
@@ -283,7 +293,7 @@ int b2sv_plan_ops(const b2sv_ops *ops, int num_qubits, int dtype, uint64_t *pass
                 nr += ps.hdr.n_rounds;
                 na += ps.hdr.n_ops;
                 nabs += ps.n_absorbed;
-                nf += ps.hdr.fused_store;
+                nf += ps.hdr.fused_store != 0;
             }
         if (passes)
             *passes = np;

@@ -2,7 +2,9 @@
 #include "schedule.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
+#include <functional>
 
 namespace b2sv {
 namespace {
@@ -104,6 +106,115 @@ OpKind classify(const Prim &p) {
     return KIND_GENERAL;
 }
 
+// ---- factored form of a 2x2 (see DevDense) ---------------------------------------------------------
+// M = diag(P0, P1) * [[1, t01], [t10, 1]] * diag(1, q1) with |q1| = 1 and t01, t10 real:
+//   out0 = P0 * (v0 + t01 * (q1 v1)),   out1 = P1 * ((q1 v1) + t10 * v0).
+// Exists iff m00, m11 != 0 and arg(m01 m10) = arg(m00 m11) (mod pi) -- true for every unitary --
+// and is accepted when both shears are moderate (|t| <= kShearMax; unitaries with a dominant
+// diagonal have |t| <= 1) and the neglected imaginary part is at rounding level.
+struct Factored {
+    cplx q1, P0, P1;
+    double t01, t10;
+};
+constexpr double kShearMax = 2.0;
+constexpr double kShearImagTol = 32.0 * 2.220446049250313e-16;
+
+bool factor_2x2(const cplx m[4], Factored &f) {
+    const cplx a = m[0], b = m[1], c = m[2], d = m[3];
+    const double na = std::abs(a), nd = std::abs(d), nb = std::abs(b), nc = std::abs(c);
+    if (!(na > 0.0) || !(nd > 0.0) || !std::isfinite(na + nd + nb + nc))
+        return false;
+    if (nb > kShearMax * na || nc > kShearMax * nd)
+        return false;
+    cplx q1(1.0, 0.0);
+    if (nb >= nc && nb > 0.0) {
+        const cplx z = b / a;
+        q1 = z / std::abs(z);
+    } else if (nc > 0.0) {
+        const cplx z = c / d;
+        q1 = std::conj(z) / std::abs(z);
+    }
+    const cplx t01 = b / (a * q1), t10 = c * q1 / d;
+    if (std::abs(t01.imag()) > kShearImagTol * (1.0 + std::abs(t01)) ||
+        std::abs(t10.imag()) > kShearImagTol * (1.0 + std::abs(t10)))
+        return false;
+    f.q1 = q1;
+    f.P0 = a;
+    f.P1 = d / q1;
+    f.t01 = t01.real();
+    f.t10 = t10.real();
+    return true;
+}
+
+bool is_free_2x2(const Prim &p) { return p.type == Prim::C1Q && p.cmask == 0 && p.tag < 0; }
+
+// An uncontrolled 2x2 whose anti-diagonal dominates is rewritten as X * (X M): X M has the dominant
+// diagonal the factored form wants, and the X is absorbed into the tile's address map for free.
+std::vector<Prim> split_antidiagonal(const std::vector<Prim> &prims) {
+    std::vector<Prim> out;
+    out.reserve(prims.size() + prims.size() / 2);
+    for (const Prim &p : prims) {
+        if (!is_free_2x2(p) || classify(p) == KIND_PERM ||
+            std::abs(p.m[1]) * std::abs(p.m[2]) <= std::abs(p.m[0]) * std::abs(p.m[3])) {
+            out.push_back(p);
+            continue;
+        }
+        const cplx xm[4] = {p.m[2], p.m[3], p.m[0], p.m[1]}; // X M: rows swapped
+        Factored f;
+        if (!factor_2x2(xm, f)) {
+            out.push_back(p);
+            continue;
+        }
+        Prim q = p;
+        if (xm[1] == cplx(0.0) && xm[2] == cplx(0.0)) { // X M is diagonal (e.g. PauliY)
+            q.type = Prim::DIAG;
+            q.pmask = bit(p.target);
+            q.target = -1;
+            q.m[0] = xm[0];
+            q.m[1] = xm[3];
+            q.m[2] = q.m[3] = 0;
+        } else {
+            for (int i = 0; i < 4; i++)
+                q.m[i] = xm[i];
+        }
+        out.push_back(q);
+        Prim x;
+        x.type = Prim::C1Q;
+        x.target = p.target;
+        x.m[0] = x.m[3] = 0;
+        x.m[1] = x.m[2] = 1;
+        out.push_back(x);
+    }
+    return out;
+}
+
+template <typename real>
+void fill_dense(DevDense &dd, const std::vector<Factored> &fs) {
+    std::memset(&dd, 0, sizeof(dd));
+    const int G = static_cast<int>(fs.size());
+    real *pre = reinterpret_cast<real *>(dd.pre), *post = reinterpret_cast<real *>(dd.post);
+    real *t = reinterpret_cast<real *>(dd.t);
+    for (int j = 0; j < (1 << G); j++) {
+        cplx a(1.0, 0.0), b(1.0, 0.0);
+        for (int k = 0; k < G; k++) {
+            if ((j >> k) & 1) {
+                a *= fs[k].q1;
+                b *= fs[k].P1;
+            } else {
+                b *= fs[k].P0;
+            }
+        }
+        pre[2 * j] = static_cast<real>(a.real());
+        pre[2 * j + 1] = static_cast<real>(a.imag());
+        post[2 * j] = static_cast<real>(b.real());
+        post[2 * j + 1] = static_cast<real>(b.imag());
+    }
+    for (int k = 0; k < G; k++) {
+        t[2 * k] = static_cast<real>(fs[k].t01);
+        t[2 * k + 1] = static_cast<real>(fs[k].t10);
+    }
+}
+
 // Dependency filter shared by pass- and round-level greedy selection.
 struct Blocker {
     uint64_t t = 0; // bits some skipped op acts on non-diagonally
@@ -192,7 +303,9 @@ DevOp make_devop(const Prim &p, const uint8_t *tile_bits, int B, const uint8_t *
 std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedConfig &cfg) {
     const int B = cfg.B, R = cfg.R, low = std::min(cfg.low, cfg.B);
     B2_ASSERT(B <= kMaxTileBits && R <= kMaxRegBits && R <= B);
-    const std::vector<Prim> prims = fuse_single_qubit(prims_in);
+    const bool factor = cfg.factor && cfg.free_perms && cfg.fuse;
+    const std::vector<Prim> prims =
+        factor ? split_antidiagonal(fuse_single_qubit(prims_in)) : fuse_single_qubit(prims_in);
     const int N = static_cast<int>(prims.size());
     std::vector<char> done(N, 0);
     std::vector<Pass> passes;
@@ -434,6 +547,23 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                         tile_pos(p.target) == slot_bits[k];
             }
             ps.hdr.round_kind[n_rounds] = dense ? static_cast<uint8_t>(now.size()) : 0;
+            if (dense && factor && now.size() >= 2 &&
+                ps.dense.size() < static_cast<size_t>(kMaxDense)) {
+                std::vector<Factored> fs(now.size());
+                bool ok = true;
+                for (size_t k = 0; ok && k < now.size(); k++)
+                    ok = factor_2x2(prims[now[k]].m, fs[k]);
+                if (ok) {
+                    DevDense dd;
+                    if (cfg.f32)
+                        fill_dense<float>(dd, fs);
+                    else
+                        fill_dense<double>(dd, fs);
+                    ps.hdr.round_dense[n_rounds] = static_cast<uint8_t>(ps.dense.size());
+                    ps.hdr.round_kind[n_rounds] = static_cast<uint8_t>(8 + now.size());
+                    ps.dense.push_back(dd);
+                }
+            }
             uint8_t *rbits = ps.hdr.round_regbits[n_rounds];
             {
                 std::vector<uint32_t> free_cols; // ((1 << j) << 16) | storage column of free bit j
@@ -480,53 +610,122 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
             reset_logical();
         }
         if (n_rounds >= 1 && cfg.fuse_store) {
-            // Fused store: possible when five thread-id bits of the last round can be given free
-            // tile bits whose images under the trailing permutations stay inside logical bits 0..4
-            // and span them -- then every warp-wide store covers whole contiguous runs.
             const int last = n_rounds - 1;
             uint32_t reg_mask = 0;
             for (int k = 0; k < R; k++)
                 reg_mask |= 1u << ps.hdr.round_regbits[last][k];
-            std::vector<int> lanes, others;
-            std::vector<uint32_t> basis;
-            for (int j = 0; j < B; j++) {
-                if (reg_mask & (1u << j))
-                    continue;
-                uint32_t v = Lcol[j];
-                bool ok = v < 32u && lanes.size() < 5;
-                if (ok) {
-                    for (uint32_t b : basis)
-                        v = std::min(v, v ^ b);
-                    ok = v != 0;
-                }
-                if (ok) {
-                    basis.push_back(v);
-                    std::sort(basis.rbegin(), basis.rend());
-                    lanes.push_back(j);
-                } else {
-                    others.push_back(j);
-                }
-            }
-            if (lanes.size() == 5) {
-                auto spread = [&](uint32_t v) {
-                    uint64_t g = 0;
-                    for (int j = 0; j < B; j++)
-                        if ((v >> j) & 1u)
-                            g |= bit(ps.hdr.tile_bits[j]);
-                    return g;
-                };
-                lanes.insert(lanes.end(), others.begin(), others.end());
+            auto spread = [&](uint32_t v) {
+                uint64_t g = 0;
+                for (int j = 0; j < B; j++)
+                    if ((v >> j) & 1u)
+                        g |= bit(ps.hdr.tile_bits[j]);
+                return g;
+            };
+            // thread-id bit k of the last round <-> free tile bit lanes[k]; fills the store maps
+            auto commit = [&](const std::vector<int> &lanes, int mode) {
                 for (size_t k = 0; k < lanes.size(); k++) {
                     const int j = lanes[k];
                     ps.hdr.round_col[last][k] =
                         ((1u << j) << 16) | phys_slot(McolLast[j], B, cfg.SW);
                     ps.hdr.store_free[k] = spread(Lcol[j]);
+                    ps.hdr.store_free_l[k] = static_cast<uint16_t>(Lcol[j]);
                 }
-                for (int k = 0; k < R; k++)
-                    ps.hdr.store_reg[k] = spread(Lcol[ps.hdr.round_regbits[last][k]]);
-                for (int c = 0; c < n_cx; c++)
-                    ps.hdr.store_cx[c] = ps.hdr.cx[c].round == n_rounds ? spread(cx_logical[c]) : 0;
-                ps.hdr.fused_store = 1;
+                for (int k = 0; k < R; k++) {
+                    const uint32_t v = Lcol[ps.hdr.round_regbits[last][k]];
+                    ps.hdr.store_reg[k] = spread(v);
+                    ps.hdr.store_reg_l[k] = static_cast<uint16_t>(v);
+                }
+                for (int c = 0; c < n_cx; c++) {
+                    const uint32_t v = ps.hdr.cx[c].round == n_rounds ? cx_logical[c] : 0;
+                    ps.hdr.store_cx[c] = spread(v);
+                    ps.hdr.store_cx_l[c] = static_cast<uint16_t>(v);
+                }
+                ps.hdr.fused_store = static_cast<uint8_t>(mode);
+            };
+            std::vector<int> free_js;
+            for (int j = 0; j < B; j++)
+                if (!(reg_mask & (1u << j)))
+                    free_js.push_back(j);
+            if (cfg.store_mode == 2) {
+                // Staged store: any lane assignment is correct; pick the SW lowest thread-id bits
+                // (= the lanes of one shared-memory wavefront) so that the index-order scatter --
+                // and, when possible, the round's gather too -- is free of bank conflicts.
+                const uint32_t bank_mask = (1u << cfg.SW) - 1u;
+                auto rank_ok = [&](const std::vector<int> &sel, bool storage) {
+                    std::vector<uint32_t> basis;
+                    for (int j : sel) {
+                        uint32_t v = (storage ? phys_slot(McolLast[j], B, cfg.SW) : Lcol[j]) & bank_mask;
+                        for (uint32_t b : basis)
+                            v = std::min(v, v ^ b);
+                        if (v == 0)
+                            return false;
+                        basis.push_back(v);
+                        std::sort(basis.rbegin(), basis.rend());
+                    }
+                    return true;
+                };
+                std::vector<int> best;
+                int best_score = 0;
+                const int nf = static_cast<int>(free_js.size());
+                std::vector<int> idx(cfg.SW);
+                // enumerate SW-subsets of the free bits (at most C(9,4) = 126)
+                std::function<void(int, int)> rec = [&](int pos, int start) {
+                    if (best_score == 2)
+                        return;
+                    if (pos == cfg.SW) {
+                        std::vector<int> sel;
+                        for (int i : idx)
+                            sel.push_back(free_js[i]);
+                        if (!rank_ok(sel, false))
+                            return;
+                        const int score = rank_ok(sel, true) ? 2 : 1;
+                        if (score > best_score) {
+                            best_score = score;
+                            best = sel;
+                        }
+                        return;
+                    }
+                    for (int i = start; i < nf; i++) {
+                        idx[pos] = i;
+                        rec(pos + 1, i + 1);
+                    }
+                };
+                if (nf >= cfg.SW)
+                    rec(0, 0);
+                if (best_score > 0) {
+                    std::vector<int> lanes = best;
+                    for (int j : free_js)
+                        if (std::find(best.begin(), best.end(), j) == best.end())
+                            lanes.push_back(j);
+                    commit(lanes, 2);
+                }
+            }
+            if (!ps.hdr.fused_store) {
+                // Direct store from registers: possible when five thread-id bits of the last round can
+                // be given free tile bits whose images under the trailing permutations stay inside
+                // logical bits 0..4 and span them -- then every warp-wide store covers whole runs.
+                std::vector<int> lanes, others;
+                std::vector<uint32_t> basis;
+                for (int j : free_js) {
+                    uint32_t v = Lcol[j];
+                    bool ok = v < 32u && lanes.size() < 5;
+                    if (ok) {
+                        for (uint32_t b : basis)
+                            v = std::min(v, v ^ b);
+                        ok = v != 0;
+                    }
+                    if (ok) {
+                        basis.push_back(v);
+                        std::sort(basis.rbegin(), basis.rend());
+                        lanes.push_back(j);
+                    } else {
+                        others.push_back(j);
+                    }
+                }
+                if (lanes.size() == 5) {
+                    lanes.insert(lanes.end(), others.begin(), others.end());
+                    commit(lanes, 1);
+                }
             }
         }
         for (int j = 0; j < B; j++)

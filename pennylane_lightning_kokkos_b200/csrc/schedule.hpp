@@ -22,7 +22,8 @@ constexpr int kMaxOpsPerPass = 80;
 constexpr int kMaxTileBits = 16;
 constexpr int kMaxRegBits = 5;
 constexpr int kMaxFreeBits = 12; // tile bits that are not register bits (= log2 threads)
-constexpr int kMaxCx = 24;       // conditional address toggles per pass
+constexpr int kMaxCx = 32;       // conditional address toggles per pass
+constexpr int kMaxDense = 12;    // factored dense rounds per pass
 
 enum OpKind : uint8_t { KIND_GENERAL = 0, KIND_REAL = 1, KIND_PERM = 2, KIND_DIAG = 3 };
 // flag bits stored in DevOp::kind above the OpKind
@@ -43,6 +44,20 @@ struct alignas(16) DevOp {
 };
 static_assert(sizeof(DevOp) == 112, "DevOp layout");
 
+// Factored dense round (see schedule.cpp factor_2x2): every gate k of the round is written as
+//   M_k = diag(P0_k, P1_k) * [[1, t01_k], [t10_k, 1]] * diag(1, q1_k)      (t real, |t| <~ 1)
+// so the round is  post[s] * (prod_k shear_k) * pre[s]  with per-slot constants
+//   pre[j] = prod_k q1_k^bit_k(j),  post[j] = prod_k P{bit_k(j)}_k,   j over the G gate slots:
+// 2 FMAs per amplitude and gate + two complex multiplies per amplitude and round, instead of 8
+// multiply-adds per amplitude and gate. Tables are stored in the state's own precision
+// (16 x double2 or 32 x float2 = 256 bytes each).
+struct alignas(16) DevDense {
+    unsigned char pre[256];
+    unsigned char post[256];
+    unsigned char t[96]; // (t01_k, t10_k) per gate, in the state's real type
+};
+static_assert(sizeof(DevDense) == 608, "DevDense layout");
+
 struct DevCx { // address toggle: from round `round` on, slot ^= vec when (tile_base & gcm) == gcv
     uint64_t gcm, gcv;
     uint16_t vec;   // phys(M e_t) at the time the X was absorbed
@@ -57,15 +72,21 @@ struct alignas(16) DevPassHeader {
     int32_t n_cx;
     uint8_t tile_bits[kMaxTileBits];  // ascending bit positions; tile_bits[j]=j for j<low_bits
     uint8_t round_regbits[kMaxRounds][8]; // logical tile-local positions held in registers, by slot
-    // 0: generic round (op interpreter); g >= 1: "dense" round = exactly g uncontrolled 2x2 gates,
-    // the k-th one on register slot k (straight-line code, no per-op dispatch)
+    // 0: generic round (op interpreter); 1 <= g <= 5: "dense" round = exactly g uncontrolled 2x2
+    // gates, the k-th one on register slot k (straight-line code, no per-op dispatch);
+    // 8 + g: the same in factored form, constants in PassParams::dense[round_dense[rd]]
     uint8_t round_kind[kMaxRounds];
+    uint8_t round_dense[kMaxRounds];
+    uint8_t pad3_[8];
     // tile id -> index with the tile bits cleared: base = OR_k ((id & seg_mask[k]) << seg_shift[k]),
     // one segment per run of consecutive non-tile index bits
     uint32_t seg_mask[kMaxTileBits + 1];
     uint8_t seg_shift[kMaxTileBits + 1];
     uint8_t n_seg;
-    // fused store: the last round writes its registers straight to HBM (no scatter, no store phase)
+    // how the tile leaves the SM: 0 = store phase (worker threads copy shared -> HBM through the
+    // final address map); 1 = the last round writes its registers straight to HBM; 2 = staged: the
+    // last round scatters the tile into shared memory in index order and the store warps stream
+    // its rows to HBM with bulk async copies while the workers start their next tile
     uint8_t fused_store;
     uint8_t pad2_[13];
     // global index offsets (already pushed through the permutations absorbed after the last round):
@@ -73,6 +94,12 @@ struct alignas(16) DevPassHeader {
     uint64_t store_free[kMaxFreeBits];
     uint64_t store_reg[8];
     uint64_t store_cx[kMaxCx];
+    // the same three as tile-local logical indices (staged store: the last round scatters the tile
+    // into shared memory in index order and bulk-copy engines stream its rows to HBM)
+    uint16_t store_free_l[kMaxFreeBits];
+    uint16_t store_reg_l[8];
+    uint16_t store_cx_l[kMaxCx];
+    uint16_t pad4_[4];
     uint16_t round_begin[kMaxRounds + 1]; // op index ranges per round
     uint16_t pad_[3];
     // storage offset phys(M e_r) of register bit s in round rd
@@ -89,6 +116,7 @@ static_assert(sizeof(DevPassHeader) % 16 == 0, "header must be copyable in 16-by
 struct PassParams {
     DevPassHeader hdr;
     DevOp ops[kMaxOpsPerPass];
+    DevDense dense[kMaxDense];
 };
 static_assert(sizeof(PassParams) <= 32000, "kernel parameter space is 32764 bytes");
 
@@ -97,6 +125,7 @@ struct Pass {
     Prim matk;              // when is_matk
     DevPassHeader hdr{};    // otherwise
     std::vector<DevOp> ops;
+    std::vector<DevDense> dense; // factored dense rounds
     std::vector<int> tags;  // per op: Prim::tag
     int n_absorbed = 0;     // permutation primitives folded into the address map
 };
@@ -111,7 +140,10 @@ struct SchedConfig {
     bool fuse = true;  // false: one pass per primitive group (reference schedule)
     bool free_perms = true; // fold CNOT / X into the address map
     bool fuse_store = true; // let the last round of a pass write straight to HBM when coalescing allows
+    int store_mode = 2;     // preferred DevPassHeader::fused_store mode when fuse_store is on
     int max_heavy = 8;      // arithmetic ops per pass before the pass turns FP64-bound
+    bool f32 = false;       // complex64 state: factored-round tables are stored as float
+    bool factor = true;     // factored dense rounds (D * shear * D form of the fused 2x2s)
 };
 
 // Shared-memory swizzle (same function as tile_kernel.cu phys<B,SW>): XOR-folds every higher

@@ -483,6 +483,13 @@ void State::run_local(const std::vector<Prim> &prims) {
     if (const char *e = getenv("B2SV_MAX_HEAVY"))
         cfg.max_heavy = std::max(1, atoi(e));
     cfg.SW = dtype_ == 1 ? 3 : 4;
+    cfg.f32 = dtype_ != 1;
+    if (const char *e = getenv("B2SV_FACTOR"))
+        cfg.factor = atoi(e) != 0;
+    if (const char *e = getenv("B2SV_STORE_MODE")) { // 0 store phase, 1 direct from registers, 2 staged
+        cfg.store_mode = std::max(0, std::min(2, atoi(e)));
+        cfg.fuse_store = cfg.store_mode != 0;
+    }
     cfg.n_local = n_local_;
     cfg.n_alloc = n_eff_;
     cfg.fuse = fuse_;
@@ -513,8 +520,12 @@ void State::upload_and_run(const std::vector<Pass> &passes) {
             B2_ASSERT(ps.ops.size() <= static_cast<size_t>(kMaxOpsPerPass));
             params->hdr = ps.hdr;
             std::memcpy(params->ops, ps.ops.data(), sizeof(DevOp) * ps.ops.size());
+            B2_ASSERT(ps.dense.size() <= static_cast<size_t>(kMaxDense));
+            if (!ps.dense.empty())
+                std::memcpy(params->dense, ps.dense.data(), sizeof(DevDense) * ps.dense.size());
             launch_tile_pass(dtype_, d_state_, *params, n_eff_, rank_bits, stream_);
-            last_upload_bytes_ += sizeof(DevPassHeader) + sizeof(DevOp) * ps.ops.size();
+            last_upload_bytes_ += sizeof(DevPassHeader) + sizeof(DevOp) * ps.ops.size() +
+                                  sizeof(DevDense) * ps.dense.size();
         }
         sweeps++;
         launches++;

@@ -99,6 +99,22 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t *mbar, uint32_t parity) 
         mbar_wait<SLEEP_NS>(mbar, parity);
     __syncwarp();
 }
+// bulk async copy shared -> global (one contiguous run), tracked by the issuing thread's bulk group
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
+                 "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { // the sources have been read (reusable)
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+// generic-proxy writes to shared memory become visible to the async proxy (the bulk copy engine)
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
 __device__ __forceinline__ void group_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -318,6 +334,47 @@ __device__ __forceinline__ void dense_round(amp_t (&a)[NS], const DevOp *ops) {
         }
     }
 }
+// The same round in factored form (DevDense): per-slot phase, G real shears (one FMA per real
+// number and gate), per-slot scale. 4 + 2 G + 4 multiply-adds per amplitude instead of 8 G.
+template <int G, int R, int NS, typename amp_t, typename real>
+__device__ __forceinline__ void dense_factored(amp_t (&a)[NS], const DevDense &dd) {
+    constexpr int GG = G < R ? G : R;
+    constexpr int GM = (1 << GG) - 1;
+    const amp_t *pre = reinterpret_cast<const amp_t *>(dd.pre);
+    const amp_t *post = reinterpret_cast<const amp_t *>(dd.post);
+    const real *t = reinterpret_cast<const real *>(dd.t);
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        if ((s & GM) == 0)
+            continue; // pre[0] = 1
+        const amp_t p = pre[s & GM];
+        const amp_t v = a[s];
+        a[s].x = p.x * v.x - p.y * v.y;
+        a[s].y = p.x * v.y + p.y * v.x;
+    }
+#pragma unroll
+    for (int k = 0; k < GG; k++) {
+        const real t01 = t[2 * k], t10 = t[2 * k + 1];
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            if (s & (1 << k))
+                continue;
+            const int s1 = s | (1 << k);
+            const amp_t v0 = a[s], v1 = a[s1];
+            a[s].x = fma(t01, v1.x, v0.x);
+            a[s].y = fma(t01, v1.y, v0.y);
+            a[s1].x = fma(t10, v0.x, v1.x);
+            a[s1].y = fma(t10, v0.y, v1.y);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const amp_t p = post[s & GM];
+        const amp_t v = a[s];
+        a[s].x = p.x * v.x - p.y * v.y;
+        a[s].y = p.x * v.y + p.y * v.x;
+    }
+}
 template <int R, int NS, typename amp_t>
 __device__ __forceinline__ void scatter_round(amp_t *tile, const amp_t (&a)[NS], uint32_t pb,
                                               const uint32_t (&poff)[R]) {
@@ -356,13 +413,38 @@ __device__ __forceinline__ void store_round(amp_t *__restrict__ state, const amp
         state[x] = a[s];
     }
 }
+// last round of a staged pass: registers -> shared memory in (final, logical) index order, so that
+// every run of 2^low amplitudes is one contiguous piece the bulk-copy engine can stream to HBM
 template <int R, int NS, int NF, typename amp_t>
-__device__ __forceinline__ void finish_round(bool fused, amp_t *__restrict__ state, amp_t *tile,
+__device__ __forceinline__ void stage_round(amp_t *tile, const amp_t (&a)[NS],
+                                            const DevPassHeader &ph, uint64_t tbr, int tid) {
+    uint32_t i0 = 0;
+#pragma unroll
+    for (int c = 0; c < NF; c++)
+        i0 ^= (0u - ((static_cast<uint32_t>(tid) >> c) & 1u)) & ph.store_free_l[c];
+    for (int c = 0; c < ph.n_cx; c++)
+        if ((tbr & ph.cx[c].gcm) == ph.cx[c].gcv)
+            i0 ^= ph.store_cx_l[c];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        uint32_t x = i0;
+#pragma unroll
+        for (int c = 0; c < R; c++)
+            if (s & (1 << c))
+                x ^= ph.store_reg_l[c];
+        tile[x] = a[s];
+    }
+}
+// mode: 0 = scatter back in place, 1 = registers -> HBM, 2 = stage in index order
+template <int R, int NS, int NF, typename amp_t>
+__device__ __forceinline__ void finish_round(int mode, amp_t *__restrict__ state, amp_t *tile,
                                              const amp_t (&a)[NS], uint32_t pb,
                                              const uint32_t (&poff)[R], const DevPassHeader &ph,
                                              uint64_t tb, uint64_t tbr, int tid) {
-    if (fused)
+    if (mode == 1)
         store_round<R, NS, NF>(state, a, ph, tb, tbr, tid);
+    else if (mode == 2)
+        stage_round<R, NS, NF>(tile, a, ph, tbr, tid);
     else
         scatter_round<R, NS>(tile, a, pb, poff);
 }
@@ -371,20 +453,26 @@ __device__ __forceinline__ void finish_round(bool fused, amp_t *__restrict__ sta
 // The pass descriptor travels as a __grid_constant__ kernel parameter (constant bank): no upload,
 // and the dense rounds read their gate matrices through uniform constant loads instead of holding
 // them in 16 vector registers per thread.
-constexpr int kTileBuffers = 3;
 constexpr int kProducerThreads = 128; // one warpgroup that does nothing but stream tiles into shared memory
 
-template <typename real, int B, int R, int GT>
-__global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
+// Optional phase timers (B2SV_TILE_PROF=1): cycles summed over the lead thread of every worker group
+// / producer warpgroup of every CTA. [0] workers waiting for a tile, [1] workers busy on tiles,
+// [2] producers waiting for a free buffer, [3] producers issuing copies, [4] tiles, [5] CTA lifetime,
+// [6] workers in the last (fused-store) round of a tile, [7] workers in the other rounds.
+__device__ unsigned long long g_tile_prof[8];
+
+template <typename real, int B, int R, int GT, int NG, int NB, bool PROF>
+__global__ void __launch_bounds__(NG * GT + kProducerThreads, 1)
     tile_exec_kernel(typename AmpT<real>::type *__restrict__ state,
                      const __grid_constant__ PassParams pp, uint64_t rank_bits,
                      uint32_t n_tiles) {
+    constexpr int kTileBuffers = NB;
     using amp_t = typename AmpT<real>::type;
     constexpr int SW = (sizeof(amp_t) == 16) ? 3 : 4;
     constexpr int NS = 1 << R;
     constexpr int TILE = 1 << B;
     constexpr int NF = B - R; // non-register tile bits = thread-id bits within a group
-    constexpr int NTHREADS = 2 * GT + kProducerThreads;
+    constexpr int NTHREADS = NG * GT + kProducerThreads;
     static_assert((1 << NF) == GT, "one register group per thread");
     static_assert(NF <= kMaxFreeBits, "too many thread-id bits");
     constexpr int EPT = TILE / GT; // amplitudes per thread in the store phase (= NS)
@@ -394,8 +482,10 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
     DevOp *sops = reinterpret_cast<DevOp *>(smem_raw + kTileBuffers * sizeof(amp_t) * TILE);
     uint64_t *rowoff = reinterpret_cast<uint64_t *>(sops + kMaxOpsPerPass);
     __shared__ DevPassHeader hdr;
-    __shared__ uint32_t xoff_all[2][kMaxRounds + 1];
-    __shared__ __align__(8) uint64_t full[kTileBuffers], empty[kTileBuffers];
+    __shared__ uint32_t xoff_all[NG][kMaxRounds + 1];
+    __shared__ __align__(8) uint64_t full[kTileBuffers], empty[kTileBuffers], computed[kTileBuffers];
+    static_assert(NG == 2, "one store warp per worker group: the helper warpgroup has 2 + 2 warps");
+    constexpr int kLoadThreads = 64; // helper warps 0-1 stream tiles in, warps 2-3 stream staged tiles out
 
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(&pp.hdr);
@@ -408,8 +498,9 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
         for (int i = threadIdx.x; i < n_ops * static_cast<int>(sizeof(DevOp) / 16); i += NTHREADS)
             odst[i] = osrc[i];
         if (threadIdx.x < kTileBuffers) {
-            mbar_init(&full[threadIdx.x], kProducerThreads);
+            mbar_init(&full[threadIdx.x], kLoadThreads);
             mbar_init(&empty[threadIdx.x], 1);
+            mbar_init(&computed[threadIdx.x], 1);
         }
     }
     __syncthreads();
@@ -438,22 +529,62 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
         return tb;
     };
 
-    if (threadIdx.x >= 2 * GT) {
-        // ---- producer warps: HBM -> shared (identity address map), one tile ahead of the workers
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n");
-        const int ptid = threadIdx.x - 2 * GT;
+    long long t_start = 0;
+    if constexpr (PROF)
+        t_start = clock64();
+    if (threadIdx.x >= NG * GT) {
+        // ---- helper warpgroup
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
+        const int ptid = threadIdx.x - NG * GT;
+        if (ptid >= kLoadThreads) {
+            // store warps (one per worker group): stream staged tiles to HBM with bulk async copies,
+            // then hand the buffer back to the load warps
+            if (pp.hdr.fused_store != 2)
+                return;
+            const int g = (ptid - kLoadThreads) >> 5, lane = ptid & 31;
+            const uint32_t row_bytes = static_cast<uint32_t>(sizeof(amp_t)) << low;
+            const int n_rows = 1 << (B - low);
+            for (uint32_t k = g; k < n_mine; k += NG) {
+                const int bi = k % kTileBuffers;
+                mbar_wait_warp<100>(&computed[bi], (k / kTileBuffers) & 1u);
+                const uint64_t tb = tile_base_of(k);
+                const unsigned char *buf = reinterpret_cast<const unsigned char *>(tiles + bi * TILE);
+                for (int r = lane; r < n_rows; r += 32)
+                    bulk_store(&state[tb | rowoff[r]], buf + static_cast<size_t>(r) * row_bytes, row_bytes);
+                bulk_commit();
+                bulk_wait_read_all();
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&empty[bi]);
+            }
+            return;
+        }
+        // load warps: HBM -> shared (swizzled slots), running ahead of the workers
+        long long p_wait = 0, p_t0 = 0;
         for (uint32_t k = 0; k < n_mine; k++) {
             const int bi = k % kTileBuffers;
+            if constexpr (PROF)
+                p_t0 = clock64();
             if (k >= kTileBuffers)
                 mbar_wait_warp<400>(&empty[bi], ((k / kTileBuffers) - 1) & 1u);
+            if constexpr (PROF)
+                p_wait += clock64() - p_t0;
             const uint64_t tb = tile_base_of(k);
             amp_t *buf = tiles + bi * TILE;
 #pragma unroll 8
-            for (int e = 0; e < TILE / kProducerThreads; e++) {
-                const uint32_t i = e * kProducerThreads + ptid;
+            for (int e = 0; e < TILE / kLoadThreads; e++) {
+                const uint32_t i = e * kLoadThreads + ptid;
                 cp_async_amp(&buf[phys<B, SW>(i)], &state[tb | rowoff[i >> low] | (i & lowmask)]);
             }
             cp_async_arrive(&full[bi]);
+        }
+        if constexpr (PROF) {
+            if (ptid == 0) {
+                const long long life = clock64() - t_start;
+                atomicAdd(&g_tile_prof[2], static_cast<unsigned long long>(p_wait));
+                atomicAdd(&g_tile_prof[3], static_cast<unsigned long long>(life - p_wait));
+                atomicAdd(&g_tile_prof[5], static_cast<unsigned long long>(life));
+            }
         }
         return;
     }
@@ -463,7 +594,8 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
     const int grp = threadIdx.x / GT;
     const int tid = threadIdx.x % GT;
     uint32_t *xoff = xoff_all[grp];
-    for (uint32_t k = grp; k < n_mine; k += 2) {
+    long long w_wait = 0, w_t0 = 0, w_tiles = 0, w_last = 0, w_round = 0, w_r0 = 0;
+    for (uint32_t k = grp; k < n_mine; k += NG) {
         const int bi = k % kTileBuffers;
         amp_t *tile = tiles + bi * TILE;
         const uint64_t tb = tile_base_of(k);
@@ -475,8 +607,14 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
                     x ^= hdr.cx[c].vec;
             xoff[tid] = x;
         }
+        if constexpr (PROF)
+            w_t0 = clock64();
         mbar_wait_warp<40>(&full[bi], (k / kTileBuffers) & 1u);
         group_sync(1 + grp, GT);
+        if constexpr (PROF) {
+            w_wait += clock64() - w_t0;
+            w_tiles++;
+        }
 
 #pragma unroll 1
         for (int rd = 0; rd < n_rounds; rd++) {
@@ -492,6 +630,8 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
             for (int s = 0; s < R; s++)
                 poff[s] = hdr.round_poff[rd][s];
             const int o_begin = pp.hdr.round_begin[rd], o_end = pp.hdr.round_begin[rd + 1];
+            if constexpr (PROF)
+                w_r0 = clock64();
             amp_t a[NS];
 #pragma unroll
             for (int s = 0; s < NS; s++) {
@@ -508,10 +648,12 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
             const int kind = pp.hdr.round_kind[rd];
             // fused store: the last round's registers go straight to HBM; the tile buffer is free
             // as soon as every thread of the group has gathered from it
-            const bool fused = pp.hdr.fused_store && rd == n_rounds - 1;
+            // staged store: the last round scatters in index order (after every gather of the group
+            // is done) and the group's store warp streams the buffer out in the background
+            const int fused = rd == n_rounds - 1 ? pp.hdr.fused_store : 0;
             if (fused) {
                 group_sync(1 + grp, GT);
-                if (tid == 0)
+                if (fused == 1 && tid == 0)
                     mbar_arrive(&empty[bi]);
             }
             if (kind == 0) {
@@ -523,6 +665,17 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
                 // dense round: gate k acts on register slot k; each case is straight-line code from
                 // the gathered registers to the scatter, so ptxas renames freely (no moves)
                 switch (kind) {
+#define B2_FACT(G)                                                                              \
+    case 8 + G:                                                                                 \
+        dense_factored<G, R, NS, amp_t, real>(a, pp.dense[pp.hdr.round_dense[rd]]);             \
+        finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, \
+                                tid);                                                           \
+        break;
+                    B2_FACT(2)
+                    B2_FACT(3)
+                    B2_FACT(4)
+                    B2_FACT(5)
+#undef B2_FACT
                 case 1:
                     dense_round<1, R, NS, amp_t, real>(a, pp.ops + o_begin);
                     finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
@@ -545,11 +698,23 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
                     break;
                 }
             }
-            if (!fused)
+            if (fused == 2) {
+                fence_async_smem();
                 group_sync(1 + grp, GT);
+                if (tid == 0)
+                    mbar_arrive(&computed[bi]);
+            } else if (!fused) {
+                group_sync(1 + grp, GT);
+            }
+            if constexpr (PROF) {
+                if (fused)
+                    w_last += clock64() - w_r0;
+                else
+                    w_round += clock64() - w_r0;
+            }
         }
         if (pp.hdr.fused_store && n_rounds > 0)
-            continue; // stored from registers, buffer already released
+            continue; // stored from registers or handed to the store warp
 
         // ---- shared -> HBM through the final address map
         {
@@ -577,13 +742,23 @@ __global__ void __launch_bounds__(2 * GT + kProducerThreads, 1)
         if (tid == 0)
             mbar_arrive(&empty[bi]);
     }
+    if constexpr (PROF) {
+        if (tid == 0) {
+            const long long life = clock64() - t_start;
+            atomicAdd(&g_tile_prof[0], static_cast<unsigned long long>(w_wait));
+            atomicAdd(&g_tile_prof[1], static_cast<unsigned long long>(life - w_wait));
+            atomicAdd(&g_tile_prof[4], static_cast<unsigned long long>(w_tiles));
+            atomicAdd(&g_tile_prof[6], static_cast<unsigned long long>(w_last));
+            atomicAdd(&g_tile_prof[7], static_cast<unsigned long long>(w_round));
+        }
+    }
 }
 
 // ---- host side ----------------------------------------------------------------------------------
 namespace {
 constexpr int kMinLow = 4;
-template <typename real, int B> constexpr size_t tile_smem_bytes() {
-    return kTileBuffers * sizeof(typename AmpT<real>::type) * (size_t(1) << B) +
+template <typename real, int B, int NB> constexpr size_t tile_smem_bytes() {
+    return NB * sizeof(typename AmpT<real>::type) * (size_t(1) << B) +
            sizeof(DevOp) * kMaxOpsPerPass + sizeof(uint64_t) * (size_t(1) << (B - kMinLow));
 }
 int sm_count() {
@@ -595,12 +770,20 @@ int sm_count() {
     }
     return n;
 }
-template <typename real, int B, int R, int GT>
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+bool tile_prof() {
+    static const bool v = env_int("B2SV_TILE_PROF", 0) != 0;
+    return v;
+}
+template <typename real, int B, int R, int GT, int NG, int NB, bool PROF>
 void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
                     cudaStream_t stream) {
     using amp_t = typename AmpT<real>::type;
-    auto kern = tile_exec_kernel<real, B, R, GT>;
-    constexpr size_t smem = tile_smem_bytes<real, B>();
+    auto kern = tile_exec_kernel<real, B, R, GT, NG, NB, PROF>;
+    constexpr size_t smem = tile_smem_bytes<real, B, NB>();
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -611,8 +794,8 @@ void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_
     // one persistent CTA per SM; with fewer than 2 tiles per SM spread them one per CTA
     const unsigned grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(sm_count()));
     // the descriptor is copied into the launch's parameter buffer by the runtime at this call
-    kern<<<grid, 2 * GT + kProducerThreads, smem, stream>>>(static_cast<amp_t *>(state), pp,
-                                                            rank_bits, n_tiles);
+    kern<<<grid, NG * GT + kProducerThreads, smem, stream>>>(static_cast<amp_t *>(state), pp,
+                                                             rank_bits, n_tiles);
     CUDA_CHECK(cudaGetLastError());
 }
 } // namespace
@@ -626,10 +809,22 @@ void tile_config(int dtype, int *B, int *R) {
 
 void launch_tile_pass(int dtype, void *state, const PassParams &pp, int n_eff,
                       uint64_t rank_bits, cudaStream_t stream) {
-    if (dtype == 1)
-        launch_variant<double, 12, 4, 256>(state, pp, n_eff, rank_bits, stream);
-    else
-        launch_variant<float, 13, 5, 256>(state, pp, n_eff, rank_bits, stream);
+    if (dtype == 1) {
+        if (tile_prof())
+            launch_variant<double, 12, 4, 256, 2, 3, true>(state, pp, n_eff, rank_bits, stream);
+        else
+            launch_variant<double, 12, 4, 256, 2, 3, false>(state, pp, n_eff, rank_bits, stream);
+    } else {
+        launch_variant<float, 13, 5, 256, 2, 3, false>(state, pp, n_eff, rank_bits, stream);
+    }
+}
+
+// Reads and clears the phase timers (zeros unless B2SV_TILE_PROF=1).
+void tile_prof_read(unsigned long long out[8]) {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpyFromSymbol(out, g_tile_prof, sizeof(unsigned long long) * 8));
+    unsigned long long z[8] = {0};
+    CUDA_CHECK(cudaMemcpyToSymbol(g_tile_prof, z, sizeof(z)));
 }
 
 } // namespace b2sv

@@ -16,6 +16,7 @@ int main(int argc, char **argv) {
     cfg.B = argc > 3 ? atoi(argv[3]) : 12;
     cfg.R = argc > 4 ? atoi(argv[4]) : 4;
     cfg.low = argc > 5 ? atoi(argv[5]) : 5;
+    cfg.max_heavy = argc > 6 ? atoi(argv[6]) : cfg.max_heavy;
     cfg.SW = 3;
     cfg.n_local = n;
     cfg.n_alloc = n;
@@ -56,7 +57,7 @@ int main(int argc, char **argv) {
             printf("    round %d: regbits", rd);
             for (int s = 0; s < cfg.R; s++)
                 printf(" %d", p.hdr.round_regbits[rd][s]);
-            printf("  ops %d  gather conflict degree %d\n", p.hdr.round_begin[rd + 1] - p.hdr.round_begin[rd], worst);
+            printf("  kind %d  ops %d  gather conflict degree %d\n", p.hdr.round_kind[rd], p.hdr.round_begin[rd + 1] - p.hdr.round_begin[rd], worst);
         }
         tot_ops += p.hdr.n_ops;
         tot_rounds += p.hdr.n_rounds;

@@ -515,3 +515,31 @@ def test_config2_layer_properties_at_scale(ops):
     sv.apply_ops(ol, adjoint=True)  # undo the layer
     sv.DeviceToHost(a)
     assert np.max(np.abs(a - 2.0 ** (-n / 2))) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("max_heavy", [8, 16])
+def test_factored_dense_rounds_vs_reference(ops, ref, dtype, max_heavy, monkeypatch):
+    """Layered circuits run as factored dense rounds (D * shear * D form, anti-diagonal-dominant
+    gates split into X * (X M)); they must equal the reference and the unfactored executor."""
+    n = 14
+    circ = layered_circuit(n, 3, seed=5)
+    for w in range(n):  # diagonals that vanish (exactly or almost): the X-split path
+        circ.append(("RX", [w], False, [np.pi - 1e-3 * w]))
+        circ.append(("RY", [(w + 3) % n], False, [np.pi + 1e-9 * w]))
+        circ.append(("PauliY", [(w + 5) % n], False, []))
+        circ.append(("Hadamard", [(w + 7) % n], False, []))
+    st = random_state(n, 77, dtype)
+    r = ref.RefStateVector(n, dtype)
+    r.h2d(st)
+    r.apply_ops(circ)
+    want = r.d2h()
+    tol = TOL[dtype] * (10 if dtype == np.complex64 else 1)
+    monkeypatch.setenv("B2SV_MAX_HEAVY", str(max_heavy))
+    for factor in ("1", "0"):
+        monkeypatch.setenv("B2SV_FACTOR", factor)
+        sv = sv_class(ops, dtype)(n)
+        sv.HostToDevice(st)
+        sv.apply([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ],
+                 [c[3] for c in circ])
+        assert rel_err(to_host(sv, n, dtype), want) < tol, factor

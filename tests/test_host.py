@@ -90,7 +90,8 @@ def test_scheduler_plan_config2_shape():
     n, layers = 30, 4
     p = plan(layered_circuit(n, layers, seed=42), n)
     assert p["arithmetic_ops"] == n * layers            # 120 fused 2x2 gates
-    assert p["absorbed_perms"] == n * layers            # 120 CNOTs, all free
+    # 120 CNOTs, all free, plus the X factors split off 2x2s whose anti-diagonal dominates
+    assert n * layers <= p["absorbed_perms"] <= 2 * n * layers
     assert p["passes"] <= 17
     assert p["rounds"] <= 3 * p["passes"]
     assert p["fused_stores"] >= p["passes"] // 2

@@ -1,0 +1,95 @@
+"""CPU tests of the host logic that decides what the tile executor does: named gates are lowered,
+scheduled into passes / rounds (free permutations, dense + factored rounds, fused stores) and the
+resulting descriptors are re-executed by the scalar pass emulator (tests/emu.py), then compared
+with the NumPy oracle. No GPU, no product library involved."""
+import numpy as np
+import pytest
+
+import emu
+from cases import GATES, gate_cases, layered_circuit, random_circuit, random_state, sel_circuit
+from oracle import np_oracle as npo
+
+
+def check(circ, n, f32=False, tol=None, **kw):
+    psi = random_state(n, seed=len(circ) + n)
+    got, stats = emu.run(circ, n, psi, f32=f32, **kw)
+    want = npo.apply_ops(psi, n, circ)
+    err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+    assert err < (tol or (2e-5 if f32 else 1e-12)), (err, stats)
+    return stats
+
+
+@pytest.mark.parametrize("factor", [True, False])
+def test_layered_circuit_factored_rounds(factor):
+    n = 14
+    circ = layered_circuit(n, 3, seed=42)
+    st = check(circ, n, factor=factor)
+    assert (st["factored"] > 0) == factor
+    # every CNOT and every X split off an anti-diagonal-dominant 2x2 is absorbed: no generic rounds
+    assert st["rounds"] == st["dense"] + st["factored"]
+
+
+@pytest.mark.parametrize("max_heavy", [1, 4, 12, 16])
+def test_layered_circuit_pass_budgets(max_heavy):
+    n = 13
+    check(layered_circuit(n, 2, seed=7), n, max_heavy=max_heavy)
+
+
+def test_layered_circuit_c64_tables_in_float():
+    n = 14
+    st = check(layered_circuit(n, 2, seed=3), n, f32=True)
+    assert st["factored"] > 0
+
+
+@pytest.mark.parametrize("store_mode", [0, 1, 2])
+def test_store_modes(store_mode):
+    n = 14
+    st = check(layered_circuit(n, 3, seed=21), n, store_mode=store_mode)
+    check(random_circuit(n, 200, seed=store_mode), n, store_mode=store_mode)
+    if store_mode == 0:
+        assert st["direct_stores"] == 0 and st["staged_stores"] == 0
+    elif store_mode == 1:
+        assert st["direct_stores"] > 0 and st["staged_stores"] == 0
+    else:
+        assert st["staged_stores"] >= st["passes"] - 1
+
+
+@pytest.mark.parametrize("B,low", [(11, 5), (12, 4), (12, 6)])
+def test_tile_geometries(B, low):
+    n = 13
+    check(layered_circuit(n, 2, seed=11), n, B=B, low=low)
+    check(random_circuit(n, 120, seed=B * 10 + low), n, B=B, low=low)
+
+
+def test_antidiagonal_dominant_gates_split_into_x():
+    # RX/RY near pi have a vanishing diagonal: X * (X M) keeps the shears bounded
+    n = 13
+    circ = []
+    for w in range(n):
+        circ.append(("RX", [w], False, [np.pi - 1e-3 * w]))
+        circ.append(("RY", [(w + 3) % n], False, [np.pi + 1e-9 * w]))
+        circ.append(("PauliY", [(w + 5) % n], False, []))
+        circ.append(("Hadamard", [(w + 7) % n], False, []))
+    st = check(circ, n)
+    assert st["factored"] > 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_circuits_every_gate(seed):
+    n = 13
+    check(random_circuit(n, 250, seed=seed), n)
+
+
+def test_random_circuits_c64():
+    n = 14
+    check(random_circuit(n, 150, seed=99), n, f32=True, tol=5e-5)
+
+
+def test_every_gate_pattern():
+    n = 13
+    for case in gate_cases(n, seed=5, per_gate=3):
+        check([case], n)
+
+
+def test_sel_circuit():
+    check(sel_circuit(13, 3), 13)
