@@ -1,5 +1,6 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r1c_pytest_gpu.log
-cat gpurun_out/r1c_pytest_gpu.log
-timeout 900 python benchmarks/tile_experiments.py > gpurun_out/r1c_tile_experiments.jsonl 2>&1
-cat gpurun_out/r1c_tile_experiments.jsonl
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+echo new; python benchmarks/single_pass.py
+echo auto; timeout 900 python benchmarks/configs.py 2>&1 | tee gpurun_out/r1_configs_1_3_4_v18.json | cut -c1-300
+echo base; cd _base; timeout 900 python benchmarks/configs.py --configs 3 2>&1 | cut -c1-300; cd ..
+timeout 600 python bench.py --no-cpu-baseline 2>/dev/null | cut -c1-200

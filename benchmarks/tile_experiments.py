@@ -16,17 +16,16 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SETTINGS = [
-    {},
-    {"B2SV_STORE_MODE": "1"},
-    {"B2SV_TILE_PROF": "1"},
+    {"B2SV_MAX_HEAVY": "4", "B2SV_TILE_FLAGS": "4"},
+    {"B2SV_MAX_HEAVY": "4", "B2SV_TILE_FLAGS": "12"},
+    {"B2SV_MAX_HEAVY": "4", "B2SV_TILE_FLAGS": "8"},
     {"B2SV_MAX_HEAVY": "4"},
-    {"B2SV_MAX_HEAVY": "4", "B2SV_STORE_MODE": "1"},
-    {"B2SV_MAX_HEAVY": "6"},
+    {"B2SV_TILE_FLAGS": "12"},
+    {"B2SV_TILE_FLAGS": "4"},
+    {"B2SV_TILE_FLAGS": "8"},
+    {},
+    {"B2SV_TILE_FLAGS": "8", "B2SV_MAX_HEAVY": "12"},
     {"B2SV_MAX_HEAVY": "12"},
-    {"B2SV_MAX_HEAVY": "12", "B2SV_TILE_PROF": "1"},
-    {"B2SV_MAX_HEAVY": "16"},
-    {"B2SV_TILE_LOW": "4", "B2SV_MAX_HEAVY": "12"},
-    {"B2SV_TILE_LOW": "4"},
 ]
 
 
@@ -50,26 +49,37 @@ def child(args):
                                       [c[2] for c in circ])
     sv.apply_ops(oplist)
     sv.sync()
-    prof = np.zeros(8, dtype=np.uint64)
+    prof = np.zeros(16, dtype=np.uint64)
     _lib.lib.b2sv_debug_tile_prof(prof.ctypes.data_as(C.POINTER(C.c_uint64)))
     sv.reset_stats()
+    import subprocess as sp
+    mon = sp.Popen(["nvidia-smi", "--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu",
+                    "--format=csv,noheader,nounits", "-lms", "50"], stdout=sp.PIPE, text=True)
+    time.sleep(0.2)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         sv.apply_ops(oplist)
     sv.sync()
     dt = (time.perf_counter() - t0) / args.steps
+    mon.terminate()
+    rows = [[float(x) for x in l.split(",")] for l in mon.stdout.read().splitlines() if l.count(",") == 3]
+    rows = rows[4:] or rows
+    clk = {"sm_mhz": float(np.median([r[0] for r in rows])), "mem_mhz": float(np.median([r[1] for r in rows])),
+           "power_w": float(np.median([r[2] for r in rows])), "temp_c": float(np.max([r[3] for r in rows]))} if rows else {}
     st = sv.stats()
     sweeps = st["sweeps"] / args.steps
     _lib.lib.b2sv_debug_tile_prof(prof.ctypes.data_as(C.POINTER(C.c_uint64)))
     norm = sv.ExpectationValue("Identity", [0], [], np.zeros(0))
     out = {"ms_per_step": dt * 1e3, "sweeps": sweeps, "ms_per_sweep": dt * 1e3 / sweeps,
-           "gbs_per_sweep": 2 * 16 * (1 << n) / (dt / sweeps) / 1e9, "norm": norm, "layers": layers}
+           "gbs_per_sweep": 2 * 16 * (1 << n) / (dt / sweeps) / 1e9, "norm": norm, "layers": layers, **clk}
     if prof[5]:
         p = [float(x) for x in prof]
         out["prof"] = {"worker_wait_frac": p[0] / (p[0] + p[1]), "producer_wait_frac": p[2] / (p[2] + p[3]),
                        "worker_cycles_per_tile": (p[0] + p[1]) / p[4], "worker_wait_cycles_per_tile": p[0] / p[4],
                        "cta_cycles_per_sweep": p[5] / (148.0 * st["sweeps"]),
-                       "last_round_cycles_per_tile": p[6] / p[4], "other_rounds_cycles_per_tile": p[7] / p[4]}
+                       "last_round_cycles_per_tile": p[6] / p[4], "other_rounds_cycles_per_tile": p[7] / p[4],
+                       "worker_prologue_cycles_per_tile": p[10] / p[4], "store_wait_per_tile": p[8] / p[4],
+                       "store_drain_per_tile": p[9] / p[4], "load_issue_per_tile": p[11] / p[4]}
     print("RESULT " + json.dumps(out), flush=True)
 
 
@@ -77,7 +87,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--layers", type=int, default=4)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--child", action="store_true")
     ap.add_argument("--only", type=int, default=-1)
     args = ap.parse_args()

@@ -84,8 +84,8 @@ int b2sv_set_fusion(b2sv_state *s, int fuse);
 int b2sv_get_stats(const b2sv_state *s, uint64_t *sweeps, uint64_t *launches);
 int b2sv_reset_stats(b2sv_state *s);
 /* developer aid: phase timers of the tile executor (all zero unless B2SV_TILE_PROF=1 is set in the
- * environment); reads and clears 8 cycle counters, see csrc/tile_kernel.cu g_tile_prof */
-int b2sv_debug_tile_prof(uint64_t *out8);
+ * environment); reads and clears 16 cycle counters, see csrc/tile_kernel.cu g_tile_prof */
+int b2sv_debug_tile_prof(uint64_t *out16);
 /* sharded states: global<->local qubit swaps done so far, bytes each rank sent, and whether the
  * NVLink peer-memory swap kernel (1) or NCCL send/recv (0) carries them */
 int b2sv_comm_stats(const b2sv_state *s, uint64_t *swaps, uint64_t *swap_bytes, int *peer_path);

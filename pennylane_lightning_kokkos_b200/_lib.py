@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2sv.so")
+# B2SV_LIB: developer override (kernel A/B experiments load a differently built libb2sv)
+LIB_PATH = os.environ.get("B2SV_LIB") or os.path.join(_HERE, "libb2sv.so")
 
 
 class PLException(RuntimeError):

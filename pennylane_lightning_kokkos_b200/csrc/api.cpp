@@ -229,13 +229,13 @@ int b2sv_reset_stats(b2sv_state *s) {
         st(s).reduce_launches = 0;
     });
 }
-int b2sv_debug_tile_prof(uint64_t *out8) {
+int b2sv_debug_tile_prof(uint64_t *out16) {
     return guard([&] {
-        B2_ABORT_IF(!out8, "null output");
-        unsigned long long v[8];
+        B2_ABORT_IF(!out16, "null output");
+        unsigned long long v[16];
         tile_prof_read(v);
-        for (int i = 0; i < 8; i++)
-            out8[i] = v[i];
+        for (int i = 0; i < 16; i++)
+            out16[i] = v[i];
     });
 }
 int b2sv_comm_stats(const b2sv_state *s, uint64_t *swaps, uint64_t *swap_bytes, int *peer_path) {

@@ -16,7 +16,7 @@ void tile_config(int dtype, int *B, int *R);
 struct PassParams;
 void launch_tile_pass(int dtype, void *state, const PassParams &pass, int n_eff,
                       uint64_t rank_bits, cudaStream_t stream);
-void tile_prof_read(unsigned long long out[8]);
+void tile_prof_read(unsigned long long out[16]);
 
 // ---- state management
 void launch_set_basis(int dtype, void *state, uint64_t len, uint64_t index, cudaStream_t st);

@@ -4,7 +4,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <functional>
 
 namespace b2sv {
 namespace {
@@ -300,7 +299,48 @@ DevOp make_devop(const Prim &p, const uint8_t *tile_bits, int B, const uint8_t *
 
 } // namespace
 
+double schedule_cost(const std::vector<Pass> &passes) {
+    // measured (profiles/r1_tile_ablation.md): 1 round 6.3-6.6 ms, +0.8-1.0 ms per further round
+    double c = 0.0;
+    for (const Pass &ps : passes)
+        c += ps.is_matk ? 8.0 : 5.6 + 0.9 * std::max(1, static_cast<int>(ps.hdr.n_rounds));
+    return c;
+}
+
+namespace {
+std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const SchedConfig &cfg);
+constexpr int kAutoBudgetMinBits = 25; // from 2^25 amplitudes on, trying several budgets pays
+}
+
 std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedConfig &cfg) {
+    if (cfg.max_heavy > 0)
+        return build_schedule_fixed(prims_in, cfg);
+    if (std::max(cfg.n_alloc, cfg.n_local) < kAutoBudgetMinBits) {
+        // small states: a sweep costs microseconds, so host time and launch count matter more than
+        // the balance inside a pass -- one cheap greedy build with a generous budget
+        SchedConfig c = cfg;
+        c.max_heavy = 16;
+        return build_schedule_fixed(prims_in, c);
+    }
+    std::vector<Pass> best;
+    double best_cost = 0.0;
+    for (int mh : {8, 12, 16, 24}) {
+        SchedConfig c = cfg;
+        c.max_heavy = mh;
+        std::vector<Pass> s = build_schedule_fixed(prims_in, c);
+        const double cost = schedule_cost(s);
+        if (best.empty() || cost < best_cost) {
+            best = std::move(s);
+            best_cost = cost;
+        }
+        if (static_cast<int>(prims_in.size()) <= mh)
+            break; // larger budgets cannot change anything
+    }
+    return best;
+}
+
+namespace {
+std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const SchedConfig &cfg) {
     const int B = cfg.B, R = cfg.R, low = std::min(cfg.low, cfg.B);
     B2_ASSERT(B <= kMaxTileBits && R <= kMaxRegBits && R <= B);
     const bool factor = cfg.factor && cfg.free_perms && cfg.fuse;
@@ -325,43 +365,101 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
             done[first++] = 1;
             continue;
         }
-        // ---- choose the ops and the tile bits of this pass
+        // ---- choose the tile bits of this pass, then its ops
+        // select(T, window, out): scan the pending ops in program order; an op joins the pass when
+        // nothing it depends on was skipped (Blocker), its target is a tile bit and the arithmetic
+        // budget allows. Returns 64 * (arithmetic ops) + (free permutations).
+        // With grow > 0 the tile takes up to `grow` further target bits first come, first served.
+        auto select = [&](uint64_t tmask, int grow, int window, std::vector<int> *out,
+                          uint64_t *tmask_out) {
+            Blocker blk;
+            int heavy = 0, n_light = 0, n_ops = 0, seen = 0;
+            for (int i = first; i < N && n_ops < kMaxOpsPerPass && seen < window; i++) {
+                if (done[i])
+                    continue;
+                seen++;
+                const Prim &p = prims[i];
+                if (p.type == Prim::MATK)
+                    break; // full barrier
+                const bool light = cfg.free_perms && p.type == Prim::C1Q && p.tag < 0 &&
+                                   classify(p) == KIND_PERM;
+                // balance: a pass is HBM-bound up to ~max_heavy gates; beyond that the arithmetic is
+                // the limit, so later passes (which stream the state anyway) should take the rest
+                bool fits = !blk.blocked(p) && (light || heavy < cfg.max_heavy);
+                if (fits && p.type == Prim::C1Q) {
+                    B2_ABORT_IF(p.target >= cfg.n_local,
+                                "internal: non-diagonal target on a global (rank) qubit");
+                    if (!(tmask & bit(p.target))) {
+                        if (grow > 0) {
+                            tmask |= bit(p.target);
+                            grow--;
+                        } else {
+                            fits = false;
+                        }
+                    }
+                }
+                if (fits) {
+                    if (out)
+                        out->push_back(i);
+                    heavy += light ? 0 : 1;
+                    n_light += light ? 1 : 0;
+                    n_ops++;
+                } else {
+                    blk.skip(p);
+                }
+            }
+            if (tmask_out)
+                *tmask_out = tmask;
+            return heavy * 64 + n_light;
+        };
         uint64_t tile_mask = low_mask;
         int free_bits = B - low;
-        Blocker blk;
-        std::vector<int> chosen;
-        int heavy = 0; // arithmetic ops taken so far (permutations are free: address-map updates)
-        for (int i = first; i < N && static_cast<int>(chosen.size()) < kMaxOpsPerPass; i++) {
-            if (done[i])
-                continue;
-            const Prim &p = prims[i];
-            if (p.type == Prim::MATK)
-                break; // full barrier
-            const bool light = cfg.free_perms && p.type == Prim::C1Q && p.tag < 0 &&
-                               classify(p) == KIND_PERM;
-            // balance: a pass is HBM-bound up to ~max_heavy gates; beyond that the FP64 pipe is the
-            // limit, so later passes (which stream the state anyway) should take the rest
-            bool fits = !blk.blocked(p) && (light || heavy < cfg.max_heavy);
-            if (fits && p.type == Prim::C1Q) {
-                B2_ABORT_IF(p.target >= cfg.n_local,
-                            "internal: non-diagonal target on a global (rank) qubit");
-                if (!(tile_mask & bit(p.target))) {
-                    if (free_bits > 0) {
-                        tile_mask |= bit(p.target);
-                        free_bits--;
-                    } else {
-                        fits = false;
+        if (prims[first].type == Prim::C1Q && !(tile_mask & bit(prims[first].target)) && free_bits > 0) {
+            tile_mask |= bit(prims[first].target); // progress: the oldest pending op always runs
+            free_bits--;
+        }
+        // Grow the tile one bit at a time by marginal gain over a look-ahead window: the candidate
+        // whose addition lets the most arithmetic join the pass wins, the earliest one on ties.
+        // (For layered circuits this finds the blocks of neighbouring wires whose gates of several
+        // layers can run in one sweep.)
+        constexpr int kWindow = 384, kMaxCand = 20;
+        while (free_bits > 0 && cfg.lookahead) {
+            std::vector<int> cand;
+            {
+                uint64_t seen_bits = tile_mask;
+                int seen = 0;
+                for (int i = first; i < N && seen < kWindow && static_cast<int>(cand.size()) < kMaxCand; i++) {
+                    if (done[i])
+                        continue;
+                    seen++;
+                    const Prim &p = prims[i];
+                    if (p.type == Prim::MATK)
+                        break;
+                    if (p.type == Prim::C1Q && !(seen_bits & bit(p.target)) && p.target < cfg.n_local) {
+                        seen_bits |= bit(p.target);
+                        cand.push_back(p.target);
                     }
                 }
             }
-            if (fits) {
-                chosen.push_back(i);
-                done[i] = 1;
-                heavy += light ? 0 : 1;
-            } else {
-                blk.skip(p);
+            if (cand.empty())
+                break;
+            int best = cand[0], best_score = -1;
+            if (cfg.lookahead)
+            for (int c : cand) {
+                const int sc = select(tile_mask | bit(c), 0, kWindow, nullptr, nullptr);
+                if (sc > best_score) {
+                    best_score = sc;
+                    best = c;
+                }
             }
+            tile_mask |= bit(best);
+            free_bits--;
         }
+        std::vector<int> chosen;
+        select(tile_mask, free_bits, N, &chosen, &tile_mask);
+        free_bits = B - __builtin_popcountll(tile_mask);
+        for (int i : chosen)
+            done[i] = 1;
         B2_ASSERT(!chosen.empty());
         for (int b = 0; free_bits > 0; b++) { // pad the tile with the lowest unused local bits
             B2_ASSERT(b < std::max(cfg.n_local, cfg.n_alloc));
@@ -378,6 +476,13 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                 if (tile_mask & bit(b))
                     ps.hdr.tile_bits[j++] = static_cast<uint8_t>(b);
             B2_ASSERT(j == B);
+        }
+        for (int e = 0; e < 64 && (e << 7) < (1 << B); e++) {
+            uint64_t off = 0;
+            for (int j = 7; j < B; j++)
+                if (((e << 7) >> j) & 1)
+                    off |= bit(ps.hdr.tile_bits[j]);
+            ps.hdr.load_off[e] = off;
         }
         { // tile-id deposit segments: runs of consecutive non-tile bits
             int n_seg = 0, id_bit = 0, below = 0; // below = tile bits under the current position
@@ -547,8 +652,7 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                         tile_pos(p.target) == slot_bits[k];
             }
             ps.hdr.round_kind[n_rounds] = dense ? static_cast<uint8_t>(now.size()) : 0;
-            if (dense && factor && now.size() >= 2 &&
-                ps.dense.size() < static_cast<size_t>(kMaxDense)) {
+            if (dense && factor && now.size() >= 2 && n_rounds < kMaxDense) {
                 std::vector<Factored> fs(now.size());
                 bool ok = true;
                 for (size_t k = 0; ok && k < now.size(); k++)
@@ -559,9 +663,10 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                         fill_dense<float>(dd, fs);
                     else
                         fill_dense<double>(dd, fs);
-                    ps.hdr.round_dense[n_rounds] = static_cast<uint8_t>(ps.dense.size());
                     ps.hdr.round_kind[n_rounds] = static_cast<uint8_t>(8 + now.size());
-                    ps.dense.push_back(dd);
+                    if (ps.dense.size() <= static_cast<size_t>(n_rounds))
+                        ps.dense.resize(n_rounds + 1, DevDense{});
+                    ps.dense[n_rounds] = dd;
                 }
             }
             uint8_t *rbits = ps.hdr.round_regbits[n_rounds];
@@ -628,17 +733,14 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
                     ps.hdr.round_col[last][k] =
                         ((1u << j) << 16) | phys_slot(McolLast[j], B, cfg.SW);
                     ps.hdr.store_free[k] = spread(Lcol[j]);
-                    ps.hdr.store_free_l[k] = static_cast<uint16_t>(Lcol[j]);
                 }
                 for (int k = 0; k < R; k++) {
                     const uint32_t v = Lcol[ps.hdr.round_regbits[last][k]];
                     ps.hdr.store_reg[k] = spread(v);
-                    ps.hdr.store_reg_l[k] = static_cast<uint16_t>(v);
                 }
                 for (int c = 0; c < n_cx; c++) {
                     const uint32_t v = ps.hdr.cx[c].round == n_rounds ? cx_logical[c] : 0;
                     ps.hdr.store_cx[c] = spread(v);
-                    ps.hdr.store_cx_l[c] = static_cast<uint16_t>(v);
                 }
                 ps.hdr.fused_store = static_cast<uint8_t>(mode);
             };
@@ -646,61 +748,7 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
             for (int j = 0; j < B; j++)
                 if (!(reg_mask & (1u << j)))
                     free_js.push_back(j);
-            if (cfg.store_mode == 2) {
-                // Staged store: any lane assignment is correct; pick the SW lowest thread-id bits
-                // (= the lanes of one shared-memory wavefront) so that the index-order scatter --
-                // and, when possible, the round's gather too -- is free of bank conflicts.
-                const uint32_t bank_mask = (1u << cfg.SW) - 1u;
-                auto rank_ok = [&](const std::vector<int> &sel, bool storage) {
-                    std::vector<uint32_t> basis;
-                    for (int j : sel) {
-                        uint32_t v = (storage ? phys_slot(McolLast[j], B, cfg.SW) : Lcol[j]) & bank_mask;
-                        for (uint32_t b : basis)
-                            v = std::min(v, v ^ b);
-                        if (v == 0)
-                            return false;
-                        basis.push_back(v);
-                        std::sort(basis.rbegin(), basis.rend());
-                    }
-                    return true;
-                };
-                std::vector<int> best;
-                int best_score = 0;
-                const int nf = static_cast<int>(free_js.size());
-                std::vector<int> idx(cfg.SW);
-                // enumerate SW-subsets of the free bits (at most C(9,4) = 126)
-                std::function<void(int, int)> rec = [&](int pos, int start) {
-                    if (best_score == 2)
-                        return;
-                    if (pos == cfg.SW) {
-                        std::vector<int> sel;
-                        for (int i : idx)
-                            sel.push_back(free_js[i]);
-                        if (!rank_ok(sel, false))
-                            return;
-                        const int score = rank_ok(sel, true) ? 2 : 1;
-                        if (score > best_score) {
-                            best_score = score;
-                            best = sel;
-                        }
-                        return;
-                    }
-                    for (int i = start; i < nf; i++) {
-                        idx[pos] = i;
-                        rec(pos + 1, i + 1);
-                    }
-                };
-                if (nf >= cfg.SW)
-                    rec(0, 0);
-                if (best_score > 0) {
-                    std::vector<int> lanes = best;
-                    for (int j : free_js)
-                        if (std::find(best.begin(), best.end(), j) == best.end())
-                            lanes.push_back(j);
-                    commit(lanes, 2);
-                }
-            }
-            if (!ps.hdr.fused_store) {
+            {
                 // Direct store from registers: possible when five thread-id bits of the last round can
                 // be given free tile bits whose images under the trailing permutations stay inside
                 // logical bits 0..4 and span them -- then every warp-wide store covers whole runs.
@@ -738,5 +786,7 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
     }
     return passes;
 }
+
+} // namespace
 
 } // namespace b2sv

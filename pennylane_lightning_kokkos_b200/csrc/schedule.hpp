@@ -23,7 +23,7 @@ constexpr int kMaxTileBits = 16;
 constexpr int kMaxRegBits = 5;
 constexpr int kMaxFreeBits = 12; // tile bits that are not register bits (= log2 threads)
 constexpr int kMaxCx = 32;       // conditional address toggles per pass
-constexpr int kMaxDense = 12;    // factored dense rounds per pass
+constexpr int kMaxDense = 8;     // rounds 0 .. kMaxDense-1 of a pass may run in factored form
 
 enum OpKind : uint8_t { KIND_GENERAL = 0, KIND_REAL = 1, KIND_PERM = 2, KIND_DIAG = 3 };
 // flag bits stored in DevOp::kind above the OpKind
@@ -74,19 +74,17 @@ struct alignas(16) DevPassHeader {
     uint8_t round_regbits[kMaxRounds][8]; // logical tile-local positions held in registers, by slot
     // 0: generic round (op interpreter); 1 <= g <= 5: "dense" round = exactly g uncontrolled 2x2
     // gates, the k-th one on register slot k (straight-line code, no per-op dispatch);
-    // 8 + g: the same in factored form, constants in PassParams::dense[round_dense[rd]]
+    // 8 + g: the same in factored form, constants in PassParams::dense[rd] (indexed by the round, so
+    // that the first rounds read them through uniform constant loads at compile-time offsets)
     uint8_t round_kind[kMaxRounds];
-    uint8_t round_dense[kMaxRounds];
-    uint8_t pad3_[8];
+    uint8_t pad3_[kMaxRounds + 8];
     // tile id -> index with the tile bits cleared: base = OR_k ((id & seg_mask[k]) << seg_shift[k]),
     // one segment per run of consecutive non-tile index bits
     uint32_t seg_mask[kMaxTileBits + 1];
     uint8_t seg_shift[kMaxTileBits + 1];
     uint8_t n_seg;
     // how the tile leaves the SM: 0 = store phase (worker threads copy shared -> HBM through the
-    // final address map); 1 = the last round writes its registers straight to HBM; 2 = staged: the
-    // last round scatters the tile into shared memory in index order and the store warps stream
-    // its rows to HBM with bulk async copies while the workers start their next tile
+    // final address map); 1 = fused store, the last round writes its registers straight to HBM
     uint8_t fused_store;
     uint8_t pad2_[13];
     // global index offsets (already pushed through the permutations absorbed after the last round):
@@ -94,12 +92,9 @@ struct alignas(16) DevPassHeader {
     uint64_t store_free[kMaxFreeBits];
     uint64_t store_reg[8];
     uint64_t store_cx[kMaxCx];
-    // the same three as tile-local logical indices (staged store: the last round scatters the tile
-    // into shared memory in index order and bulk-copy engines stream its rows to HBM)
-    uint16_t store_free_l[kMaxFreeBits];
-    uint16_t store_reg_l[8];
-    uint16_t store_cx_l[kMaxCx];
-    uint16_t pad4_[4];
+    // load warps: global index offset of tile-local index e * 128 (the part of a load thread's
+    // element index that does not depend on the thread), e < 2^B / 128
+    uint64_t load_off[64];
     uint16_t round_begin[kMaxRounds + 1]; // op index ranges per round
     uint16_t pad_[3];
     // storage offset phys(M e_r) of register bit s in round rd
@@ -125,7 +120,7 @@ struct Pass {
     Prim matk;              // when is_matk
     DevPassHeader hdr{};    // otherwise
     std::vector<DevOp> ops;
-    std::vector<DevDense> dense; // factored dense rounds
+    std::vector<DevDense> dense; // factored dense rounds: entry rd belongs to round rd (others zero)
     std::vector<int> tags;  // per op: Prim::tag
     int n_absorbed = 0;     // permutation primitives folded into the address map
 };
@@ -140,10 +135,14 @@ struct SchedConfig {
     bool fuse = true;  // false: one pass per primitive group (reference schedule)
     bool free_perms = true; // fold CNOT / X into the address map
     bool fuse_store = true; // let the last round of a pass write straight to HBM when coalescing allows
-    int store_mode = 2;     // preferred DevPassHeader::fused_store mode when fuse_store is on
-    int max_heavy = 8;      // arithmetic ops per pass before the pass turns FP64-bound
+    // arithmetic ops per pass; 0 = automatic: build the schedule for several budgets and keep the
+    // cheapest under the cost model of schedule_cost()
+    int max_heavy = 0;
     bool f32 = false;       // complex64 state: factored-round tables are stored as float
     bool factor = true;     // factored dense rounds (D * shear * D form of the fused 2x2s)
+    // grow the tile by marginal gain over a look-ahead window instead of first come, first served;
+    // off by default: no fewer passes on the circuits tried, and it costs host time per pass
+    bool lookahead = false;
 };
 
 // Shared-memory swizzle (same function as tile_kernel.cu phys<B,SW>): XOR-folds every higher
@@ -159,5 +158,8 @@ inline uint32_t phys_slot(uint32_t i, int B, int SW) {
 std::vector<Prim> fuse_single_qubit(const std::vector<Prim> &prims);
 // Main entry.
 std::vector<Pass> build_schedule(const std::vector<Prim> &prims, const SchedConfig &cfg);
+// Cost model (arbitrary units, fitted on 30-qubit complex128 sweeps on a B200): a pass costs what
+// streaming the state costs, plus a smaller amount for every register round it runs on the tile.
+double schedule_cost(const std::vector<Pass> &passes);
 
 } // namespace b2sv

@@ -486,10 +486,8 @@ void State::run_local(const std::vector<Prim> &prims) {
     cfg.f32 = dtype_ != 1;
     if (const char *e = getenv("B2SV_FACTOR"))
         cfg.factor = atoi(e) != 0;
-    if (const char *e = getenv("B2SV_STORE_MODE")) { // 0 store phase, 1 direct from registers, 2 staged
-        cfg.store_mode = std::max(0, std::min(2, atoi(e)));
-        cfg.fuse_store = cfg.store_mode != 0;
-    }
+    if (const char *e = getenv("B2SV_FUSE_STORE")) // 0: always go through the store phase
+        cfg.fuse_store = atoi(e) != 0;
     cfg.n_local = n_local_;
     cfg.n_alloc = n_eff_;
     cfg.fuse = fuse_;

@@ -1,804 +1,10 @@
-// b2sv: the tile executor -- ONE kernel applies every gate of a fused pass in a single HBM sweep.
-//
-// Replaces the reference's one-gate-per-sweep functor dispatch
-// (reference StateVectorKokkos.hpp:807-824 applyGateFunctor -> GateFunctors.hpp, one
-// Kokkos::parallel_for over 2^(n-k) per gate).
-//
-// Execution model (one persistent CTA per SM, two worker groups, three rotating tile buffers):
-//   * a tile = 2^B amplitudes (B = 12 for complex128 -> 64 KiB) whose indices differ in the pass's
-//     B tile bits; the CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-//   * each worker group (GT threads) owns every second tile of the CTA: it waits for the tile to
-//     land in shared memory, runs all rounds of the pass on it in registers, streams it back to
-//     HBM in place, and then refills the buffer it just freed with the tile three steps ahead
-//     (cp.async = LDGSTS with a per-amplitude XOR-swizzled destination; completion is handed to the
-//     other group through an mbarrier). So while two tiles are being computed a third is always
-//     in flight, and the HBM stream and the FP64 pipe overlap inside every SM.
-//   * a round: every thread gathers the 2^R amplitudes whose indices differ only in the round's R
-//     "register bits", applies all ops of the round in registers, scatters back in place.
-// HBM traffic is exactly one read + one write of the state per pass, whatever the number of gates.
-//
-// Shared-memory layout: amplitude i of the tile lives at slot phys(i) = i ^ fold(i) where fold XORs
-// the higher SW-bit groups of i into its low SW bits (SW = log2(128 B / sizeof(amp))). phys is
-// GF(2)-linear, so phys(base | off) = phys(base) ^ phys(off), and any 8 (c128) / 16 (c64) consecutive
-// lanes hit distinct 16 B / 8 B bank groups for every choice of register bits.
-#include "schedule.hpp"
-
-#include <algorithm>
-#include <cstdlib>
-#include <cuda_runtime.h>
+// b2sv: tile executor, complex128 instantiations + dtype dispatch (kernel: tile_kernel.cuh).
+#include "tile_kernel.cuh"
 
 namespace b2sv {
 
-template <typename real> struct AmpT;
-template <> struct AmpT<double> {
-    using type = double2;
-};
-template <> struct AmpT<float> {
-    using type = float2;
-};
-
-template <int B, int SW> __device__ __forceinline__ uint32_t phys(uint32_t i) {
-    uint32_t f = 0;
-#pragma unroll
-    for (int s = SW; s < B; s += SW)
-        f ^= (i >> s);
-    return i ^ (f & ((1u << SW) - 1u));
-}
-
-// ---- async-copy / mbarrier / named-barrier primitives ----------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void cp_async_amp(double2 *dst, const double2 *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_amp(float2 *dst, const float2 *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(dst)), "l"(src)
-                 : "memory");
-}
-// the mbarrier receives one arrival from this thread once all its cp.async issued so far have landed
-__device__ __forceinline__ void cp_async_arrive(uint64_t *mbar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(mbar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint64_t *mbar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(
-                     smem_u32(mbar))
-                 : "memory");
-}
-// Polling must not steal issue slots from the arithmetic warps of the same SM sub-partition: the
-// try_wait carries a suspend-time hint and a missed poll backs off with nanosleep.
-template <int SLEEP_NS>
-__device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
-    const uint32_t a = smem_u32(mbar);
-    uint32_t ok;
-    uint32_t spins = 0;
-    while (true) {
-        asm volatile("{\n .reg .pred p;\n"
-                     " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-                     " selp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok)
-                     : "r"(a), "r"(parity), "r"(static_cast<uint32_t>(SLEEP_NS * 4))
-                     : "memory");
-        if (ok)
-            break;
-        __nanosleep(SLEEP_NS);
-        if (++spins == (1u << 24))
-            __trap(); // a lost hand-off must surface as a CUDA error, never as a hung GPU
-    }
-}
-// one lane polls, the rest of the warp parks at the warp barrier (no 32-wide spinning)
-template <int SLEEP_NS>
-__device__ __forceinline__ void mbar_wait_warp(uint64_t *mbar, uint32_t parity) {
-    if ((threadIdx.x & 31) == 0)
-        mbar_wait<SLEEP_NS>(mbar, parity);
-    __syncwarp();
-}
-// bulk async copy shared -> global (one contiguous run), tracked by the issuing thread's bulk group
-__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
-                 "r"(smem_u32(ssrc)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() {
-    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read_all() { // the sources have been read (reusable)
-    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-}
-// generic-proxy writes to shared memory become visible to the async proxy (the bulk copy engine)
-__device__ __forceinline__ void fence_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-}
-__device__ __forceinline__ void group_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// ---- register-level op bodies -------------------------------------------------------------------
-template <int TS, int NS, typename amp_t, typename real>
-__device__ __forceinline__ void op_general(amp_t (&a)[NS], const real (&m)[8], uint32_t act,
-                                           bool pred) {
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        if (s & (1 << TS))
-            continue;
-        constexpr int dummy = 0;
-        (void)dummy;
-        const int s1 = s | (1 << TS);
-        if (pred && ((act >> s) & 1u)) {
-            const amp_t v0 = a[s], v1 = a[s1];
-            amp_t r0, r1;
-            r0.x = m[0] * v0.x - m[1] * v0.y + m[2] * v1.x - m[3] * v1.y;
-            r0.y = m[0] * v0.y + m[1] * v0.x + m[2] * v1.y + m[3] * v1.x;
-            r1.x = m[4] * v0.x - m[5] * v0.y + m[6] * v1.x - m[7] * v1.y;
-            r1.y = m[4] * v0.y + m[5] * v0.x + m[6] * v1.y + m[7] * v1.x;
-            a[s] = r0;
-            a[s1] = r1;
-        }
-    }
-}
-template <int TS, int NS, typename amp_t, typename real>
-__device__ __forceinline__ void op_real(amp_t (&a)[NS], const real (&m)[8], uint32_t act,
-                                        bool pred) {
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        if (s & (1 << TS))
-            continue;
-        const int s1 = s | (1 << TS);
-        if (pred && ((act >> s) & 1u)) {
-            const amp_t v0 = a[s], v1 = a[s1];
-            amp_t r0, r1;
-            r0.x = m[0] * v0.x + m[2] * v1.x;
-            r0.y = m[0] * v0.y + m[2] * v1.y;
-            r1.x = m[4] * v0.x + m[6] * v1.x;
-            r1.y = m[4] * v0.y + m[6] * v1.y;
-            a[s] = r0;
-            a[s1] = r1;
-        }
-    }
-}
-template <int TS, int NS, typename amp_t>
-__device__ __forceinline__ void op_perm(amp_t (&a)[NS], uint32_t act, bool pred) {
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        if (s & (1 << TS))
-            continue;
-        const int s1 = s | (1 << TS);
-        if (pred && ((act >> s) & 1u)) {
-            const amp_t t = a[s];
-            a[s] = a[s1];
-            a[s1] = t;
-        }
-    }
-}
-template <int NS, typename amp_t, typename real>
-__device__ __forceinline__ void op_diag(amp_t (&a)[NS], const real (&m)[8], uint32_t act,
-                                        uint32_t par, bool odd_base, bool pred) {
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        if (pred && ((act >> s) & 1u)) {
-            const bool odd = odd_base ^ (((par >> s) & 1u) != 0);
-            const real pr = odd ? m[2] : m[0];
-            const real pi = odd ? m[3] : m[1];
-            const amp_t v = a[s];
-            amp_t r;
-            r.x = pr * v.x - pi * v.y;
-            r.y = pr * v.y + pi * v.x;
-            a[s] = r;
-        }
-    }
-}
-
-// ---- fast paths: no control of any kind, so no predicate and full instruction-level parallelism
-template <int TS, int NS, typename amp_t, typename real>
-__device__ __forceinline__ void fast_general(amp_t (&a)[NS], const real (&m)[8]) {
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        if (s & (1 << TS))
-            continue;
-        const int s1 = s | (1 << TS);
-        const amp_t v0 = a[s], v1 = a[s1];
-        amp_t r0, r1;
-        r0.x = m[0] * v0.x - m[1] * v0.y + m[2] * v1.x - m[3] * v1.y;
-        r0.y = m[0] * v0.y + m[1] * v0.x + m[2] * v1.y + m[3] * v1.x;
-        r1.x = m[4] * v0.x - m[5] * v0.y + m[6] * v1.x - m[7] * v1.y;
-        r1.y = m[4] * v0.y + m[5] * v0.x + m[6] * v1.y + m[7] * v1.x;
-        a[s] = r0;
-        a[s1] = r1;
-    }
-}
-template <int TS, int NS, typename amp_t, typename real>
-__device__ __forceinline__ void fast_real(amp_t (&a)[NS], const real (&m)[8]) {
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        if (s & (1 << TS))
-            continue;
-        const int s1 = s | (1 << TS);
-        const amp_t v0 = a[s], v1 = a[s1];
-        amp_t r0, r1;
-        r0.x = m[0] * v0.x + m[2] * v1.x;
-        r0.y = m[0] * v0.y + m[2] * v1.y;
-        r1.x = m[4] * v0.x + m[6] * v1.x;
-        r1.y = m[4] * v0.y + m[6] * v1.y;
-        a[s] = r0;
-        a[s1] = r1;
-    }
-}
-
-template <int R, int NS, typename amp_t, typename real>
-__device__ __forceinline__ void run_op(amp_t (&a)[NS], const DevOp &op, uint64_t tile_base,
-                                       uint32_t base_local) {
-    real m[8];
-    {
-        const double2 *mp = reinterpret_cast<const double2 *>(op.m);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const double2 t = mp[i];
-            m[2 * i] = static_cast<real>(t.x);
-            m[2 * i + 1] = static_cast<real>(t.y);
-        }
-    }
-    const int kind = op.kind & OPF_KIND_MASK;
-    const int ts = op.tslot;
-    if ((op.kind & OPF_UNCOND) && kind <= KIND_REAL) {
-        // code = kind * 8 + ts; one flat switch keeps the hot bodies contiguous
-        switch (kind * 8 + ts) {
-#define B2_FAST(TS)                                                                             \
-    case TS:                                                                                    \
-        if constexpr (TS < R)                                                                   \
-            fast_general<TS, NS>(a, m);                                                         \
-        break;                                                                                  \
-    case 8 + TS:                                                                                \
-        if constexpr (TS < R)                                                                   \
-            fast_real<TS, NS>(a, m);                                                            \
-        break;
-            B2_FAST(0)
-            B2_FAST(1)
-            B2_FAST(2)
-            B2_FAST(3)
-            B2_FAST(4)
-#undef B2_FAST
-        default:
-            break;
-        }
-        return;
-    }
-    if ((tile_base & op.gcm) != op.gcv)
-        return; // CTA-uniform: the whole tile fails the control
-    const bool pred = (base_local & op.lcm) == op.lcv;
-    const uint32_t act = op.slot_act;
-    if (kind == KIND_DIAG) {
-        const bool odd =
-            ((__popcll(tile_base & op.gpm) + __popc(base_local & op.lpm)) & 1) != 0;
-        op_diag<NS>(a, m, act, op.slot_par, odd, pred);
-        return;
-    }
-    switch (ts) {
-#define B2_CASE(TS)                                                                             \
-    case TS:                                                                                    \
-        if constexpr (TS < R) {                                                                 \
-            if (kind == KIND_GENERAL)                                                           \
-                op_general<TS, NS>(a, m, act, pred);                                            \
-            else if (kind == KIND_REAL)                                                         \
-                op_real<TS, NS>(a, m, act, pred);                                               \
-            else                                                                                \
-                op_perm<TS, NS>(a, act, pred);                                                  \
-        }                                                                                       \
-        break;
-        B2_CASE(0)
-        B2_CASE(1)
-        B2_CASE(2)
-        B2_CASE(3)
-        B2_CASE(4)
-#undef B2_CASE
-    default:
-        break;
-    }
-}
-
-// G uncontrolled 2x2 gates, gate k on register slot k (k < R), fully unrolled.
-template <int G, int R, int NS, typename amp_t, typename real>
-__device__ __forceinline__ void dense_round(amp_t (&a)[NS], const DevOp *ops) {
-#pragma unroll
-    for (int k = 0; k < G; k++) {
-        if constexpr (true) {
-            if (k >= R)
-                break;
-        }
-        real m[8];
-        const double2 *mp = reinterpret_cast<const double2 *>(ops[k].m);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const double2 t = mp[i];
-            m[2 * i] = static_cast<real>(t.x);
-            m[2 * i + 1] = static_cast<real>(t.y);
-        }
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-            if (s & (1 << k))
-                continue;
-            const int s1 = s | (1 << k);
-            const amp_t v0 = a[s], v1 = a[s1];
-            amp_t r0, r1;
-            r0.x = m[0] * v0.x - m[1] * v0.y + m[2] * v1.x - m[3] * v1.y;
-            r0.y = m[0] * v0.y + m[1] * v0.x + m[2] * v1.y + m[3] * v1.x;
-            r1.x = m[4] * v0.x - m[5] * v0.y + m[6] * v1.x - m[7] * v1.y;
-            r1.y = m[4] * v0.y + m[5] * v0.x + m[6] * v1.y + m[7] * v1.x;
-            a[s] = r0;
-            a[s1] = r1;
-        }
-    }
-}
-// The same round in factored form (DevDense): per-slot phase, G real shears (one FMA per real
-// number and gate), per-slot scale. 4 + 2 G + 4 multiply-adds per amplitude instead of 8 G.
-template <int G, int R, int NS, typename amp_t, typename real>
-__device__ __forceinline__ void dense_factored(amp_t (&a)[NS], const DevDense &dd) {
-    constexpr int GG = G < R ? G : R;
-    constexpr int GM = (1 << GG) - 1;
-    const amp_t *pre = reinterpret_cast<const amp_t *>(dd.pre);
-    const amp_t *post = reinterpret_cast<const amp_t *>(dd.post);
-    const real *t = reinterpret_cast<const real *>(dd.t);
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        if ((s & GM) == 0)
-            continue; // pre[0] = 1
-        const amp_t p = pre[s & GM];
-        const amp_t v = a[s];
-        a[s].x = p.x * v.x - p.y * v.y;
-        a[s].y = p.x * v.y + p.y * v.x;
-    }
-#pragma unroll
-    for (int k = 0; k < GG; k++) {
-        const real t01 = t[2 * k], t10 = t[2 * k + 1];
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-            if (s & (1 << k))
-                continue;
-            const int s1 = s | (1 << k);
-            const amp_t v0 = a[s], v1 = a[s1];
-            a[s].x = fma(t01, v1.x, v0.x);
-            a[s].y = fma(t01, v1.y, v0.y);
-            a[s1].x = fma(t10, v0.x, v1.x);
-            a[s1].y = fma(t10, v0.y, v1.y);
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        const amp_t p = post[s & GM];
-        const amp_t v = a[s];
-        a[s].x = p.x * v.x - p.y * v.y;
-        a[s].y = p.x * v.y + p.y * v.x;
-    }
-}
-template <int R, int NS, typename amp_t>
-__device__ __forceinline__ void scatter_round(amp_t *tile, const amp_t (&a)[NS], uint32_t pb,
-                                              const uint32_t (&poff)[R]) {
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        uint32_t x = pb;
-#pragma unroll
-        for (int c = 0; c < R; c++)
-            if (s & (1 << c))
-                x ^= poff[c];
-        tile[x] = a[s];
-    }
-}
-
-// last round of a pass: registers -> HBM directly. Addresses are XOR-combinations of global index
-// offsets read from the (uniform) pass descriptor; computed here, after the arithmetic, so nothing
-// extra stays live across the round.
-template <int R, int NS, int NF, typename amp_t>
-__device__ __forceinline__ void store_round(amp_t *__restrict__ state, const amp_t (&a)[NS],
-                                            const DevPassHeader &ph, uint64_t tb, uint64_t tbr,
-                                            int tid) {
-    uint64_t addr0 = tb;
-#pragma unroll
-    for (int c = 0; c < NF; c++)
-        addr0 ^= (uint64_t(0) - ((static_cast<uint64_t>(tid) >> c) & 1u)) & ph.store_free[c];
-    for (int c = 0; c < ph.n_cx; c++)
-        if ((tbr & ph.cx[c].gcm) == ph.cx[c].gcv)
-            addr0 ^= ph.store_cx[c];
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        uint64_t x = addr0;
-#pragma unroll
-        for (int c = 0; c < R; c++)
-            if (s & (1 << c))
-                x ^= ph.store_reg[c];
-        state[x] = a[s];
-    }
-}
-// last round of a staged pass: registers -> shared memory in (final, logical) index order, so that
-// every run of 2^low amplitudes is one contiguous piece the bulk-copy engine can stream to HBM
-template <int R, int NS, int NF, typename amp_t>
-__device__ __forceinline__ void stage_round(amp_t *tile, const amp_t (&a)[NS],
-                                            const DevPassHeader &ph, uint64_t tbr, int tid) {
-    uint32_t i0 = 0;
-#pragma unroll
-    for (int c = 0; c < NF; c++)
-        i0 ^= (0u - ((static_cast<uint32_t>(tid) >> c) & 1u)) & ph.store_free_l[c];
-    for (int c = 0; c < ph.n_cx; c++)
-        if ((tbr & ph.cx[c].gcm) == ph.cx[c].gcv)
-            i0 ^= ph.store_cx_l[c];
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        uint32_t x = i0;
-#pragma unroll
-        for (int c = 0; c < R; c++)
-            if (s & (1 << c))
-                x ^= ph.store_reg_l[c];
-        tile[x] = a[s];
-    }
-}
-// mode: 0 = scatter back in place, 1 = registers -> HBM, 2 = stage in index order
-template <int R, int NS, int NF, typename amp_t>
-__device__ __forceinline__ void finish_round(int mode, amp_t *__restrict__ state, amp_t *tile,
-                                             const amp_t (&a)[NS], uint32_t pb,
-                                             const uint32_t (&poff)[R], const DevPassHeader &ph,
-                                             uint64_t tb, uint64_t tbr, int tid) {
-    if (mode == 1)
-        store_round<R, NS, NF>(state, a, ph, tb, tbr, tid);
-    else if (mode == 2)
-        stage_round<R, NS, NF>(tile, a, ph, tbr, tid);
-    else
-        scatter_round<R, NS>(tile, a, pb, poff);
-}
-
-// ---- the kernel ---------------------------------------------------------------------------------
-// The pass descriptor travels as a __grid_constant__ kernel parameter (constant bank): no upload,
-// and the dense rounds read their gate matrices through uniform constant loads instead of holding
-// them in 16 vector registers per thread.
-constexpr int kProducerThreads = 128; // one warpgroup that does nothing but stream tiles into shared memory
-
-// Optional phase timers (B2SV_TILE_PROF=1): cycles summed over the lead thread of every worker group
-// / producer warpgroup of every CTA. [0] workers waiting for a tile, [1] workers busy on tiles,
-// [2] producers waiting for a free buffer, [3] producers issuing copies, [4] tiles, [5] CTA lifetime,
-// [6] workers in the last (fused-store) round of a tile, [7] workers in the other rounds.
-__device__ unsigned long long g_tile_prof[8];
-
-template <typename real, int B, int R, int GT, int NG, int NB, bool PROF>
-__global__ void __launch_bounds__(NG * GT + kProducerThreads, 1)
-    tile_exec_kernel(typename AmpT<real>::type *__restrict__ state,
-                     const __grid_constant__ PassParams pp, uint64_t rank_bits,
-                     uint32_t n_tiles) {
-    constexpr int kTileBuffers = NB;
-    using amp_t = typename AmpT<real>::type;
-    constexpr int SW = (sizeof(amp_t) == 16) ? 3 : 4;
-    constexpr int NS = 1 << R;
-    constexpr int TILE = 1 << B;
-    constexpr int NF = B - R; // non-register tile bits = thread-id bits within a group
-    constexpr int NTHREADS = NG * GT + kProducerThreads;
-    static_assert((1 << NF) == GT, "one register group per thread");
-    static_assert(NF <= kMaxFreeBits, "too many thread-id bits");
-    constexpr int EPT = TILE / GT; // amplitudes per thread in the store phase (= NS)
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    amp_t *tiles = reinterpret_cast<amp_t *>(smem_raw); // kTileBuffers buffers of TILE amplitudes
-    DevOp *sops = reinterpret_cast<DevOp *>(smem_raw + kTileBuffers * sizeof(amp_t) * TILE);
-    uint64_t *rowoff = reinterpret_cast<uint64_t *>(sops + kMaxOpsPerPass);
-    __shared__ DevPassHeader hdr;
-    __shared__ uint32_t xoff_all[NG][kMaxRounds + 1];
-    __shared__ __align__(8) uint64_t full[kTileBuffers], empty[kTileBuffers], computed[kTileBuffers];
-    static_assert(NG == 2, "one store warp per worker group: the helper warpgroup has 2 + 2 warps");
-    constexpr int kLoadThreads = 64; // helper warps 0-1 stream tiles in, warps 2-3 stream staged tiles out
-
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(&pp.hdr);
-        uint4 *dst = reinterpret_cast<uint4 *>(&hdr);
-        for (int i = threadIdx.x; i < static_cast<int>(sizeof(DevPassHeader) / 16); i += NTHREADS)
-            dst[i] = src[i];
-        const int n_ops = pp.hdr.n_ops;
-        const uint4 *osrc = reinterpret_cast<const uint4 *>(pp.ops);
-        uint4 *odst = reinterpret_cast<uint4 *>(sops);
-        for (int i = threadIdx.x; i < n_ops * static_cast<int>(sizeof(DevOp) / 16); i += NTHREADS)
-            odst[i] = osrc[i];
-        if (threadIdx.x < kTileBuffers) {
-            mbar_init(&full[threadIdx.x], kLoadThreads);
-            mbar_init(&empty[threadIdx.x], 1);
-            mbar_init(&computed[threadIdx.x], 1);
-        }
-    }
-    __syncthreads();
-
-    const int low = hdr.low_bits;
-    for (int r = threadIdx.x; r < (1 << (B - low)); r += NTHREADS) {
-        uint64_t off = 0;
-        for (int j = low; j < B; j++)
-            if ((r >> (j - low)) & 1)
-                off |= uint64_t(1) << hdr.tile_bits[j];
-        rowoff[r] = off;
-    }
-    const int n_rounds = pp.hdr.n_rounds;
-    const uint32_t lowmask = (1u << low) - 1u;
-    __syncthreads();
-
-    // tiles of this CTA: k = 0 .. n_mine-1  <->  global tile blockIdx.x + k * gridDim.x
-    const uint32_t n_mine = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    auto tile_base_of = [&](uint32_t k) { // deposit the tile id into the non-tile index bits
-        const uint32_t t = blockIdx.x + k * gridDim.x;
-        uint64_t tb = 0;
-        const int n_seg = pp.hdr.n_seg;
-#pragma unroll 1
-        for (int j = 0; j < n_seg; j++)
-            tb |= static_cast<uint64_t>(t & pp.hdr.seg_mask[j]) << pp.hdr.seg_shift[j];
-        return tb;
-    };
-
-    long long t_start = 0;
-    if constexpr (PROF)
-        t_start = clock64();
-    if (threadIdx.x >= NG * GT) {
-        // ---- helper warpgroup
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
-        const int ptid = threadIdx.x - NG * GT;
-        if (ptid >= kLoadThreads) {
-            // store warps (one per worker group): stream staged tiles to HBM with bulk async copies,
-            // then hand the buffer back to the load warps
-            if (pp.hdr.fused_store != 2)
-                return;
-            const int g = (ptid - kLoadThreads) >> 5, lane = ptid & 31;
-            const uint32_t row_bytes = static_cast<uint32_t>(sizeof(amp_t)) << low;
-            const int n_rows = 1 << (B - low);
-            for (uint32_t k = g; k < n_mine; k += NG) {
-                const int bi = k % kTileBuffers;
-                mbar_wait_warp<100>(&computed[bi], (k / kTileBuffers) & 1u);
-                const uint64_t tb = tile_base_of(k);
-                const unsigned char *buf = reinterpret_cast<const unsigned char *>(tiles + bi * TILE);
-                for (int r = lane; r < n_rows; r += 32)
-                    bulk_store(&state[tb | rowoff[r]], buf + static_cast<size_t>(r) * row_bytes, row_bytes);
-                bulk_commit();
-                bulk_wait_read_all();
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(&empty[bi]);
-            }
-            return;
-        }
-        // load warps: HBM -> shared (swizzled slots), running ahead of the workers
-        long long p_wait = 0, p_t0 = 0;
-        for (uint32_t k = 0; k < n_mine; k++) {
-            const int bi = k % kTileBuffers;
-            if constexpr (PROF)
-                p_t0 = clock64();
-            if (k >= kTileBuffers)
-                mbar_wait_warp<400>(&empty[bi], ((k / kTileBuffers) - 1) & 1u);
-            if constexpr (PROF)
-                p_wait += clock64() - p_t0;
-            const uint64_t tb = tile_base_of(k);
-            amp_t *buf = tiles + bi * TILE;
-#pragma unroll 8
-            for (int e = 0; e < TILE / kLoadThreads; e++) {
-                const uint32_t i = e * kLoadThreads + ptid;
-                cp_async_amp(&buf[phys<B, SW>(i)], &state[tb | rowoff[i >> low] | (i & lowmask)]);
-            }
-            cp_async_arrive(&full[bi]);
-        }
-        if constexpr (PROF) {
-            if (ptid == 0) {
-                const long long life = clock64() - t_start;
-                atomicAdd(&g_tile_prof[2], static_cast<unsigned long long>(p_wait));
-                atomicAdd(&g_tile_prof[3], static_cast<unsigned long long>(life - p_wait));
-                atomicAdd(&g_tile_prof[5], static_cast<unsigned long long>(life));
-            }
-        }
-        return;
-    }
-
-    // ---- worker groups: tile k is computed by group k & 1
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
-    const int grp = threadIdx.x / GT;
-    const int tid = threadIdx.x % GT;
-    uint32_t *xoff = xoff_all[grp];
-    long long w_wait = 0, w_t0 = 0, w_tiles = 0, w_last = 0, w_round = 0, w_r0 = 0;
-    for (uint32_t k = grp; k < n_mine; k += NG) {
-        const int bi = k % kTileBuffers;
-        amp_t *tile = tiles + bi * TILE;
-        const uint64_t tb = tile_base_of(k);
-        const uint64_t tbr = tb | rank_bits;
-        if (tid <= n_rounds) { // CTA-uniform address toggles visible from round `tid` on
-            uint32_t x = 0;
-            for (int c = 0; c < hdr.n_cx; c++)
-                if (hdr.cx[c].round <= tid && (tbr & hdr.cx[c].gcm) == hdr.cx[c].gcv)
-                    x ^= hdr.cx[c].vec;
-            xoff[tid] = x;
-        }
-        if constexpr (PROF)
-            w_t0 = clock64();
-        mbar_wait_warp<40>(&full[bi], (k / kTileBuffers) & 1u);
-        group_sync(1 + grp, GT);
-        if constexpr (PROF) {
-            w_wait += clock64() - w_t0;
-            w_tiles++;
-        }
-
-#pragma unroll 1
-        for (int rd = 0; rd < n_rounds; rd++) {
-            // this thread's register group: logical base index (high half), storage slot (low half)
-            uint32_t acc = 0;
-#pragma unroll
-            for (int c = 0; c < NF; c++)
-                acc ^= (0u - ((static_cast<uint32_t>(tid) >> c) & 1u)) & hdr.round_col[rd][c];
-            const uint32_t base = acc >> 16;
-            const uint32_t pb = (acc & 0xffffu) ^ xoff[rd];
-            uint32_t poff[R];
-#pragma unroll
-            for (int s = 0; s < R; s++)
-                poff[s] = hdr.round_poff[rd][s];
-            const int o_begin = pp.hdr.round_begin[rd], o_end = pp.hdr.round_begin[rd + 1];
-            if constexpr (PROF)
-                w_r0 = clock64();
-            amp_t a[NS];
-#pragma unroll
-            for (int s = 0; s < NS; s++) {
-                uint32_t x = pb;
-#pragma unroll
-                for (int c = 0; c < R; c++)
-                    if (s & (1 << c))
-                        x ^= poff[c];
-                a[s] = tile[x];
-            }
-            // a zero the compiler cannot see through: the 2^R scatter addresses are recomputed
-            // after the arithmetic instead of being kept alive -- and spilled -- across the round
-            const uint32_t opaque_zero = pp.hdr.pad_[0];
-            const int kind = pp.hdr.round_kind[rd];
-            // fused store: the last round's registers go straight to HBM; the tile buffer is free
-            // as soon as every thread of the group has gathered from it
-            // staged store: the last round scatters in index order (after every gather of the group
-            // is done) and the group's store warp streams the buffer out in the background
-            const int fused = rd == n_rounds - 1 ? pp.hdr.fused_store : 0;
-            if (fused) {
-                group_sync(1 + grp, GT);
-                if (fused == 1 && tid == 0)
-                    mbar_arrive(&empty[bi]);
-            }
-            if (kind == 0) {
-#pragma unroll 1
-                for (int oi = o_begin; oi < o_end; oi++)
-                    run_op<R, NS, amp_t, real>(a, sops[oi], tbr, base);
-                finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
-            } else {
-                // dense round: gate k acts on register slot k; each case is straight-line code from
-                // the gathered registers to the scatter, so ptxas renames freely (no moves)
-                switch (kind) {
-#define B2_FACT(G)                                                                              \
-    case 8 + G:                                                                                 \
-        dense_factored<G, R, NS, amp_t, real>(a, pp.dense[pp.hdr.round_dense[rd]]);             \
-        finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, \
-                                tid);                                                           \
-        break;
-                    B2_FACT(2)
-                    B2_FACT(3)
-                    B2_FACT(4)
-                    B2_FACT(5)
-#undef B2_FACT
-                case 1:
-                    dense_round<1, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
-                    break;
-                case 2:
-                    dense_round<2, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
-                    break;
-                case 3:
-                    dense_round<3, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
-                    break;
-                case 4:
-                    dense_round<4, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
-                    break;
-                default:
-                    dense_round<5, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
-                    break;
-                }
-            }
-            if (fused == 2) {
-                fence_async_smem();
-                group_sync(1 + grp, GT);
-                if (tid == 0)
-                    mbar_arrive(&computed[bi]);
-            } else if (!fused) {
-                group_sync(1 + grp, GT);
-            }
-            if constexpr (PROF) {
-                if (fused)
-                    w_last += clock64() - w_r0;
-                else
-                    w_round += clock64() - w_r0;
-            }
-        }
-        if (pp.hdr.fused_store && n_rounds > 0)
-            continue; // stored from registers or handed to the store warp
-
-        // ---- shared -> HBM through the final address map
-        {
-            constexpr int NT = NF; // log2(GT)
-            uint32_t sl = xoff[n_rounds];
-#pragma unroll
-            for (int c = 0; c < NT; c++)
-                sl ^= (0u - ((static_cast<uint32_t>(tid) >> c) & 1u)) & hdr.final_col[c];
-            uint32_t ecol[B - NT];
-#pragma unroll
-            for (int c = 0; c < B - NT; c++)
-                ecol[c] = hdr.final_col[NT + c];
-#pragma unroll
-            for (int e = 0; e < EPT; e++) {
-                const uint32_t i = e * GT + tid;
-                uint32_t x = sl;
-#pragma unroll
-                for (int c = 0; c < B - NT; c++)
-                    if (e & (1 << c))
-                        x ^= ecol[c];
-                state[tb | rowoff[i >> low] | (i & lowmask)] = tile[x];
-            }
-        }
-        group_sync(1 + grp, GT); // every thread of the group is done with this buffer (and xoff)
-        if (tid == 0)
-            mbar_arrive(&empty[bi]);
-    }
-    if constexpr (PROF) {
-        if (tid == 0) {
-            const long long life = clock64() - t_start;
-            atomicAdd(&g_tile_prof[0], static_cast<unsigned long long>(w_wait));
-            atomicAdd(&g_tile_prof[1], static_cast<unsigned long long>(life - w_wait));
-            atomicAdd(&g_tile_prof[4], static_cast<unsigned long long>(w_tiles));
-            atomicAdd(&g_tile_prof[6], static_cast<unsigned long long>(w_last));
-            atomicAdd(&g_tile_prof[7], static_cast<unsigned long long>(w_round));
-        }
-    }
-}
-
-// ---- host side ----------------------------------------------------------------------------------
-namespace {
-constexpr int kMinLow = 4;
-template <typename real, int B, int NB> constexpr size_t tile_smem_bytes() {
-    return NB * sizeof(typename AmpT<real>::type) * (size_t(1) << B) +
-           sizeof(DevOp) * kMaxOpsPerPass + sizeof(uint64_t) * (size_t(1) << (B - kMinLow));
-}
-int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        CUDA_CHECK(cudaGetDevice(&dev));
-        CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    }
-    return n;
-}
-int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-bool tile_prof() {
-    static const bool v = env_int("B2SV_TILE_PROF", 0) != 0;
-    return v;
-}
-template <typename real, int B, int R, int GT, int NG, int NB, bool PROF>
-void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
-                    cudaStream_t stream) {
-    using amp_t = typename AmpT<real>::type;
-    auto kern = tile_exec_kernel<real, B, R, GT, NG, NB, PROF>;
-    constexpr size_t smem = tile_smem_bytes<real, B, NB>();
-    static bool configured = false;
-    if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-        configured = true;
-    }
-    const uint32_t n_tiles = 1u << (n_eff - B);
-    // one persistent CTA per SM; with fewer than 2 tiles per SM spread them one per CTA
-    const unsigned grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(sm_count()));
-    // the descriptor is copied into the launch's parameter buffer by the runtime at this call
-    kern<<<grid, NG * GT + kProducerThreads, smem, stream>>>(static_cast<amp_t *>(state), pp,
-                                                             rank_bits, n_tiles);
-    CUDA_CHECK(cudaGetLastError());
-}
-} // namespace
+void launch_tile_pass_c64(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
+                          cudaStream_t stream); // tile_kernel_c64.cu
 
 // Tile geometry per dtype: complex128 -> 2^12 amps (64 KiB), complex64 -> 2^13 amps (64 KiB);
 // three buffers per CTA (192 KiB of the 227 KiB an sm_100 CTA may use).
@@ -809,21 +15,17 @@ void tile_config(int dtype, int *B, int *R) {
 
 void launch_tile_pass(int dtype, void *state, const PassParams &pp, int n_eff,
                       uint64_t rank_bits, cudaStream_t stream) {
-    if (dtype == 1) {
-        if (tile_prof())
-            launch_variant<double, 12, 4, 256, 2, 3, true>(state, pp, n_eff, rank_bits, stream);
-        else
-            launch_variant<double, 12, 4, 256, 2, 3, false>(state, pp, n_eff, rank_bits, stream);
-    } else {
-        launch_variant<float, 13, 5, 256, 2, 3, false>(state, pp, n_eff, rank_bits, stream);
-    }
+    if (dtype == 1)
+        launch_tile_pass_t<double, 12, 4>(state, pp, n_eff, rank_bits, stream);
+    else
+        launch_tile_pass_c64(state, pp, n_eff, rank_bits, stream);
 }
 
-// Reads and clears the phase timers (zeros unless B2SV_TILE_PROF=1).
-void tile_prof_read(unsigned long long out[8]) {
+// Reads and clears the phase timers (zeros unless B2SV_TILE_PROF=1; complex128 kernels only).
+void tile_prof_read(unsigned long long out[16]) {
     CUDA_CHECK(cudaDeviceSynchronize());
-    CUDA_CHECK(cudaMemcpyFromSymbol(out, g_tile_prof, sizeof(unsigned long long) * 8));
-    unsigned long long z[8] = {0};
+    CUDA_CHECK(cudaMemcpyFromSymbol(out, g_tile_prof, sizeof(unsigned long long) * 16));
+    unsigned long long z[16] = {0};
     CUDA_CHECK(cudaMemcpyToSymbol(g_tile_prof, z, sizeof(z)));
 }
 

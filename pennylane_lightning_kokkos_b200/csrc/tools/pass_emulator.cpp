@@ -8,6 +8,7 @@
 // build: see tests/conftest.py (g++ -shared with ../schedule.cpp ../gates.cpp)
 #include "schedule.hpp"
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -118,7 +119,7 @@ template <typename real> struct Emu {
                     off |= uint64_t(1) << h.tile_bits[j];
             rowoff[r] = off;
         }
-        std::vector<amp> tile(TILE), a(NS), staged;
+        std::vector<amp> tile(TILE), a(NS);
         for (uint32_t t = 0; t < n_tiles; t++) {
             uint64_t tb = 0;
             for (int j = 0; j < h.n_seg; j++)
@@ -133,8 +134,6 @@ template <typename real> struct Emu {
                         xoff[r] ^= h.cx[c].vec;
             for (int rd = 0; rd < h.n_rounds; rd++) {
                 const int fused = rd == h.n_rounds - 1 ? h.fused_store : 0;
-                if (fused == 2 && staged.empty())
-                    staged.resize(TILE);
                 const int kind = h.round_kind[rd];
                 const int ob = h.round_begin[rd], oe = h.round_begin[rd + 1];
                 for (int tid = 0; tid < GT; tid++) {
@@ -157,7 +156,7 @@ template <typename real> struct Emu {
                         for (int oi = ob; oi < oe; oi++)
                             run_op(a.data(), ps.ops[oi], tbr, base);
                     } else if (kind >= 8) {
-                        dense_factored(a.data(), kind - 8, ps.dense[h.round_dense[rd]]);
+                        dense_factored(a.data(), kind - 8, ps.dense[rd]);
                     } else {
                         for (int k = 0; k < kind; k++) {
                             DevOp op = ps.ops[ob + k];
@@ -165,22 +164,7 @@ template <typename real> struct Emu {
                             run_op(a.data(), op, tbr, base);
                         }
                     }
-                    if (fused == 2) {
-                        uint32_t i0 = 0;
-                        for (int c = 0; c < NF; c++)
-                            if ((tid >> c) & 1)
-                                i0 ^= h.store_free_l[c];
-                        for (int c = 0; c < h.n_cx; c++)
-                            if ((tbr & h.cx[c].gcm) == h.cx[c].gcv)
-                                i0 ^= h.store_cx_l[c];
-                        for (int s = 0; s < NS; s++) {
-                            uint32_t x = i0;
-                            for (int c = 0; c < R; c++)
-                                if (s & (1 << c))
-                                    x ^= h.store_reg_l[c];
-                            staged[x] = a[s];
-                        }
-                    } else if (fused == 1) {
+                    if (fused == 1) {
                         uint64_t addr0 = tb;
                         for (int c = 0; c < NF; c++)
                             if ((tid >> c) & 1)
@@ -200,11 +184,6 @@ template <typename real> struct Emu {
                             tile[slot_addr(s)] = a[s];
                     }
                 }
-            }
-            if (h.fused_store == 2 && h.n_rounds > 0) { // rows of 2^low amplitudes, bulk-copied
-                for (uint32_t i = 0; i < static_cast<uint32_t>(TILE); i++)
-                    state[tb | rowoff[i >> h.low_bits] | (i & lowmask)] = staged[i];
-                continue;
             }
             if (h.fused_store && h.n_rounds > 0)
                 continue;
@@ -230,8 +209,8 @@ int run(int n, int B, int R, int low, int max_heavy, int factor, int store_mode,
     cfg.f32 = sizeof(real) == 4;
     cfg.factor = factor != 0;
     cfg.max_heavy = max_heavy;
+    cfg.lookahead = getenv("B2EMU_NO_LOOKAHEAD") == nullptr;
     cfg.fuse_store = store_mode != 0;
-    cfg.store_mode = store_mode;
     cfg.n_local = n;
     cfg.n_alloc = std::max(n, B);
     const int n_eff = cfg.n_alloc;
@@ -276,7 +255,8 @@ extern "C" {
 const char *b2emu_last_error() { return g_err.c_str(); }
 
 // names / wires / params as in b2sv_ops_create; state: 2^n interleaved (re, im) doubles, in place.
-// stats (6 values): passes, rounds, dense rounds, factored rounds, direct stores, staged stores.
+// stats (6 values): passes, rounds, dense rounds, factored rounds, fused stores, (unused).
+// store_mode: 0 = always the store phase, 1 = fused stores where the schedule allows.
 int b2emu_run(int n, int f32, int B, int R, int low, int max_heavy, int factor, int store_mode,
               int n_ops,
               const char **names, const int64_t *wires_flat, const int *nw, const int *inverse,

@@ -35,7 +35,7 @@ def lib():
     return _lib
 
 
-def run(circ, n, psi, f32=False, B=None, R=None, low=5, max_heavy=8, factor=True, store_mode=2):
+def run(circ, n, psi, f32=False, B=None, R=None, low=5, max_heavy=8, factor=True, store_mode=1):
     """Apply `circ` [(name, wires, inverse, params)] to psi through schedule + emulated passes."""
     B = B or (13 if f32 else 12)
     R = R or (5 if f32 else 4)
@@ -54,5 +54,5 @@ def run(circ, n, psi, f32=False, B=None, R=None, low=5, max_heavy=8, factor=True
                          stats.ctypes.data_as(C.c_void_p))
     if rc != 0:
         raise RuntimeError(lib().b2emu_last_error().decode())
-    keys = ("passes", "rounds", "dense", "factored", "direct_stores", "staged_stores")
+    keys = ("passes", "rounds", "dense", "factored", "fused_stores", "unused")
     return st, dict(zip(keys, (int(x) for x in stats)))

@@ -29,7 +29,7 @@ def test_layered_circuit_factored_rounds(factor):
     assert st["rounds"] == st["dense"] + st["factored"]
 
 
-@pytest.mark.parametrize("max_heavy", [1, 4, 12, 16])
+@pytest.mark.parametrize("max_heavy", [0, 1, 4, 12, 16])
 def test_layered_circuit_pass_budgets(max_heavy):
     n = 13
     check(layered_circuit(n, 2, seed=7), n, max_heavy=max_heavy)
@@ -41,17 +41,12 @@ def test_layered_circuit_c64_tables_in_float():
     assert st["factored"] > 0
 
 
-@pytest.mark.parametrize("store_mode", [0, 1, 2])
+@pytest.mark.parametrize("store_mode", [0, 1])
 def test_store_modes(store_mode):
     n = 14
     st = check(layered_circuit(n, 3, seed=21), n, store_mode=store_mode)
     check(random_circuit(n, 200, seed=store_mode), n, store_mode=store_mode)
-    if store_mode == 0:
-        assert st["direct_stores"] == 0 and st["staged_stores"] == 0
-    elif store_mode == 1:
-        assert st["direct_stores"] > 0 and st["staged_stores"] == 0
-    else:
-        assert st["staged_stores"] >= st["passes"] - 1
+    assert (st["fused_stores"] > 0) == (store_mode == 1)
 
 
 @pytest.mark.parametrize("B,low", [(11, 5), (12, 4), (12, 6)])
