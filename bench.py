@@ -45,7 +45,7 @@ if ROOT not in sys.path:
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 TOUCH = {"RX": 1.0, "RY": 1.0, "RZ": 1.0, "CNOT": 0.5}
-NCU_TRAFFIC_30Q = 34.319e9  # bytes per tile-kernel launch, see profiles/
+NCU_TRAFFIC_30Q = 34.328e9  # dram read + write bytes per tile-kernel launch (profiles/r1_ncu_tile_v20.summary.txt)
 
 
 def layer_circuit(n, layers, seed=42):
@@ -351,9 +351,9 @@ def run_b200(args):
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                # (profiles/r1_ncu_tile_v16.summary.txt at n = 30)
+                # (profiles/r1_ncu_tile_v20.summary.txt at n = 30)
                 "traffic": NCU_TRAFFIC_30Q if args.qubits == 30 else None, "peak_source": which,
-                "kernel": "tile_exec_kernel<double,12,4,256,2,3> (persistent, 148 CTAs x 640 threads)",
+                "kernel": "tile_exec_kernel<double,12,4,256,2,3,FACT> (persistent, 148 CTAs x 640 threads)",
                 "algorithmic_bytes_per_launch": sweep_bytes,
                 "avg_launch_ms": avg_launch_ms,
                 "note": "achieved = 2*16*2^n bytes per tile-kernel launch / (CUDA-event time of the "

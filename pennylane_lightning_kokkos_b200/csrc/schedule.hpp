@@ -23,7 +23,7 @@ constexpr int kMaxTileBits = 16;
 constexpr int kMaxRegBits = 5;
 constexpr int kMaxFreeBits = 12; // tile bits that are not register bits (= log2 threads)
 constexpr int kMaxCx = 32;       // conditional address toggles per pass
-constexpr int kMaxDense = 8;     // rounds 0 .. kMaxDense-1 of a pass may run in factored form
+constexpr int kMaxDense = 6;     // rounds 0 .. kMaxDense-1 of a pass may run in factored form
 
 enum OpKind : uint8_t { KIND_GENERAL = 0, KIND_REAL = 1, KIND_PERM = 2, KIND_DIAG = 3 };
 // flag bits stored in DevOp::kind above the OpKind

@@ -459,10 +459,12 @@ struct TileInfo {
     uint32_t pad_;
 };
 
-// FACT / INTERP: the kernel contains the factored-round bodies / the per-op interpreter. A pass is
+// FACT / INTERP / DENSEK: the kernel contains the factored-round bodies / the per-op interpreter / the
+// unfactored dense rounds of 2..5 gates (one-gate dense rounds are in every variant). A pass is
 // launched on the leanest variant that covers its rounds: code the pass never runs would still cost
 // it registers (ptxas allocates for the union of all paths of the round loop).
-template <typename real, int B, int R, int GT, int NG, int NB, bool FACT, bool INTERP, bool PROF>
+template <typename real, int B, int R, int GT, int NG, int NB, bool FACT, bool INTERP, bool DENSEK,
+          bool PROF>
 __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
     tile_exec_kernel(typename AmpT<real>::type *__restrict__ state,
                      const __grid_constant__ PassParams pp, uint64_t rank_bits,
@@ -685,7 +687,9 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
             } else if (kind >= 8) {
                 if constexpr (!FACT)
                     __trap(); // the launcher picked a variant without the factored bodies
-                // factored dense round; the first four rounds of a pass use compile-time table offsets
+                // factored dense round; the first four rounds of a pass use compile-time table offsets (LDCU),
+                // later ones index the table at run time (LDC). Measured: giving rounds 4 and 5 fixed
+                // offsets too makes ptxas' code for the whole loop 10 % slower, so they stay generic.
                 bool done = false;
                 if constexpr (FACT)
                 switch (rd) {
@@ -729,21 +733,29 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
                     dense_round<1, R, NS, amp_t, real>(a, pp.ops + o_begin);
                     finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
                     break;
-                case 2:
-                    dense_round<2, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
-                    break;
-                case 3:
-                    dense_round<3, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
-                    break;
-                case 4:
-                    dense_round<4, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
-                    break;
                 default:
-                    dense_round<5, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
+                    if constexpr (DENSEK) {
+                        switch (kind) {
+                        case 2:
+                            dense_round<2, R, NS, amp_t, real>(a, pp.ops + o_begin);
+                            finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
+                            break;
+                        case 3:
+                            dense_round<3, R, NS, amp_t, real>(a, pp.ops + o_begin);
+                            finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
+                            break;
+                        case 4:
+                            dense_round<4, R, NS, amp_t, real>(a, pp.ops + o_begin);
+                            finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
+                            break;
+                        default:
+                            dense_round<5, R, NS, amp_t, real>(a, pp.ops + o_begin);
+                            finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
+                            break;
+                        }
+                    } else {
+                        __trap(); // the launcher picked a variant without these bodies
+                    }
                     break;
                 }
             }
@@ -822,11 +834,12 @@ bool tile_prof() {
     static const bool v = env_int("B2SV_TILE_PROF", 0) != 0;
     return v;
 }
-template <typename real, int B, int R, int GT, int NG, int NB, bool FACT, bool INTERP, bool PROF>
+template <typename real, int B, int R, int GT, int NG, int NB, bool FACT, bool INTERP, bool DENSEK,
+          bool PROF>
 void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
                     cudaStream_t stream) {
     using amp_t = typename AmpT<real>::type;
-    auto kern = tile_exec_kernel<real, B, R, GT, NG, NB, FACT, INTERP, PROF>;
+    auto kern = tile_exec_kernel<real, B, R, GT, NG, NB, FACT, INTERP, DENSEK, PROF>;
     constexpr size_t smem = tile_smem_bytes<real, B, NB>();
     static bool configured = false;
     if (!configured) {
@@ -848,21 +861,23 @@ void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_
 template <typename real, int B, int R>
 void launch_tile_pass_t(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
                         cudaStream_t stream) {
-    bool fact = false, interp = false;
+    bool fact = false, interp = false, densek = false;
     for (int rd = 0; rd < pp.hdr.n_rounds; rd++) {
-        fact |= pp.hdr.round_kind[rd] >= 8;
-        interp |= pp.hdr.round_kind[rd] == 0;
+        const int kind = pp.hdr.round_kind[rd];
+        fact |= kind >= 8;
+        interp |= kind == 0;
+        densek |= kind >= 2 && kind < 8;
     }
     if (tile_prof())
-        launch_variant<real, B, R, 256, 2, 3, true, true, true>(state, pp, n_eff, rank_bits, stream);
-    else if (fact && interp)
-        launch_variant<real, B, R, 256, 2, 3, true, true, false>(state, pp, n_eff, rank_bits, stream);
-    else if (fact)
-        launch_variant<real, B, R, 256, 2, 3, true, false, false>(state, pp, n_eff, rank_bits, stream);
-    else if (interp)
-        launch_variant<real, B, R, 256, 2, 3, false, true, false>(state, pp, n_eff, rank_bits, stream);
+        launch_variant<real, B, R, 256, 2, 3, true, true, true, true>(state, pp, n_eff, rank_bits, stream);
+    else if (fact && !interp && !densek) // layered circuits: factored rounds (+ single gates)
+        launch_variant<real, B, R, 256, 2, 3, true, false, false, false>(state, pp, n_eff, rank_bits, stream);
+    else if (!fact && !interp)           // unfactored dense rounds, single gates, permutation-only passes
+        launch_variant<real, B, R, 256, 2, 3, false, false, true, false>(state, pp, n_eff, rank_bits, stream);
+    else if (!fact)                      // controlled / diagonal ops through the interpreter
+        launch_variant<real, B, R, 256, 2, 3, false, true, true, false>(state, pp, n_eff, rank_bits, stream);
     else
-        launch_variant<real, B, R, 256, 2, 3, false, false, false>(state, pp, n_eff, rank_bits, stream);
+        launch_variant<real, B, R, 256, 2, 3, true, true, true, false>(state, pp, n_eff, rank_bits, stream);
 }
 } // namespace
 
