@@ -412,7 +412,7 @@ struct BitList {
 constexpr int kMargSmemBits = 11;
 template <typename amp_t, bool PRIVATE>
 __global__ void __launch_bounds__(256)
-    k_probs_marginal(const amp_t *__restrict__ s, uint64_t len, BitList bl,
+    k_probs_marginal(const amp_t *__restrict__ s, uint64_t len, BitList bl, uint64_t index_or,
                      double *__restrict__ out) {
     __shared__ double hist[PRIVATE ? (1 << kMargSmemBits) : 1];
     const int nb = 1 << bl.m;
@@ -426,8 +426,9 @@ __global__ void __launch_bounds__(256)
         const amp_t a = s[i];
         const double p = double(a.x) * a.x + double(a.y) * a.y;
         uint64_t bin = 0;
+        const uint64_t gi = i | index_or; // sharded states: the rank supplies the top index bits
         for (int j = 0; j < bl.m; j++)
-            bin |= ((i >> bl.pos[j]) & 1ull) << (bl.m - 1 - j);
+            bin |= ((gi >> bl.pos[j]) & 1ull) << (bl.m - 1 - j);
         if (PRIVATE)
             atomicAdd(&hist[bin], p);
         else if (p != 0.0)
@@ -505,15 +506,27 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
 template <typename amp_t>
 __global__ void __launch_bounds__(256)
     k_sample(const amp_t *__restrict__ s, uint64_t len, const double *__restrict__ ccdf,
-             uint64_t nchunks, int nq, size_t shots, uint64_t seed,
+             uint64_t nchunks, int nq, size_t shots, uint64_t seed, ShardCdf sh,
              unsigned long long *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const size_t shot = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (shot >= shots)
         return;
-    const double total = ccdf[nchunks];
+    // Sharded states: every rank draws the same U in (0, global total]; the rank whose interval
+    // (offset, offset + local total] holds it resolves the shot, the others write zeros (the outputs
+    // are summed over the ranks afterwards).
+    const double total = sh.sharded ? sh.global_total : ccdf[nchunks];
     const uint64_t r = splitmix64(seed ^ splitmix64(shot));
-    const double U = (double((r >> 11) + 1) * 0x1.0p-53) * total; // (0, total]
+    double U = (double((r >> 11) + 1) * 0x1.0p-53) * total; // (0, total]
+    if (sh.sharded) {
+        if (!(sh.offset < U && U <= sh.upper)) {
+            if (lane == 0)
+                for (int j = 0; j < nq; j++)
+                    out[shot * nq + j] = 0ull;
+            return;
+        }
+        U -= sh.offset;
+    }
     // binary search over chunks: largest c with ccdf[c] < U
     uint64_t lo = 0, hi = nchunks; // invariant: ccdf[lo] < U (ccdf[0] = 0 < U), answer in [lo, hi)
     while (hi - lo > 1) {
@@ -556,10 +569,23 @@ __global__ void __launch_bounds__(256)
     }
     if (!have)
         found = last_nz; // rounding at the chunk end: fall back to the last populated entry
+    found |= sh.index_or;
     if (lane == 0) {
         for (int j = 0; j < nq; j++) // MSB (wire 0) first, as the reference (MF.hpp:113-115)
             out[shot * nq + (nq - 1 - j)] = (found >> j) & 1ull;
     }
+}
+
+// 0/1 sample bits <-> doubles, in place (so that the all-reduce over ranks can sum them)
+__global__ void k_u64_to_f64(unsigned long long *p, size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+        reinterpret_cast<double *>(p)[i] = static_cast<double>(p[i]);
+}
+__global__ void k_f64_to_u64(unsigned long long *p, size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+        p[i] = static_cast<unsigned long long>(reinterpret_cast<double *>(p)[i] + 0.5);
 }
 
 int reduce_grid(uint64_t work) {
@@ -586,19 +612,36 @@ template <typename amp_t>
 __global__ void __launch_bounds__(256)
     k_peer_swap(amp_t *__restrict__ mine, amp_t *__restrict__ peer, uint64_t npairs, int lbit,
                 int selbit, int my_bit) {
+    // Four pairs per thread and iteration: all eight loads (four of them NVLink round trips) are in
+    // flight before the first store, which is what keeps the link busy.
+    constexpr int U = 4;
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-    for (uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < npairs;
-         k += stride) {
-        // k enumerates local indices with bits {lbit, selbit} removed (lbit != selbit)
-        const int p0 = lbit < selbit ? lbit : selbit, p1 = lbit < selbit ? selbit : lbit;
-        uint64_t i = insert_zero(insert_zero(k, p0), p1);
-        i |= static_cast<uint64_t>(my_bit) << selbit;
-        const uint64_t im = i | (static_cast<uint64_t>(1 - my_bit) << lbit); // my half to give away
-        const uint64_t ip = i | (static_cast<uint64_t>(my_bit) << lbit);     // partner's half
-        const amp_t a = mine[im];
-        const amp_t b = peer[ip];
-        mine[im] = b;
-        peer[ip] = a;
+    const int p0 = lbit < selbit ? lbit : selbit, p1 = lbit < selbit ? selbit : lbit;
+    for (uint64_t k0 = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k0 < npairs;
+         k0 += stride * U) {
+        uint64_t im[U], ip[U];
+        amp_t a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            // k enumerates local indices with bits {lbit, selbit} removed (lbit != selbit)
+            const uint64_t k = k0 + u * stride;
+            uint64_t i = insert_zero(insert_zero(k < npairs ? k : k0, p0), p1);
+            i |= static_cast<uint64_t>(my_bit) << selbit;
+            im[u] = i | (static_cast<uint64_t>(1 - my_bit) << lbit); // my half to give away
+            ip[u] = i | (static_cast<uint64_t>(my_bit) << lbit);     // partner's half
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            b[u] = peer[ip[u]];
+            a[u] = mine[im[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (k0 + u * stride < npairs) {
+                peer[ip[u]] = a[u];
+                mine[im[u]] = b[u];
+            }
+        }
     }
 }
 void launch_peer_swap(int dtype, void *mine, void *peer, int n_local, int lbit, int my_bit,
@@ -742,7 +785,7 @@ void launch_probs_full(int dtype, const void *state, uint64_t len, double *d_out
                    (k_probs_full<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, d_out)));
 }
 void launch_probs_marginal(int dtype, const void *state, uint64_t len, const int *h_bitpos, int m,
-                           double *d_out, cudaStream_t st) {
+                           uint64_t index_or, double *d_out, cudaStream_t st) {
     BitList bl{};
     bl.m = m;
     for (int j = 0; j < m; j++)
@@ -750,12 +793,12 @@ void launch_probs_marginal(int dtype, const void *state, uint64_t len, const int
     const int grid = reduce_grid(len);
     if (m <= kMargSmemBits) {
         DISPATCH_DTYPE(dtype,
-                       (k_probs_marginal<float2, true><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), len, bl, d_out)),
-                       (k_probs_marginal<double2, true><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, bl, d_out)));
+                       (k_probs_marginal<float2, true><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), len, bl, index_or, d_out)),
+                       (k_probs_marginal<double2, true><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, bl, index_or, d_out)));
     } else {
         DISPATCH_DTYPE(dtype,
-                       (k_probs_marginal<float2, false><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), len, bl, d_out)),
-                       (k_probs_marginal<double2, false><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, bl, d_out)));
+                       (k_probs_marginal<float2, false><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), len, bl, index_or, d_out)),
+                       (k_probs_marginal<double2, false><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, bl, index_or, d_out)));
     }
 }
 void launch_chunk_sums(int dtype, const void *state, uint64_t len, double *d_chunk,
@@ -772,13 +815,24 @@ void launch_scan_chunks(double *d_chunk, uint64_t nchunks, cudaStream_t st) {
 }
 void launch_sample(int dtype, const void *state, uint64_t len, const double *d_chunk_cdf,
                    uint64_t nchunks, int num_qubits, size_t shots, uint64_t seed,
-                   unsigned long long *d_out, cudaStream_t st) {
+                   const ShardCdf &sh, unsigned long long *d_out, cudaStream_t st) {
     if (shots == 0)
         return;
     const int grid = static_cast<int>((shots * 32 + 255) / 256);
     DISPATCH_DTYPE(dtype,
-                   (k_sample<float2><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), len, d_chunk_cdf, nchunks, num_qubits, shots, seed, d_out)),
-                   (k_sample<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, d_chunk_cdf, nchunks, num_qubits, shots, seed, d_out)));
+                   (k_sample<float2><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), len, d_chunk_cdf, nchunks, num_qubits, shots, seed, sh, d_out)),
+                   (k_sample<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, d_chunk_cdf, nchunks, num_qubits, shots, seed, sh, d_out)));
+}
+
+void launch_bits_to_f64(unsigned long long *d, size_t n, cudaStream_t st) {
+    if (n)
+        k_u64_to_f64<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d, n);
+    CUDA_CHECK(cudaGetLastError());
+}
+void launch_f64_to_bits(unsigned long long *d, size_t n, cudaStream_t st) {
+    if (n)
+        k_f64_to_u64<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d, n);
+    CUDA_CHECK(cudaGetLastError());
 }
 
 } // namespace b2sv

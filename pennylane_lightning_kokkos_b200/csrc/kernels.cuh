@@ -76,14 +76,25 @@ void launch_csr_spmv(int dtype, const void *x, void *y, const double2 *d_data,
 void launch_probs_full(int dtype, const void *state, uint64_t len, double *d_out, cudaStream_t st);
 // d_out must be zeroed; bitpos[j] = index bit of requested wire j (wire order = output bit order,
 // first wire = MSB of the output index)
+// index_or: ORed into the local index before the bits are read (rank << n_local on sharded states)
 void launch_probs_marginal(int dtype, const void *state, uint64_t len, const int *h_bitpos, int m,
-                           double *d_out, cudaStream_t st);
+                           uint64_t index_or, double *d_out, cudaStream_t st);
 constexpr int kSampleChunkBits = 12;
 void launch_chunk_sums(int dtype, const void *state, uint64_t len, double *d_chunk,
                        cudaStream_t st);
 void launch_scan_chunks(double *d_chunk, uint64_t nchunks, cudaStream_t st); // exclusive, + total
+// where this shard sits in the global cumulative distribution (all zero / false on one GPU)
+struct ShardCdf {
+    int sharded;          // 0: the state is not sharded, the fields below are ignored
+    double offset;        // probability mass held by the lower ranks
+    double upper;         // offset + this rank's mass, computed the same way on every rank
+    double global_total;  // sum over all ranks
+    uint64_t index_or;    // rank << n_local
+};
 void launch_sample(int dtype, const void *state, uint64_t len, const double *d_chunk_cdf,
                    uint64_t nchunks, int num_qubits, size_t shots, uint64_t seed,
-                   unsigned long long *d_out, cudaStream_t st);
+                   const ShardCdf &sh, unsigned long long *d_out, cudaStream_t st);
+void launch_bits_to_f64(unsigned long long *d, size_t n, cudaStream_t st); // in place
+void launch_f64_to_bits(unsigned long long *d, size_t n, cudaStream_t st); // in place
 
 } // namespace b2sv

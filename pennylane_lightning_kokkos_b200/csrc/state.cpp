@@ -398,13 +398,19 @@ void State::apply_prims_sharded(std::vector<Prim> pending) {
             }
         }
         for (int q : need) {
+            // victim: farthest next use (Belady), but not a qubit that sits on one of the low index
+            // bits -- swapping those moves 16..256-byte pieces and halves the NVLink efficiency
             int victim = -1;
-            for (int o = 0; o < n_; o++) {
-                if (l2p_[o] >= n_local_ || ((need_mask >> o) & 1))
-                    continue;
-                if (victim < 0 || next_use[o] > next_use[victim] ||
-                    (next_use[o] == next_use[victim] && l2p_[o] > l2p_[victim]))
-                    victim = o;
+            for (int min_pos : {5, 0}) {
+                for (int o = 0; o < n_; o++) {
+                    if (l2p_[o] >= n_local_ || l2p_[o] < min_pos || ((need_mask >> o) & 1))
+                        continue;
+                    if (victim < 0 || next_use[o] > next_use[victim] ||
+                        (next_use[o] == next_use[victim] && l2p_[o] > l2p_[victim]))
+                        victim = o;
+                }
+                if (victim >= 0)
+                    break;
             }
             B2_ASSERT(victim >= 0);
             swap_phys(l2p_[q], l2p_[victim]);
@@ -721,7 +727,8 @@ void State::axpy(cplx alpha, const State &x) {
 // ---- probabilities / sampling -----------------------------------------------------------------------
 void State::probs(const std::vector<int64_t> &wires_in, double *out) const {
     CUDA_CHECK(cudaSetDevice(device_));
-    B2_ABORT_IF(world_ > 1, "probs on a sharded state: use the per-rank slices");
+    if (comm_)
+        normalize_layout(); // wire w <-> index bit n-1-w again, rank = top bits
     std::vector<int64_t> wires = wires_in;
     bool all_sorted = wires.empty();
     if (!wires.empty() && static_cast<int>(wires.size()) == n_) {
@@ -730,12 +737,15 @@ void State::probs(const std::vector<int64_t> &wires_in, double *out) const {
             all_sorted = all_sorted && wires[i] == i;
     }
     double *d_p;
-    if (all_sorted) { // MK.hpp:389-408
+    if (all_sorted && !comm_) { // MK.hpp:389-408
         const uint64_t len = local_length();
         CUDA_CHECK(cudaMallocAsync(&d_p, sizeof(double) * len, stream_));
         launch_probs_full(dtype_, d_state_, len, d_p, stream_);
         CUDA_CHECK(cudaMemcpyAsync(out, d_p, sizeof(double) * len, cudaMemcpyDeviceToHost, stream_));
     } else { // MK.hpp:418-517, result directly in the requested wire order
+        if (wires.empty())
+            for (int i = 0; i < n_; i++)
+                wires.push_back(i);
         // Output digit j reports wire wires[argsort[argsort[j]]]: the reference's transposition
         // (MeasuresFunctors.hpp:162-191, MK.hpp:493-509) uses argsort where rank is meant, and
         // its own literals pin that (src/tests/Test_StateVectorKokkos_Measure.cpp:21-46). For sorted
@@ -750,9 +760,16 @@ void State::probs(const std::vector<int64_t> &wires_in, double *out) const {
         const std::vector<int> bits = wires_to_bits(eff, n_);
         const int m = static_cast<int>(bits.size());
         const uint64_t nb = uint64_t(1) << m;
+        // Sharded: every rank bins its shard into the full 2^m histogram (its rank supplies the
+        // values of the global wires), then the histograms are summed over the ranks.
+        B2_ABORT_IF(comm_ && nb > (uint64_t(1) << 30),
+                    "probs over more than 30 wires of a sharded state does not fit one all-reduce");
         CUDA_CHECK(cudaMallocAsync(&d_p, sizeof(double) * nb, stream_));
         CUDA_CHECK(cudaMemsetAsync(d_p, 0, sizeof(double) * nb, stream_));
-        launch_probs_marginal(dtype_, d_state_, local_length(), bits.data(), m, d_p, stream_);
+        launch_probs_marginal(dtype_, d_state_, local_length(), bits.data(), m,
+                              uint64_t(rank_) << n_local_, d_p, stream_);
+        if (comm_)
+            comm_allreduce_sum(comm_.get(), d_p, static_cast<int>(nb), stream_);
         CUDA_CHECK(cudaMemcpyAsync(out, d_p, sizeof(double) * nb, cudaMemcpyDeviceToHost, stream_));
     }
     CUDA_CHECK(cudaFreeAsync(d_p, stream_));
@@ -762,9 +779,10 @@ void State::probs(const std::vector<int64_t> &wires_in, double *out) const {
 
 void State::generate_samples(size_t shots, uint64_t seed, uint64_t *out) const {
     CUDA_CHECK(cudaSetDevice(device_));
-    B2_ABORT_IF(world_ > 1, "sampling on a sharded state is not supported yet");
     if (shots == 0)
         return;
+    if (comm_)
+        normalize_layout();
     const uint64_t len = local_length();
     const uint64_t csz = uint64_t(1) << kSampleChunkBits;
     const uint64_t nchunks = (len + csz - 1) / csz;
@@ -774,7 +792,38 @@ void State::generate_samples(size_t shots, uint64_t seed, uint64_t *out) const {
     CUDA_CHECK(cudaMallocAsync(&d_s, sizeof(unsigned long long) * shots * n_, stream_));
     launch_chunk_sums(dtype_, d_state_, len, d_chunk, stream_);
     launch_scan_chunks(d_chunk, nchunks, stream_);
-    launch_sample(dtype_, d_state_, len, d_chunk, nchunks, n_, shots, seed, d_s, stream_);
+    ShardCdf sh{};
+    if (comm_) {
+        // every rank learns every rank's probability mass (one small all-reduce), and builds the same
+        // prefix sums, so the ranks' intervals tile (0, total] without gaps or overlaps
+        B2_ABORT_IF(world_ > 64, "sharded sampling supports up to 64 ranks");
+        B2_ABORT_IF(shots * static_cast<size_t>(n_) > (size_t(1) << 30),
+                    "too many sample bits for one all-reduce");
+        double mass[64] = {0};
+        CUDA_CHECK(cudaMemsetAsync(d_out_, 0, sizeof(double) * 64, stream_));
+        CUDA_CHECK(cudaMemcpyAsync(d_out_ + rank_, d_chunk + nchunks, sizeof(double),
+                                   cudaMemcpyDeviceToDevice, stream_));
+        comm_allreduce_sum(comm_.get(), d_out_, world_, stream_);
+        CUDA_CHECK(cudaMemcpyAsync(mass, d_out_, sizeof(double) * world_, cudaMemcpyDeviceToHost, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        double run = 0.0;
+        for (int r = 0; r < world_; r++) {
+            if (r == rank_)
+                sh.offset = run;
+            run += mass[r];
+            if (r == rank_)
+                sh.upper = run;
+        }
+        sh.sharded = 1;
+        sh.global_total = run;
+        sh.index_or = uint64_t(rank_) << n_local_;
+    }
+    launch_sample(dtype_, d_state_, len, d_chunk, nchunks, n_, shots, seed, sh, d_s, stream_);
+    if (comm_) {
+        launch_bits_to_f64(d_s, shots * n_, stream_);
+        comm_allreduce_sum(comm_.get(), reinterpret_cast<double *>(d_s), static_cast<int>(shots * n_), stream_);
+        launch_f64_to_bits(d_s, shots * n_, stream_);
+    }
     CUDA_CHECK(cudaMemcpyAsync(out, d_s, sizeof(unsigned long long) * shots * n_,
                                cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaFreeAsync(d_chunk, stream_));

@@ -62,6 +62,24 @@ def main():
                 print(f"  {case} {np.dtype(dtype).name} n={n_eff} world={world}: amp err {err:.2e} "
                       f"expval err {e2:.2e} swaps {stats['swaps']} path {stats['path']}", flush=True)
             assert err < tol and e2 < tol, (case, dtype, err, e2)
+            # marginal probabilities over global + local wires (all-reduced histograms) and sampling
+            # (one shared random stream; each shot resolved by the rank that owns its interval)
+            for pw in ([0, g, n_eff - 1], [1, 2], list(range(min(n_eff, 10)))):
+                pw = sorted(set(pw))
+                got_p = sv.probs(pw)
+                want_p = npo.probs(want, n_eff, pw)
+                ep = float(np.max(np.abs(got_p - want_p)))
+                assert ep < (1e-12 if dtype == np.complex128 else 2e-6), (case, dtype, pw, ep)
+            shots = 4000
+            smp = sv.GenerateSamples(n_eff, shots)
+            assert smp.shape == (shots, n_eff) and smp.max() <= 1
+            t_s = torch.from_numpy(smp.astype(np.int64)).cuda()
+            t_0 = t_s.clone()
+            dist.broadcast(t_0, src=0)
+            assert bool((t_s == t_0).all()), "ranks disagree on the samples"
+            freq = smp[:, [0, n_eff - 1]].mean(axis=0)  # P(bit = 1) of a global and a local wire
+            p1 = [npo.probs(want, n_eff, [w])[1] for w in (0, n_eff - 1)]
+            assert max(abs(a - b) for a, b in zip(freq, p1)) < 0.05, (freq, p1)
             if rank == 0 and dtype == np.complex128:
                 single = ops.LightningKokkos_C128(n_eff)
                 single.apply([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ],
