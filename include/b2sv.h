@@ -153,6 +153,11 @@ int b2sv_obs_apply(const b2sv_obs *ob, b2sv_state *s);                          
 int b2sv_adjoint_jacobian(const b2sv_state *s, b2sv_obs *const *obs, int n_obs,
                           const b2sv_ops *ops, const uint64_t *trainable_params, int n_tp,
                           double *jac_out);
+/* vector-Jacobian product sum_o dy[o] * jac[o][p] (lightning_kokkos.py:689-727 vjp): computed as the
+ * adjoint Jacobian of the single Hamiltonian sum_o dy[o] O_o, i.e. one reverse sweep. vjp_out: n_tp */
+int b2sv_adjoint_vjp(const b2sv_state *s, b2sv_obs *const *obs, int n_obs, const double *dy,
+                     const b2sv_ops *ops, const uint64_t *trainable_params, int n_tp,
+                     double *vjp_out);
 
 #ifdef __cplusplus
 }

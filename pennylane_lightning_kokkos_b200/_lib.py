@@ -92,6 +92,7 @@ PROTOTYPES = {
     "b2sv_obs_wires": (C.c_int, [vp, i64p, C.c_int, ip]),
     "b2sv_obs_apply": (C.c_int, [vp, vp]),
     "b2sv_adjoint_jacobian": (C.c_int, [vp, C.POINTER(vp), C.c_int, vp, u64p, C.c_int, dp]),
+    "b2sv_adjoint_vjp": (C.c_int, [vp, C.POINTER(vp), C.c_int, dp, vp, u64p, C.c_int, dp]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

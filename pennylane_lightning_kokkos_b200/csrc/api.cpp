@@ -483,4 +483,31 @@ int b2sv_adjoint_jacobian(const b2sv_state *s, b2sv_obs *const *obs, int n_obs,
                          std::vector<uint64_t>(trainable_params, trainable_params + n_tp), jac_out);
     });
 }
+int b2sv_adjoint_vjp(const b2sv_state *s, b2sv_obs *const *obs, int n_obs, const double *dy,
+                     const b2sv_ops *ops, const uint64_t *trainable_params, int n_tp,
+                     double *vjp_out) {
+    return guard([&] {
+        B2_ABORT_IF(!ops, "null ops handle");
+        B2_ABORT_IF(!dy || !vjp_out, "null buffer");
+        // lightning_kokkos.py:689-727: the vector-Jacobian product of expectation values is the
+        // adjoint Jacobian of ONE observable, the Hamiltonian sum_i dy_i O_i -- one reverse sweep
+        // whatever the number of measurements
+        std::vector<ObsPtr> v;
+        for (int i = 0; i < n_obs; i++) {
+            B2_ABORT_IF(!obs[i] || !obs[i]->o, "null observable handle");
+            v.push_back(obs[i]->o);
+        }
+        bool all_zero = true;
+        for (int i = 0; i < n_obs; i++)
+            all_zero = all_zero && dy[i] == 0.0;
+        if (all_zero || n_tp == 0) { // lightning_kokkos.py:701-702
+            for (int i = 0; i < n_tp; i++)
+                vjp_out[i] = 0.0;
+            return;
+        }
+        std::vector<ObsPtr> ham = {make_hamiltonian_obs(std::vector<double>(dy, dy + n_obs), v)};
+        adjoint_jacobian(st(s), ham, ops->d,
+                         std::vector<uint64_t>(trainable_params, trainable_params + n_tp), vjp_out);
+    });
+}
 }

@@ -501,6 +501,27 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
                                             jac.ctypes.data_as(_lib.dp)))
             return jac.astype(rdtype, copy=False)
 
+        def vjp(self, sv, observables, operations, trainable_params, dy):
+            """Vector-Jacobian product ``dy @ jac`` the way the reference device computes it
+            (lightning_kokkos.py:689-727): the adjoint Jacobian of the one Hamiltonian
+            ``sum_i dy[i] * observables[i]`` -- a single reverse sweep."""
+            dy = np.asarray(dy)
+            if np.iscomplexobj(dy):  # lightning_kokkos.py:709-712
+                raise ValueError("The vjp method only works with a real-valued dy when the tape is "
+                                 "returning an expectation value")
+            if dy.size != len(observables):  # lightning_kokkos.py:704-707
+                raise ValueError("Number of observables in the tape must be the same as the length "
+                                 "of dy in the vjp method")
+            tp = np.ascontiguousarray(trainable_params, dtype=np.uint64).ravel()
+            n_obs = len(observables)
+            out = np.zeros(tp.size, dtype=np.float64)
+            oarr = (C.c_void_p * n_obs)(*[o._h for o in observables])
+            _, dyp, _n = _f64(dy.astype(np.float64).ravel())
+            check(lib.b2sv_adjoint_vjp(sv._h, oarr, n_obs, dyp, operations._h,
+                                       tp.ctypes.data_as(_lib.u64p), int(tp.size),
+                                       out.ctypes.data_as(_lib.dp)))
+            return out.astype(rdtype, copy=False)
+
     for cls, nm in ((NamedObs, "NamedObsKokkos"), (HermitianObs, "HermitianObsKokkos"),
                     (TensorProdObs, "TensorProdObsKokkos"), (Hamiltonian, "HamiltonianKokkos"),
                     (SparseHamiltonian, "SparseHamiltonianKokkos"), (OpsStruct, "OpsStructKokkos"),

@@ -483,6 +483,16 @@ def test_adjoint_vs_reference(ops, ref, dtype, n, layers):
     assert jac.shape == want.shape == (3, len(tp))
     tol = 1e-12 if dtype == np.complex128 else 2e-5
     assert rel_err(jac, want) < tol
+    # vjp (lightning_kokkos.py:689-727): one reverse sweep over the Hamiltonian sum_i dy_i O_i
+    dy = np.array([0.7, -1.3, 0.25])
+    got_vjp = adj.vjp(sv, g_all, ol, tp, dy)
+    assert got_vjp.shape == (len(tp),)
+    assert rel_err(got_vjp, dy @ want) < 10 * tol
+    assert np.all(adj.vjp(sv, g_all, ol, tp, np.zeros(3)) == 0)
+    with pytest.raises(ValueError):
+        adj.vjp(sv, g_all, ol, tp, dy[:2])
+    with pytest.raises(ValueError):
+        adj.vjp(sv, g_all, ol, tp, dy * 1j)
 
 
 def test_config2_layer_properties_at_scale(ops):
