@@ -1,3 +1,9 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/r1_pytest_gpu_v21.log
-python -c "import __graft_entry__ as g; g.smoke()"
+run() { python bench.py --no-cpu-baseline --steps 4 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', round(d['ms_per_step'],2), d['config']['sweeps_per_step'], round(d['roofline']['frac'],3), d['clocks']['sm_mhz'], d['clocks']['power_w_max'], d['config']['checks'])"; }
+run low5
+B2SV_TILE_LOW=4 run low4
+B2SV_TILE_LOW=3 run low3
+B2SV_TILE_LOW=2 run low2
+B2SV_TILE_LOW=3 B2SV_MAX_HEAVY=10 run low3mh10
+run low5
+B2SV_TILE_LOW=3 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2

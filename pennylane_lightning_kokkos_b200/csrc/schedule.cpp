@@ -324,7 +324,7 @@ std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedC
     }
     std::vector<Pass> best;
     double best_cost = 0.0;
-    for (int mh : {8, 12, 16, 24}) {
+    for (int mh : {8, 10, 12, 16, 24}) {
         SchedConfig c = cfg;
         c.max_heavy = mh;
         std::vector<Pass> s = build_schedule_fixed(prims_in, c);

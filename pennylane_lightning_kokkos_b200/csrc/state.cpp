@@ -23,7 +23,7 @@ int tile_low_bits() {
     static int low = 0;
     if (!low) {
         const char *e = getenv("B2SV_TILE_LOW");
-        low = e ? std::max(4, std::min(6, atoi(e))) : 5;
+        low = e ? std::max(2, std::min(6, atoi(e))) : 5;
     }
     return low;
 }

@@ -4,17 +4,24 @@
 // (reference StateVectorKokkos.hpp:807-824 applyGateFunctor -> GateFunctors.hpp, one
 // Kokkos::parallel_for over 2^(n-k) per gate).
 //
-// Execution model (one persistent CTA per SM, two worker groups, three rotating tile buffers):
+// Execution model (one persistent CTA per SM: two worker groups + one load warpgroup, three rotating
+// tile buffers):
 //   * a tile = 2^B amplitudes (B = 12 for complex128 -> 64 KiB) whose indices differ in the pass's
 //     B tile bits; the CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+//   * the load warps stream tile k into the next free buffer (cp.async = LDGSTS with a
+//     per-amplitude XOR-swizzled destination, completion on an mbarrier) and publish the tile's
+//     facts (base index, conditional address toggles) next to it;
 //   * each worker group (GT threads) owns every second tile of the CTA: it waits for the tile to
-//     land in shared memory, runs all rounds of the pass on it in registers, streams it back to
-//     HBM in place, and then refills the buffer it just freed with the tile three steps ahead
-//     (cp.async = LDGSTS with a per-amplitude XOR-swizzled destination; completion is handed to the
-//     other group through an mbarrier). So while two tiles are being computed a third is always
-//     in flight, and the HBM stream and the FP64 pipe overlap inside every SM.
+//     land, runs all rounds of the pass on it in registers and writes the last round straight to
+//     HBM in place (or, when the address map does not allow coalesced stores, through a store phase
+//     from shared memory); the buffer goes back to the load warps right after the last gather.
+//     So while two tiles are being computed a third is always in flight;
 //   * a round: every thread gathers the 2^R amplitudes whose indices differ only in the round's R
-//     "register bits", applies all ops of the round in registers, scatters back in place.
+//     "register bits", applies all ops of the round in registers, scatters back in place. Rounds of
+//     uncontrolled 2x2s run as straight-line code, in factored form (dense_factored) when the
+//     scheduler could factor every gate; anything else goes through the per-op interpreter;
+//   * the kernel is compiled in four variants per dtype that differ in which round bodies exist,
+//     the launcher (launch_tile_pass_t) picks the leanest one that covers the pass.
 // HBM traffic is exactly one read + one write of the state per pass, whatever the number of gates.
 //
 // Shared-memory layout: amplitude i of the tile lives at slot phys(i) = i ^ fold(i) where fold XORs
@@ -446,8 +453,8 @@ __device__ __forceinline__ bool factored_round_fixed(int kind, amp_t (&a)[NS], c
 constexpr int kLoadThreads = 128;
 
 // Optional phase timers (B2SV_TILE_PROF=1): cycles summed over the lead thread of every worker group
-// / producer warpgroup of every CTA. [0] workers waiting for a tile, [1] workers busy on tiles,
-// [2] producers waiting for a free buffer, [3] producers issuing copies, [4] tiles, [5] CTA lifetime,
+// / load warpgroup of every CTA. [0] workers waiting for a tile, [1] workers busy on tiles,
+// [2] load warps waiting for a free buffer, [3] load warps issuing copies, [4] tiles, [5] CTA lifetime,
 // [6] workers in the last (fused-store) round of a tile, [7] workers in the other rounds,
 // [10] workers between tiles (prologue), [11] load warps issuing one tile.
 static __device__ unsigned long long g_tile_prof[16];
@@ -812,7 +819,7 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
 
 // ---- host side ----------------------------------------------------------------------------------
 namespace {
-constexpr int kMinLow = 4;
+constexpr int kMinLow = 2; // smallest B2SV_TILE_LOW the row-offset table is sized for
 template <typename real, int B, int NB> constexpr size_t tile_smem_bytes() {
     return NB * sizeof(typename AmpT<real>::type) * (size_t(1) << B) +
            sizeof(DevOp) * kMaxOpsPerPass + sizeof(uint64_t) * (size_t(1) << (B - kMinLow));
