@@ -8,9 +8,23 @@
 //     taken in one read pass over the two vectors -- no mu = lambda copy, no generator sweep
 //     (reference: copy 2S + generator 2S + inner product 2S, ADJ.hpp:454-470);
 //   * the U^dagger updates of lambda and H_lambda between two trainable ops go through the fusing
-//     tile executor as one batch.
+//     tile executor as one batch;
+//   * a RUN of consecutive single-qubit gates (any wires; e.g. the RX/RY/RZ block of one ansatz
+//     layer) is differentiated without undoing its gates one by one: with W_k the product of the
+//     run's gates after gate k,  <H_lambda_k| G_k |lambda_k> = <H_lambda_b| W_k G_k W_k^dagger |lambda_b>,
+//     and because gates on other wires cancel, W_k G_k W_k^dagger is again a 2x2 on gate k's wire
+//     (computed on the host). So the whole run needs, per wire, the four transition sums
+//     <H_lambda_b| |i><j|_t |lambda_b>  -- one read pass per six wires (kernels.cu k_transition_1q) --
+//     and its U^dagger updates reach the states as ONE fused batch together with whatever follows.
+//     Config 3 (24 qubits, 7 layers of 72 rotations): ~0.4 TB of traffic instead of ~3.3 TB.
 // All states of one call live on one stream, so nothing synchronises until the final read-back.
 #include "adjoint.hpp"
+
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <array>
+#include <cstdlib>
 
 namespace b2sv {
 
@@ -56,12 +70,169 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
         batch.clear();
     };
 
+    // ---- runs of single-qubit gates (see the header comment)
+    struct RunOp {
+        const GateOp *op;
+        int bit;          // index bit of the gate's wire
+        cplx u[4];        // the gate as applied in the circuit (row-major 2x2)
+        long slot;        // Jacobian column, -1 = not trainable
+        cplx g[4];        // generator (trainable ops)
+        double coeff;     // -2 * scale * sign
+    };
+    std::vector<RunOp> run; // in processing order = descending op index
+    std::vector<double> jac_host(n_obs * tp_size, 0.0);
+    // B2SV_ADJOINT_RUNS=0 turns the run path off (A/B measurements); sharded states use the per-op path
+    const char *runs_env = getenv("B2SV_ADJOINT_RUNS");
+    const bool runs_enabled = !sv.sharded() && (runs_env == nullptr || atoi(runs_env) != 0);
+    double *d_tr_scratch = nullptr, *d_tr_out = nullptr;
+    auto one_qubit_matrix = [&](const GateOp &op, int *bit, cplx u[4]) {
+        if (op.wires.size() != 1 || !op.matrix.empty())
+            return false;
+        std::vector<Prim> prims;
+        const std::vector<int> bits = wires_to_bits(op.wires, sv.num_qubits());
+        if (!lower_gate(op.name, bits, op.inverse, op.params, prims) || prims.size() != 1)
+            return false;
+        const Prim &p = prims[0];
+        if (p.cmask != 0)
+            return false;
+        if (p.type == Prim::C1Q) {
+            for (int i = 0; i < 4; i++)
+                u[i] = p.m[i];
+        } else if (p.type == Prim::DIAG && __builtin_popcountll(p.pmask) == 1) {
+            u[0] = p.m[0];
+            u[1] = u[2] = 0.0;
+            u[3] = p.m[1];
+        } else {
+            return false;
+        }
+        *bit = bits[0];
+        return true;
+    };
+    auto generator_2x2 = [](const std::string &name, cplx g[4], double *scale) {
+        const cplx I(0.0, 1.0);
+        if (name == "RX") {
+            g[0] = 0, g[1] = 1, g[2] = 1, g[3] = 0, *scale = -0.5;
+        } else if (name == "RY") {
+            g[0] = 0, g[1] = -I, g[2] = I, g[3] = 0, *scale = -0.5;
+        } else if (name == "RZ") {
+            g[0] = 1, g[1] = 0, g[2] = 0, g[3] = -1, *scale = -0.5;
+        } else if (name == "PhaseShift") { // SV.hpp:1275-1281: projector |1><1|, factor 1
+            g[0] = 0, g[1] = 0, g[2] = 0, g[3] = 1, *scale = 1.0;
+        } else {
+            return false;
+        }
+        return true;
+    };
+    auto mul2 = [](const cplx a[4], const cplx b[4], cplx c[4]) {
+        const cplx r0 = a[0] * b[0] + a[1] * b[2], r1 = a[0] * b[1] + a[1] * b[3];
+        const cplx r2 = a[2] * b[0] + a[3] * b[2], r3 = a[2] * b[1] + a[3] * b[3];
+        c[0] = r0, c[1] = r1, c[2] = r2, c[3] = r3;
+    };
+    auto finish_run = [&]() {
+        if (run.empty())
+            return;
+        bool any = false;
+        for (const RunOp &r : run)
+            any = any || r.slot >= 0;
+        if (any) {
+            flush(); // lambda, H_lambda = the states right after the last gate of the run
+            // W G W^dagger per trainable gate; W = product of the run's later gates on the same wire
+            std::vector<std::array<cplx, 4>> acc(sv.num_qubits(), {cplx(1), cplx(0), cplx(0), cplx(1)});
+            struct Need {
+                int bit;
+                cplx m[4];
+                double coeff;
+                long slot;
+            };
+            std::vector<Need> needs;
+            std::vector<int> wires_needed;
+            for (const RunOp &r : run) {
+                cplx *a = acc[r.bit].data();
+                if (r.slot >= 0) {
+                    Need nd;
+                    nd.bit = r.bit;
+                    nd.coeff = r.coeff;
+                    nd.slot = r.slot;
+                    cplx t[4];
+                    const cplx ad[4] = {std::conj(a[0]), std::conj(a[2]), std::conj(a[1]), std::conj(a[3])};
+                    mul2(a, r.g, t);
+                    mul2(t, ad, nd.m);
+                    needs.push_back(nd);
+                    if (std::find(wires_needed.begin(), wires_needed.end(), r.bit) == wires_needed.end())
+                        wires_needed.push_back(r.bit);
+                }
+                mul2(a, r.u, a);
+            }
+            if (!d_tr_scratch) {
+                CUDA_CHECK(cudaMalloc(&d_tr_scratch, sizeof(double) * kReduceBlocks * kTransitionVals));
+                CUDA_CHECK(cudaMalloc(&d_tr_out, sizeof(double) * kTransitionVals));
+            }
+            std::vector<double> vals(kTransitionVals);
+            for (size_t o = 0; o < n_obs; o++) {
+                for (size_t c0 = 0; c0 < wires_needed.size(); c0 += kTransitionBits) {
+                    const int nb = static_cast<int>(std::min<size_t>(kTransitionBits, wires_needed.size() - c0));
+                    lambda->transition_1q_to(*H[o], wires_needed.data() + c0, nb, d_tr_scratch, d_tr_out);
+                    CUDA_CHECK(cudaMemcpyAsync(vals.data(), d_tr_out, sizeof(double) * kTransitionVals,
+                                               cudaMemcpyDeviceToHost, st));
+                    CUDA_CHECK(cudaStreamSynchronize(st));
+                    const cplx D(vals[0], vals[1]);
+                    for (int t = 0; t < nb; t++) {
+                        const cplx Z(vals[2 + 6 * t], vals[3 + 6 * t]), X(vals[4 + 6 * t], vals[5 + 6 * t]),
+                            W(vals[6 + 6 * t], vals[7 + 6 * t]);
+                        // E_ij = <H_lambda| (|i><j|)_t |lambda>
+                        const cplx E00 = 0.5 * (D + Z), E11 = 0.5 * (D - Z), E01 = 0.5 * (X + W),
+                                   E10 = 0.5 * (X - W);
+                        for (const Need &nd : needs)
+                            if (nd.bit == wires_needed[c0 + t]) {
+                                const cplx v = nd.m[0] * E00 + nd.m[1] * E01 + nd.m[2] * E10 + nd.m[3] * E11;
+                                jac_host[o * tp_size + nd.slot] += nd.coeff * v.imag();
+                            }
+                    }
+                }
+            }
+        }
+        for (const RunOp &r : run) { // the run's U^dagger, in sweep order
+            GateOp adj = *r.op;
+            adj.inverse = !r.op->inverse;
+            batch.push_back(std::move(adj));
+        }
+        run.clear();
+    };
+
     for (long op_idx = static_cast<long>(ops.ops.size()) - 1; op_idx >= 0; op_idx--) {
         const GateOp &op = ops.ops[op_idx];
         if (op.name == "StatePrep" || op.name == "BasisState") // ADJ.hpp:447-450
             continue;
         if (tp_it == tp_rend) // ADJ.hpp:451-453
             break;
+        if (runs_enabled) {
+            RunOp r;
+            r.op = &op;
+            r.slot = -1;
+            r.coeff = 0.0;
+            if (one_qubit_matrix(op, &r.bit, r.u)) {
+                bool ok = true;
+                if (!op.params.empty()) {
+                    if (current_param_idx == static_cast<long>(*tp_it)) {
+                        double scale = 0.0;
+                        ok = generator_2x2(op.name, r.g, &scale);
+                        if (ok) {
+                            r.slot = trainable_number;
+                            r.coeff = -2.0 * scale * (op.inverse ? -1.0 : 1.0);
+                            trainable_number--;
+                            ++tp_it;
+                        }
+                    }
+                    if (ok)
+                        current_param_idx--;
+                }
+                if (ok) {
+                    run.push_back(r);
+                    continue;
+                }
+            }
+            finish_run();
+        }
         if (!op.params.empty()) {
             if (current_param_idx == static_cast<long>(*tp_it)) {
                 flush(); // lambda and H_lambda now hold the state right after this op
@@ -94,11 +265,18 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
         adj.inverse = !op.inverse;
         batch.push_back(std::move(adj));
     }
+    finish_run();
     // ops before the first trainable one never influence the Jacobian: the batch is dropped
     lambda->allreduce_device(d_jac, static_cast<int>(n_obs * tp_size));
     CUDA_CHECK(cudaMemcpyAsync(jac, d_jac, sizeof(double) * n_obs * tp_size, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n_obs * tp_size; i++)
+        jac[i] += jac_host[i];
     CUDA_CHECK(cudaFree(d_jac));
+    if (d_tr_scratch) {
+        CUDA_CHECK(cudaFree(d_tr_scratch));
+        CUDA_CHECK(cudaFree(d_tr_out));
+    }
 }
 
 } // namespace b2sv

@@ -295,6 +295,48 @@ __global__ void __launch_bounds__(kReduceThreads)
     }
     block_reduce_store<2>(acc, partials);
 }
+// Single-qubit transition sums between two vectors, for up to NB index bits in ONE read pass
+// (adjoint sweep: every trainable 1-qubit gate of a run needs <bra| M_t |ket> for some 2x2 M on
+// its wire t, and all of those follow from four sums per wire).  With c_i = conj(bra_i):
+//   D   = sum_i c_i ket_i                     Z_t = sum_i s_t(i) c_i ket_i      (s_t = +1 / -1 by bit t)
+//   X_t = sum_i c_i ket_{i ^ 2^t}             W_t = sum_i s_t(i) c_i ket_{i ^ 2^t}
+// partials per block: D (re, im), then per bit Z, X, W (re, im each) = 2 + 6 NB doubles.
+struct TransBits {
+    int nb;
+    int pos[8];
+};
+template <typename amp_t, int NB>
+__global__ void __launch_bounds__(kReduceThreads)
+    k_transition_1q(const amp_t *__restrict__ bra, const amp_t *__restrict__ ket, uint64_t len,
+                    TransBits tb, double *__restrict__ partials) {
+    double acc[2 + 6 * NB];
+#pragma unroll
+    for (int j = 0; j < 2 + 6 * NB; j++)
+        acc[j] = 0.0;
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const amp_t h = bra[i], l = ket[i];
+        const double cx = double(h.x), cy = -double(h.y); // conj(bra_i)
+        const double dx = cx * l.x - cy * l.y, dy = cx * l.y + cy * l.x;
+        acc[0] += dx;
+        acc[1] += dy;
+#pragma unroll
+        for (int t = 0; t < NB; t++) {
+            if (t < tb.nb) {
+                const double s = ((i >> tb.pos[t]) & 1ull) ? -1.0 : 1.0;
+                const amp_t p = ket[i ^ (uint64_t(1) << tb.pos[t])];
+                const double xx = cx * p.x - cy * p.y, xy = cx * p.y + cy * p.x;
+                acc[2 + 6 * t + 0] += s * dx;
+                acc[2 + 6 * t + 1] += s * dy;
+                acc[2 + 6 * t + 2] += xx;
+                acc[2 + 6 * t + 3] += xy;
+                acc[2 + 6 * t + 4] += s * xx;
+                acc[2 + 6 * t + 5] += s * xy;
+            }
+        }
+    }
+    block_reduce_store<2 + 6 * NB>(acc, partials);
+}
 __global__ void k_finalize_scaled(const double *__restrict__ partials, int nblocks, int nv, int which,
                                   double scale, double *__restrict__ dst) {
     __shared__ double red[kReduceThreads];
@@ -824,6 +866,17 @@ void launch_sample(int dtype, const void *state, uint64_t len, const double *d_c
                    (k_sample<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), len, d_chunk_cdf, nchunks, num_qubits, shots, seed, sh, d_out)));
 }
 
+void launch_transition_1q(int dtype, const void *bra, const void *ket, uint64_t len,
+                          const int *h_bits, int nb, double *d_partials, cudaStream_t st) {
+    B2_ASSERT(nb >= 1 && nb <= kTransitionBits);
+    TransBits tb{};
+    tb.nb = nb;
+    for (int j = 0; j < nb; j++)
+        tb.pos[j] = h_bits[j];
+    DISPATCH_DTYPE(dtype,
+                   (k_transition_1q<float2, kTransitionBits><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(bra), static_cast<const float2 *>(ket), len, tb, d_partials)),
+                   (k_transition_1q<double2, kTransitionBits><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(bra), static_cast<const double2 *>(ket), len, tb, d_partials)));
+}
 void launch_bits_to_f64(unsigned long long *d, size_t n, cudaStream_t st) {
     if (n)
         k_u64_to_f64<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d, n);

@@ -72,6 +72,15 @@ void launch_csr_spmv(int dtype, const void *x, void *y, const double2 *d_data,
                      const uint32_t *d_ind, const uint64_t *d_ptr, uint64_t nrows,
                      int lanes_per_row, cudaStream_t st);
 
+// Single-qubit transition sums <bra| . |ket> for nb <= kTransitionBits index bits in one read pass.
+// d_partials: kReduceBlocks x kTransitionVals doubles; finalize with launch_finalize(..., nv =
+// kTransitionVals). Layout of the result: D (re, im), then per bit Z_t, X_t, W_t (re, im each), see
+// kernels.cu k_transition_1q.
+constexpr int kTransitionBits = 6;
+constexpr int kTransitionVals = 2 + 6 * kTransitionBits;
+void launch_transition_1q(int dtype, const void *bra, const void *ket, uint64_t len,
+                          const int *h_bits, int nb, double *d_partials, cudaStream_t st);
+
 // ---- probabilities and sampling
 void launch_probs_full(int dtype, const void *state, uint64_t len, double *d_out, cudaStream_t st);
 // d_out must be zeroed; bitpos[j] = index bit of requested wire j (wire order = output bit order,

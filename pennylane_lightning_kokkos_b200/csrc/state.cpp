@@ -694,6 +694,18 @@ void State::pauli_dot_im_to(const State &bra, uint64_t x, uint64_t z, cplx ph, d
     order_after(bra.stream_, stream_);
     reduce_launches += 2;
 }
+void State::transition_1q_to(const State &bra, const int *bits, int nb, double *d_scratch,
+                             double *d_dst) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(bra.n_ != n_ || bra.dtype_ != dtype_ || bra.device_ != device_,
+                "state vectors are not compatible");
+    B2_ABORT_IF(world_ > 1, "internal: batched transition sums are not available on sharded states");
+    order_after(stream_, bra.stream_);
+    launch_transition_1q(dtype_, bra.d_state_, d_state_, local_length(), bits, nb, d_scratch, stream_);
+    launch_finalize(d_scratch, kReduceBlocks, kTransitionVals, d_dst, stream_);
+    order_after(bra.stream_, stream_);
+    reduce_launches += 2;
+}
 void State::dot_im_to(const State &bra, double factor, double *d_dst) const {
     CUDA_CHECK(cudaSetDevice(device_));
     B2_ABORT_IF(bra.n_ != n_ || bra.dtype_ != dtype_ || bra.device_ != device_,

@@ -106,6 +106,12 @@ class State {
     void pauli_dot_im_to(const State &bra, uint64_t x, uint64_t z, cplx ph, double factor,
                          double *d_dst) const;
     void dot_im_to(const State &bra, double factor, double *d_dst) const;
+    // Single-qubit transition sums <bra| . |this> for nb <= kTransitionBits index bits in one read
+    // pass (kernels.cu k_transition_1q); d_scratch: kReduceBlocks x kTransitionVals doubles, result
+    // (kTransitionVals doubles) lands in d_dst. Not for sharded states.
+    void transition_1q_to(const State &bra, const int *bits, int nb, double *d_scratch,
+                          double *d_dst) const;
+    bool sharded() const { return world_ > 1; }
     void allreduce_device(double *d_buf, int n) const;
     // clone that lives on this state's stream (so kernels touching both need no cross-stream events)
     std::unique_ptr<State> clone_on_stream() const;
