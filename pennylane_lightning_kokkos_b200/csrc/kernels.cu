@@ -337,6 +337,74 @@ __global__ void __launch_bounds__(kReduceThreads)
     }
     block_reduce_store<2 + 6 * NB>(acc, partials);
 }
+// The same sums, tiled: a tile = the 5 lowest index bits (512-byte rows) + up to 6 chosen bits, both
+// vectors' tiles staged in shared memory, so all wires of the launch (any <= kTransitionBits of the
+// tile's bits) are served from ONE read of the two vectors; the untiled kernel above re-reads the
+// partner amplitudes once per wire. Same partials layout as k_transition_1q.
+struct TransTile {
+    int n_tile;        // number of tile bits (5 low + chosen)
+    int tile_pos[12];  // ascending index bit positions of the tile
+    int nb;            // wires of this launch
+    int wire_tpos[8];  // position (0..n_tile-1) of each wire's bit inside the tile
+};
+template <typename amp_t>
+__global__ void __launch_bounds__(256, 2)
+    k_transition_tile(const amp_t *__restrict__ bra, const amp_t *__restrict__ ket, uint64_t n_tiles,
+                      TransTile tt, double *__restrict__ partials) {
+    extern __shared__ __align__(16) unsigned char tsm[];
+    const int tile = 1 << tt.n_tile;
+    amp_t *sk = reinterpret_cast<amp_t *>(tsm);
+    amp_t *sb = sk + tile;
+    __shared__ uint64_t rowoff[64];
+    const int n_rows = tile >> 5;
+    if (static_cast<int>(threadIdx.x) < n_rows) {
+        uint64_t off = 0;
+        for (int j = 5; j < tt.n_tile; j++)
+            if ((threadIdx.x >> (j - 5)) & 1)
+                off |= uint64_t(1) << tt.tile_pos[j];
+        rowoff[threadIdx.x] = off;
+    }
+    double acc[kTransitionVals];
+#pragma unroll
+    for (int j = 0; j < kTransitionVals; j++)
+        acc[j] = 0.0;
+    __syncthreads();
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint64_t base = t; // tile id -> index with zeros at the tile's bit positions
+        for (int j = 0; j < tt.n_tile; j++)
+            base = insert_zero(base, tt.tile_pos[j]);
+        for (int e = threadIdx.x; e < tile; e += blockDim.x) {
+            const uint64_t gi = base | rowoff[e >> 5] | uint64_t(e & 31);
+            sk[e] = ket[gi];
+            sb[e] = bra[gi];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < tile; e += blockDim.x) {
+            const amp_t h = sb[e], l = sk[e];
+            const double cx = double(h.x), cy = -double(h.y);
+            const double dx = cx * l.x - cy * l.y, dy = cx * l.y + cy * l.x;
+            acc[0] += dx;
+            acc[1] += dy;
+#pragma unroll
+            for (int w = 0; w < kTransitionBits; w++) {
+                if (w < tt.nb) {
+                    const int tp = tt.wire_tpos[w];
+                    const double sg = ((e >> tp) & 1) ? -1.0 : 1.0;
+                    const amp_t p = sk[e ^ (1 << tp)];
+                    const double xx = cx * p.x - cy * p.y, xy = cx * p.y + cy * p.x;
+                    acc[2 + 6 * w + 0] += sg * dx;
+                    acc[2 + 6 * w + 1] += sg * dy;
+                    acc[2 + 6 * w + 2] += xx;
+                    acc[2 + 6 * w + 3] += xy;
+                    acc[2 + 6 * w + 4] += sg * xx;
+                    acc[2 + 6 * w + 5] += sg * xy;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    block_reduce_store<kTransitionVals>(acc, partials);
+}
 __global__ void k_finalize_scaled(const double *__restrict__ partials, int nblocks, int nv, int which,
                                   double scale, double *__restrict__ dst) {
     __shared__ double red[kReduceThreads];
@@ -876,6 +944,41 @@ void launch_transition_1q(int dtype, const void *bra, const void *ket, uint64_t 
     DISPATCH_DTYPE(dtype,
                    (k_transition_1q<float2, kTransitionBits><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(bra), static_cast<const float2 *>(ket), len, tb, d_partials)),
                    (k_transition_1q<double2, kTransitionBits><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(bra), static_cast<const double2 *>(ket), len, tb, d_partials)));
+}
+void launch_transition_tile(int dtype, const void *bra, const void *ket, int n_bits,
+                            const int *h_bits, int nb, double *d_partials, cudaStream_t st) {
+    B2_ASSERT(nb >= 1 && nb <= kTransitionBits && n_bits >= 11);
+    // tile bits: 0..4 plus the requested bits >= 5, padded with the lowest unused bits up to 11
+    uint64_t mask = 0x1f;
+    for (int j = 0; j < nb; j++)
+        mask |= uint64_t(1) << h_bits[j];
+    for (int b = 5; __builtin_popcountll(mask) < 11; b++)
+        mask |= uint64_t(1) << b;
+    TransTile tt{};
+    tt.nb = nb;
+    for (int b = 0; b < 64; b++)
+        if ((mask >> b) & 1)
+            tt.tile_pos[tt.n_tile++] = b;
+    B2_ASSERT(tt.n_tile == 11 && tt.tile_pos[10] < n_bits);
+    for (int j = 0; j < nb; j++)
+        for (int k = 0; k < tt.n_tile; k++)
+            if (tt.tile_pos[k] == h_bits[j])
+                tt.wire_tpos[j] = k;
+    const uint64_t n_tiles = uint64_t(1) << (n_bits - tt.n_tile);
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_tiles, kReduceBlocks));
+    const bool f32 = dtype != 1;
+    const size_t smem = (f32 ? sizeof(float2) : sizeof(double2)) * 2 * (size_t(1) << tt.n_tile);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_transition_tile<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        CUDA_CHECK(cudaFuncSetAttribute(k_transition_tile<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        configured = true;
+    }
+    if (grid < static_cast<unsigned>(kReduceBlocks)) // finalize sums kReduceBlocks rows
+        CUDA_CHECK(cudaMemsetAsync(d_partials, 0, sizeof(double) * kReduceBlocks * kTransitionVals, st));
+    DISPATCH_DTYPE(dtype,
+                   (k_transition_tile<float2><<<grid, 256, smem, st>>>(static_cast<const float2 *>(bra), static_cast<const float2 *>(ket), n_tiles, tt, d_partials)),
+                   (k_transition_tile<double2><<<grid, 256, smem, st>>>(static_cast<const double2 *>(bra), static_cast<const double2 *>(ket), n_tiles, tt, d_partials)));
 }
 void launch_bits_to_f64(unsigned long long *d, size_t n, cudaStream_t st) {
     if (n)

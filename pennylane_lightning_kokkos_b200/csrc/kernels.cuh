@@ -81,6 +81,10 @@ constexpr int kTransitionVals = 2 + 6 * kTransitionBits;
 void launch_transition_1q(int dtype, const void *bra, const void *ket, uint64_t len,
                           const int *h_bits, int nb, double *d_partials, cudaStream_t st);
 
+// Tiled form (needs n_bits >= 11): every requested bit is served from one read of the two vectors.
+void launch_transition_tile(int dtype, const void *bra, const void *ket, int n_bits,
+                            const int *h_bits, int nb, double *d_partials, cudaStream_t st);
+
 // ---- probabilities and sampling
 void launch_probs_full(int dtype, const void *state, uint64_t len, double *d_out, cudaStream_t st);
 // d_out must be zeroed; bitpos[j] = index bit of requested wire j (wire order = output bit order,

@@ -701,7 +701,10 @@ void State::transition_1q_to(const State &bra, const int *bits, int nb, double *
                 "state vectors are not compatible");
     B2_ABORT_IF(world_ > 1, "internal: batched transition sums are not available on sharded states");
     order_after(stream_, bra.stream_);
-    launch_transition_1q(dtype_, bra.d_state_, d_state_, local_length(), bits, nb, d_scratch, stream_);
+    if (n_eff_ >= 11 && n_eff_ == n_local_)
+        launch_transition_tile(dtype_, bra.d_state_, d_state_, n_local_, bits, nb, d_scratch, stream_);
+    else
+        launch_transition_1q(dtype_, bra.d_state_, d_state_, local_length(), bits, nb, d_scratch, stream_);
     launch_finalize(d_scratch, kReduceBlocks, kTransitionVals, d_dst, stream_);
     order_after(bra.stream_, stream_);
     reduce_launches += 2;
