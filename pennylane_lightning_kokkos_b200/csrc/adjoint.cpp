@@ -51,7 +51,7 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
     std::unique_ptr<State> mu; // only for generators that are not Pauli words
     cudaStream_t st = lambda->stream();
     double *d_jac = nullptr;
-    CUDA_CHECK(cudaMalloc(&d_jac, sizeof(double) * n_obs * tp_size));
+    CUDA_CHECK(cudaMallocAsync(&d_jac, sizeof(double) * n_obs * tp_size, st));
     CUDA_CHECK(cudaMemsetAsync(d_jac, 0, sizeof(double) * n_obs * tp_size, st));
 
     long trainable_number = static_cast<long>(tp_size) - 1;
@@ -64,9 +64,10 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
     auto flush = [&]() {
         if (batch.empty())
             return;
-        lambda->apply_ops(batch, false);
+        std::vector<State *> all = {lambda.get()};
         for (auto &h : H)
-            h->apply_ops(batch, false);
+            all.push_back(h.get());
+        State::apply_ops_to_all(all, batch); // lowered and scheduled once
         batch.clear();
     };
 
@@ -164,8 +165,8 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
                 mul2(a, r.u, a);
             }
             if (!d_tr_scratch) {
-                CUDA_CHECK(cudaMalloc(&d_tr_scratch, sizeof(double) * kReduceBlocks * kTransitionVals));
-                CUDA_CHECK(cudaMalloc(&d_tr_out, sizeof(double) * kTransitionVals));
+                CUDA_CHECK(cudaMallocAsync(&d_tr_scratch, sizeof(double) * kReduceBlocks * kTransitionVals, st));
+                CUDA_CHECK(cudaMallocAsync(&d_tr_out, sizeof(double) * kTransitionVals, st));
             }
             std::vector<double> vals(kTransitionVals);
             for (size_t o = 0; o < n_obs; o++) {
@@ -272,10 +273,10 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
     CUDA_CHECK(cudaStreamSynchronize(st));
     for (size_t i = 0; i < n_obs * tp_size; i++)
         jac[i] += jac_host[i];
-    CUDA_CHECK(cudaFree(d_jac));
+    CUDA_CHECK(cudaFreeAsync(d_jac, st));
     if (d_tr_scratch) {
-        CUDA_CHECK(cudaFree(d_tr_scratch));
-        CUDA_CHECK(cudaFree(d_tr_out));
+        CUDA_CHECK(cudaFreeAsync(d_tr_scratch, st));
+        CUDA_CHECK(cudaFreeAsync(d_tr_out, st));
     }
 }
 

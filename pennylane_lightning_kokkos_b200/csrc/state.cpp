@@ -1,5 +1,7 @@
 // b2sv: State implementation (see state.hpp).
 #include "state.hpp"
+
+#include <mutex>
 #include "comm.hpp"
 
 #include <algorithm>
@@ -33,6 +35,60 @@ int log2_exact(int x) {
         g++;
     B2_ABORT_IF((1 << g) != x, "world size must be a power of two");
     return g;
+}
+// ---- recycling of device buffers of short-lived states -----------------------------------------------
+// An adjoint Jacobian clones the state two or more times per call; cudaMalloc / cudaFree / cudaMallocHost
+// of those clones cost milliseconds, comparable with the whole sweep on 20-26 qubit states. Freed state
+// buffers of up to 2 GiB (and the small reduction buffers that go with every state) are therefore kept
+// in a small per-process pool and handed to the next state of the same size on the same device.
+struct SpareState {
+    int device;
+    size_t bytes;
+    void *p;
+};
+struct SpareAux {
+    int device;
+    double *d_partials, *d_out, *h_out;
+};
+std::mutex g_pool_mu;
+std::vector<SpareState> g_spare_states;
+std::vector<SpareAux> g_spare_aux;
+constexpr size_t kPoolMaxBytes = size_t(2) << 30;
+constexpr size_t kPoolMaxStates = 6, kPoolMaxAux = 8;
+
+void *pool_take_state(int device, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_spare_states.size(); i++)
+        if (g_spare_states[i].device == device && g_spare_states[i].bytes == bytes) {
+            void *p = g_spare_states[i].p;
+            g_spare_states.erase(g_spare_states.begin() + i);
+            return p;
+        }
+    return nullptr;
+}
+bool pool_give_state(int device, size_t bytes, void *p) { // caller: the buffer is idle
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (bytes > kPoolMaxBytes || g_spare_states.size() >= kPoolMaxStates)
+        return false;
+    g_spare_states.push_back({device, bytes, p});
+    return true;
+}
+bool pool_take_aux(int device, SpareAux *out) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_spare_aux.size(); i++)
+        if (g_spare_aux[i].device == device) {
+            *out = g_spare_aux[i];
+            g_spare_aux.erase(g_spare_aux.begin() + i);
+            return true;
+        }
+    return false;
+}
+bool pool_give_aux(const SpareAux &a) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_spare_aux.size() >= kPoolMaxAux)
+        return false;
+    g_spare_aux.push_back(a);
+    return true;
 }
 } // namespace
 
@@ -108,12 +164,37 @@ void State::init_common(const void *nccl_id) {
                 "sharded states need at least tile_bits + log2(world) local qubits");
     if (!stream_)
         CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    e = cudaMalloc(&d_state_, alloc_length() * amp_bytes());
-    B2_ABORT_IF(e != cudaSuccess, std::string("cannot allocate the state vector: ") +
-                                      cudaGetErrorString(e));
-    CUDA_CHECK(cudaMalloc(&d_partials_, sizeof(double) * kReduceBlocks * kMaxReduceVals));
-    CUDA_CHECK(cudaMalloc(&d_out_, sizeof(double) * 64));
-    CUDA_CHECK(cudaMallocHost(&h_out_, sizeof(double) * 64));
+    { // stream-ordered temporaries (cudaMallocAsync): keep up to 1 GiB cached instead of returning
+      // everything to the driver at every synchronisation
+        static std::mutex mu;
+        static uint64_t configured_devices = 0;
+        std::lock_guard<std::mutex> lk(mu);
+        if (device_ < 64 && !((configured_devices >> device_) & 1)) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device_) == cudaSuccess) {
+                uint64_t thr = uint64_t(1) << 30;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            configured_devices |= uint64_t(1) << device_;
+        }
+    }
+    // sharded states are IPC-mapped by their peers: always a fresh cudaMalloc for those
+    d_state_ = world_ > 1 ? nullptr : pool_take_state(device_, alloc_length() * amp_bytes());
+    if (!d_state_) {
+        e = cudaMalloc(&d_state_, alloc_length() * amp_bytes());
+        B2_ABORT_IF(e != cudaSuccess, std::string("cannot allocate the state vector: ") +
+                                          cudaGetErrorString(e));
+    }
+    SpareAux aux;
+    if (pool_take_aux(device_, &aux)) {
+        d_partials_ = aux.d_partials;
+        d_out_ = aux.d_out;
+        h_out_ = aux.h_out;
+    } else {
+        CUDA_CHECK(cudaMalloc(&d_partials_, sizeof(double) * kReduceBlocks * kMaxReduceVals));
+        CUDA_CHECK(cudaMalloc(&d_out_, sizeof(double) * 64));
+        CUDA_CHECK(cudaMallocHost(&h_out_, sizeof(double) * 64));
+    }
     if (world_ > 1) {
         if (!comm_)
             comm_ = std::shared_ptr<Comm>(comm_create(rank_, world_, nccl_id, device_), comm_destroy);
@@ -134,12 +215,17 @@ State::~State() {
     }
     comm_.reset();
     for (void *p : scratch_)
-        cudaFree(p);
-    cudaFree(d_state_);
-    cudaFree(d_partials_);
-    cudaFree(d_out_);
-    if (h_out_)
-        cudaFreeHost(h_out_);
+        if (!pool_give_state(device_, alloc_length() * amp_bytes(), p))
+            cudaFree(p);
+    // the stream was synchronised above: the buffers are idle and may serve the next state
+    if (world_ > 1 || !d_state_ || !pool_give_state(device_, alloc_length() * amp_bytes(), d_state_))
+        cudaFree(d_state_);
+    if (!d_partials_ || !d_out_ || !h_out_ || !pool_give_aux({device_, d_partials_, d_out_, h_out_})) {
+        cudaFree(d_partials_);
+        cudaFree(d_out_);
+        if (h_out_)
+            cudaFreeHost(h_out_);
+    }
     if (stream_ && owns_stream_)
         cudaStreamDestroy(stream_);
 }
@@ -237,7 +323,9 @@ void *State::acquire_scratch() const {
         scratch_.pop_back();
         return p;
     }
-    void *p = nullptr;
+    void *p = pool_take_state(device_, alloc_length() * amp_bytes());
+    if (p)
+        return p;
     cudaError_t e = cudaMalloc(&p, alloc_length() * amp_bytes());
     B2_ABORT_IF(e != cudaSuccess, std::string("cannot allocate a scratch state vector: ") +
                                       cudaGetErrorString(e));
@@ -248,7 +336,8 @@ void State::release_scratch(void *p) const {
         scratch_.push_back(p);
     } else {
         cudaStreamSynchronize(stream_);
-        cudaFree(p);
+        if (!pool_give_state(device_, alloc_length() * amp_bytes(), p))
+            cudaFree(p);
     }
 }
 
@@ -462,6 +551,30 @@ void State::apply_ops(const std::vector<GateOp> &ops, bool adjoint) {
     flush();
 }
 
+void State::apply_ops_to_all(const std::vector<State *> &states, const std::vector<GateOp> &ops) {
+    if (states.empty() || ops.empty())
+        return;
+    State &first = *states[0];
+    bool same = first.fuse_ && !first.comm_;
+    for (State *s : states)
+        same = same && !s->comm_ && s->n_ == first.n_ && s->dtype_ == first.dtype_ &&
+               s->device_ == first.device_ && s->fuse_;
+    if (!same) {
+        for (State *s : states)
+            s->apply_ops(ops, false);
+        return;
+    }
+    CUDA_CHECK(cudaSetDevice(first.device_));
+    std::vector<Prim> prims;
+    for (const auto &op : ops)
+        first.lower(op, false, prims);
+    if (prims.empty())
+        return;
+    const std::vector<Pass> passes = build_schedule(prims, first.sched_config());
+    for (State *s : states)
+        s->upload_and_run(passes);
+}
+
 double State::apply_generator(const std::string &name, const std::vector<int64_t> &wires) {
     std::vector<Prim> prims;
     double scale = 0.0;
@@ -481,7 +594,7 @@ void State::apply_prims(std::vector<Prim> prims) {
         run_local(prims);
 }
 
-void State::run_local(const std::vector<Prim> &prims) {
+SchedConfig State::sched_config() const {
     SchedConfig cfg;
     cfg.B = B_;
     cfg.R = R_;
@@ -497,7 +610,11 @@ void State::run_local(const std::vector<Prim> &prims) {
     cfg.n_local = n_local_;
     cfg.n_alloc = n_eff_;
     cfg.fuse = fuse_;
-    upload_and_run(build_schedule(prims, cfg));
+    return cfg;
+}
+
+void State::run_local(const std::vector<Prim> &prims) {
+    upload_and_run(build_schedule(prims, sched_config()));
 }
 
 void State::upload_and_run(const std::vector<Pass> &passes) {

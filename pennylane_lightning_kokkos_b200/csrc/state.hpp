@@ -75,6 +75,9 @@ class State {
     // ---- gates
     void apply_gate(const GateOp &op);
     void apply_ops(const std::vector<GateOp> &ops, bool adjoint);
+    // the same op list applied to several states of identical shape (adjoint sweep: lambda and every
+    // H_lambda): lowered and scheduled once, the passes launched on each state
+    static void apply_ops_to_all(const std::vector<State *> &states, const std::vector<GateOp> &ops);
     double apply_generator(const std::string &name, const std::vector<int64_t> &wires);
     void apply_prims(std::vector<Prim> prims);
     void lower(const GateOp &op, bool flip_inverse, std::vector<Prim> &out) const;
@@ -130,6 +133,7 @@ class State {
   private:
     void finish_reduce(int nv, double *out) const;
     void upload_and_run(const std::vector<Pass> &passes);
+    SchedConfig sched_config() const;
     void run_local(const std::vector<Prim> &prims);       // prims in PHYSICAL bits, all targets local
     void apply_prims_sharded(std::vector<Prim> prims);    // prims in logical bits
     Prim to_physical(const Prim &p) const;
