@@ -77,6 +77,25 @@ __global__ void k_finalize(const double *__restrict__ partials, int nblocks, int
     }
 }
 
+// one block per value (for reductions with many values): block j sums column j in a fixed order
+__global__ void k_finalize_wide(const double *__restrict__ partials, int nblocks, int nv,
+                                double *__restrict__ out) {
+    __shared__ double red[kReduceThreads];
+    const int j = blockIdx.x;
+    double x = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+        x += partials[b * nv + j];
+    red[threadIdx.x] = x;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        out[j] = red[0];
+}
+
 // ---- state management ---------------------------------------------------------------------------
 template <typename amp_t>
 __global__ void k_set_basis(amp_t *__restrict__ state, uint64_t len, uint64_t index) {
@@ -341,8 +360,9 @@ __global__ void __launch_bounds__(kReduceThreads)
 // vectors' tiles staged in shared memory, so all wires of the launch (any <= kTransitionBits of the
 // tile's bits) are served from ONE read of the two vectors; the untiled kernel above re-reads the
 // partner amplitudes once per wire. Same partials layout as k_transition_1q.
+constexpr int kTransTileBits = 11;
 struct TransTile {
-    int n_tile;        // number of tile bits (5 low + chosen)
+    int n_tile;        // number of tile bits (5 low + chosen) = kTransTileBits
     int tile_pos[12];  // ascending index bit positions of the tile
     int nb;            // wires of this launch
     int wire_tpos[8];  // position (0..n_tile-1) of each wire's bit inside the tile
@@ -352,11 +372,12 @@ __global__ void __launch_bounds__(256, 2)
     k_transition_tile(const amp_t *__restrict__ bra, const amp_t *__restrict__ ket, uint64_t n_tiles,
                       TransTile tt, double *__restrict__ partials) {
     extern __shared__ __align__(16) unsigned char tsm[];
-    const int tile = 1 << tt.n_tile;
+    constexpr int tile = 1 << kTransTileBits;
+    constexpr int per_thread = tile / 256;
     amp_t *sk = reinterpret_cast<amp_t *>(tsm);
     amp_t *sb = sk + tile;
     __shared__ uint64_t rowoff[64];
-    const int n_rows = tile >> 5;
+    constexpr int n_rows = tile >> 5;
     if (static_cast<int>(threadIdx.x) < n_rows) {
         uint64_t off = 0;
         for (int j = 5; j < tt.n_tile; j++)
@@ -373,13 +394,28 @@ __global__ void __launch_bounds__(256, 2)
         uint64_t base = t; // tile id -> index with zeros at the tile's bit positions
         for (int j = 0; j < tt.n_tile; j++)
             base = insert_zero(base, tt.tile_pos[j]);
-        for (int e = threadIdx.x; e < tile; e += blockDim.x) {
-            const uint64_t gi = base | rowoff[e >> 5] | uint64_t(e & 31);
-            sk[e] = ket[gi];
-            sb[e] = bra[gi];
+        // 8 loads of a thread (4 amplitudes of each vector) are in flight before the first store
+#pragma unroll
+        for (int u0 = 0; u0 < per_thread; u0 += 4) {
+            amp_t rk[4], rb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = (u0 + u) * 256 + threadIdx.x;
+                const uint64_t gi = base | rowoff[e >> 5] | uint64_t(e & 31);
+                rk[u] = ket[gi];
+                rb[u] = bra[gi];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = (u0 + u) * 256 + threadIdx.x;
+                sk[e] = rk[u];
+                sb[e] = rb[u];
+            }
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < tile; e += blockDim.x) {
+#pragma unroll 2
+        for (int u = 0; u < per_thread; u++) {
+            const int e = u * 256 + threadIdx.x;
             const amp_t h = sb[e], l = sk[e];
             const double cx = double(h.x), cy = -double(h.y);
             const double dx = cx * l.x - cy * l.y, dy = cx * l.y + cy * l.x;
@@ -863,7 +899,10 @@ void launch_finalize_scaled(const double *d_partials, int nblocks, int nv, int w
 }
 void launch_finalize(const double *d_partials, int nblocks, int nv, double *d_out,
                      cudaStream_t st) {
-    k_finalize<<<1, kReduceThreads, 0, st>>>(d_partials, nblocks, nv, d_out);
+    if (nv > 4)
+        k_finalize_wide<<<nv, kReduceThreads, 0, st>>>(d_partials, nblocks, nv, d_out);
+    else
+        k_finalize<<<1, kReduceThreads, 0, st>>>(d_partials, nblocks, nv, d_out);
     CUDA_CHECK(cudaGetLastError());
 }
 void launch_pauli_sum_apply(int dtype, const void *in, void *out, uint64_t len,
