@@ -495,6 +495,48 @@ def test_adjoint_vs_reference(ops, ref, dtype, n, layers):
         adj.vjp(sv, g_all, ol, tp, dy * 1j)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_adjoint_runs_equal_per_gate_path(ops, dtype, monkeypatch):
+    """Runs of single-qubit gates are differentiated from batched transition sums (adjoint.cpp); the
+    result must equal the per-gate sweep (B2SV_ADJOINT_RUNS=0) on a 20-qubit ansatz with inverse
+    gates, PhaseShift, fixed single-qubit gates inside the runs and a trainable subset."""
+    S = suffix(dtype)
+    n = 20
+    rng = np.random.default_rng(5)
+    circ = []
+    for layer in range(3):
+        for w in range(n):
+            for g in ("RX", "RY", "RZ", "PhaseShift"):
+                if rng.integers(4):
+                    circ.append((g, [w], bool(rng.integers(2)), [float(rng.uniform(-2, 2))]))
+            if rng.integers(3) == 0:
+                circ.append((("Hadamard", "S", "PauliY", "T")[int(rng.integers(4))], [w], bool(rng.integers(2)), []))
+        for w in range(n):
+            circ.append(("CNOT", [w, (w + 1 + layer) % n], False, []))
+        circ.append(("CRY", [1, 7], False, [0.3]))
+        circ.append(("IsingXX", [3, 12], False, [-0.4]))
+    names, wires = [c[0] for c in circ], [c[1] for c in circ]
+    invs, params = [c[2] for c in circ], [c[3] for c in circ]
+    n_par = sum(1 for c in circ if c[3])
+    tp = sorted(int(x) for x in rng.choice(n_par, size=(3 * n_par) // 4, replace=False))
+    N, T = getattr(ops, f"NamedObsKokkos_{S}"), getattr(ops, f"TensorProdObsKokkos_{S}")
+    H = getattr(ops, f"HamiltonianKokkos_{S}")
+    terms = random_pauli_hamiltonian(n, 12, seed=3)
+    words = [(lambda f: f[0] if len(f) == 1 else T(f))([N(nm, [w]) for nm, w in word]) for _, word in terms]
+    obs = [H([c for c, _ in terms], words), N("PauliZ", [0]), N("PauliX", [n - 1])]
+    sv = sv_class(ops, dtype)(n)
+    sv.apply(names, wires, invs, params)
+    adj = getattr(ops, f"AdjointJacobianKokkos_{S}")()
+    ol = adj.create_ops_list(names, [np.array(x) for x in params], wires, invs, [np.zeros(0)] * len(names))
+    monkeypatch.setenv("B2SV_ADJOINT_RUNS", "1")
+    jac_runs = adj.adjoint_jacobian(sv, obs, ol, tp)
+    monkeypatch.setenv("B2SV_ADJOINT_RUNS", "0")
+    jac_gate = adj.adjoint_jacobian(sv, obs, ol, tp)
+    assert jac_runs.shape == (3, len(tp))
+    assert np.max(np.abs(jac_gate)) > 1e-3
+    assert rel_err(jac_runs, jac_gate) < (1e-12 if dtype == np.complex128 else 5e-5)
+
+
 def test_config2_layer_properties_at_scale(ops):
     """BASELINE config 2 shape at 26 qubits (1 GiB state): norm preserved, U^dagger U = identity,
     sampled amplitudes equal the per-gate (unfused) path."""
