@@ -367,15 +367,31 @@ struct TransTile {
     int nb;            // wires of this launch
     int wire_tpos[8];  // position (0..n_tile-1) of each wire's bit inside the tile
 };
+__device__ __forceinline__ void cp_async_16(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                     static_cast<uint32_t>(__cvta_generic_to_shared(sdst))),
+                 "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(
+                     static_cast<uint32_t>(__cvta_generic_to_shared(sdst))),
+                 "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_amp(double2 *d, const double2 *s) { cp_async_16(d, s); }
+__device__ __forceinline__ void cp_async_amp(float2 *d, const float2 *s) { cp_async_8(d, s); }
+constexpr int kTransThreads = 512;
+// One persistent CTA per SM, two shared-memory stages: the copies of tile k+1 (cp.async) are in flight
+// while tile k is reduced.
 template <typename amp_t>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kTransThreads, 1)
     k_transition_tile(const amp_t *__restrict__ bra, const amp_t *__restrict__ ket, uint64_t n_tiles,
                       TransTile tt, double *__restrict__ partials) {
     extern __shared__ __align__(16) unsigned char tsm[];
     constexpr int tile = 1 << kTransTileBits;
-    constexpr int per_thread = tile / 256;
-    amp_t *sk = reinterpret_cast<amp_t *>(tsm);
-    amp_t *sb = sk + tile;
+    constexpr int per_thread = tile / kTransThreads;
+    amp_t *stage = reinterpret_cast<amp_t *>(tsm); // [2 stages][ket tile, bra tile]
     __shared__ uint64_t rowoff[64];
     constexpr int n_rows = tile >> 5;
     if (static_cast<int>(threadIdx.x) < n_rows) {
@@ -390,32 +406,36 @@ __global__ void __launch_bounds__(256, 2)
     for (int j = 0; j < kTransitionVals; j++)
         acc[j] = 0.0;
     __syncthreads();
-    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    auto issue = [&](uint64_t t, int st) {
         uint64_t base = t; // tile id -> index with zeros at the tile's bit positions
         for (int j = 0; j < tt.n_tile; j++)
             base = insert_zero(base, tt.tile_pos[j]);
-        // 8 loads of a thread (4 amplitudes of each vector) are in flight before the first store
+        amp_t *sk = stage + size_t(st) * 2 * tile, *sb = sk + tile;
 #pragma unroll
-        for (int u0 = 0; u0 < per_thread; u0 += 4) {
-            amp_t rk[4], rb[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int e = (u0 + u) * 256 + threadIdx.x;
-                const uint64_t gi = base | rowoff[e >> 5] | uint64_t(e & 31);
-                rk[u] = ket[gi];
-                rb[u] = bra[gi];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int e = (u0 + u) * 256 + threadIdx.x;
-                sk[e] = rk[u];
-                sb[e] = rb[u];
-            }
+        for (int u = 0; u < per_thread; u++) {
+            const int e = u * kTransThreads + threadIdx.x;
+            const uint64_t gi = base | rowoff[e >> 5] | uint64_t(e & 31);
+            cp_async_amp(&sk[e], &ket[gi]);
+            cp_async_amp(&sb[e], &bra[gi]);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    int st = 0;
+    if (blockIdx.x < n_tiles)
+        issue(blockIdx.x, 0);
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, st ^= 1) {
+        const uint64_t tn = t + gridDim.x;
+        if (tn < n_tiles) {
+            issue(tn, st ^ 1);
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         }
         __syncthreads();
+        const amp_t *sk = stage + size_t(st) * 2 * tile, *sb = sk + tile;
 #pragma unroll 2
         for (int u = 0; u < per_thread; u++) {
-            const int e = u * 256 + threadIdx.x;
+            const int e = u * kTransThreads + threadIdx.x;
             const amp_t h = sb[e], l = sk[e];
             const double cx = double(h.x), cy = -double(h.y);
             const double dx = cx * l.x - cy * l.y, dy = cx * l.y + cy * l.x;
@@ -437,7 +457,7 @@ __global__ void __launch_bounds__(256, 2)
                 }
             }
         }
-        __syncthreads();
+        __syncthreads(); // the stage is free for the copies issued in the next iteration
     }
     block_reduce_store<kTransitionVals>(acc, partials);
 }
@@ -1004,20 +1024,23 @@ void launch_transition_tile(int dtype, const void *bra, const void *ket, int n_b
             if (tt.tile_pos[k] == h_bits[j])
                 tt.wire_tpos[j] = k;
     const uint64_t n_tiles = uint64_t(1) << (n_bits - tt.n_tile);
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_tiles, kReduceBlocks));
+    int dev = 0, sms = 148;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(sms)));
     const bool f32 = dtype != 1;
-    const size_t smem = (f32 ? sizeof(float2) : sizeof(double2)) * 2 * (size_t(1) << tt.n_tile);
+    const size_t smem = (f32 ? sizeof(float2) : sizeof(double2)) * 4 * (size_t(1) << tt.n_tile); // 2 stages x 2 vectors
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_transition_tile<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        CUDA_CHECK(cudaFuncSetAttribute(k_transition_tile<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        CUDA_CHECK(cudaFuncSetAttribute(k_transition_tile<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+        CUDA_CHECK(cudaFuncSetAttribute(k_transition_tile<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
         configured = true;
     }
     if (grid < static_cast<unsigned>(kReduceBlocks)) // finalize sums kReduceBlocks rows
         CUDA_CHECK(cudaMemsetAsync(d_partials, 0, sizeof(double) * kReduceBlocks * kTransitionVals, st));
     DISPATCH_DTYPE(dtype,
-                   (k_transition_tile<float2><<<grid, 256, smem, st>>>(static_cast<const float2 *>(bra), static_cast<const float2 *>(ket), n_tiles, tt, d_partials)),
-                   (k_transition_tile<double2><<<grid, 256, smem, st>>>(static_cast<const double2 *>(bra), static_cast<const double2 *>(ket), n_tiles, tt, d_partials)));
+                   (k_transition_tile<float2><<<grid, kTransThreads, smem, st>>>(static_cast<const float2 *>(bra), static_cast<const float2 *>(ket), n_tiles, tt, d_partials)),
+                   (k_transition_tile<double2><<<grid, kTransThreads, smem, st>>>(static_cast<const double2 *>(bra), static_cast<const double2 *>(ket), n_tiles, tt, d_partials)));
 }
 void launch_bits_to_f64(unsigned long long *d, size_t n, cudaStream_t st) {
     if (n)
