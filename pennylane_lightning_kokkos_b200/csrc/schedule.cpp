@@ -373,8 +373,10 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
         auto select = [&](uint64_t tmask, int grow, int window, std::vector<int> *out,
                           uint64_t *tmask_out) {
             Blocker blk;
-            int heavy = 0, n_light = 0, n_ops = 0, seen = 0;
-            for (int i = first; i < N && n_ops < kMaxOpsPerPass && seen < window; i++) {
+            int heavy = 0, n_light = 0, n_ops = 0, seen = 0, misses = 0;
+            // after kMaxMisses pending ops in a row that could not join, the pass is taken as full
+            constexpr int kMaxMisses = 512;
+            for (int i = first; i < N && n_ops < kMaxOpsPerPass && seen < window && misses < kMaxMisses; i++) {
                 if (done[i])
                     continue;
                 seen++;
@@ -404,8 +406,10 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                     heavy += light ? 0 : 1;
                     n_light += light ? 1 : 0;
                     n_ops++;
+                    misses = 0;
                 } else {
                     blk.skip(p);
+                    misses++;
                 }
             }
             if (tmask_out)
@@ -456,7 +460,10 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
             free_bits--;
         }
         std::vector<int> chosen;
-        select(tile_mask, free_bits, N, &chosen, &tile_mask);
+        // bounded look-ahead: ops further than kScanWindow pending ops away wait for a later pass
+        // (skipping is always legal), which keeps scheduling linear in the circuit length
+        constexpr int kScanWindow = 8192;
+        select(tile_mask, free_bits, kScanWindow, &chosen, &tile_mask);
         free_bits = B - __builtin_popcountll(tile_mask);
         for (int i : chosen)
             done[i] = 1;
