@@ -13,6 +13,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+from itertools import chain as _itertools_chain
+
 import numpy as np
 
 from . import _lib
@@ -23,6 +25,10 @@ _GATES_1 = ["Identity", "PauliX", "PauliY", "PauliZ", "Hadamard", "S", "T", "CNO
             "CRX", "CRY", "CRZ", "CRot", "IsingXX", "IsingXY", "IsingYY", "IsingZZ", "MultiRZ",
             "SingleExcitation", "SingleExcitationMinus", "SingleExcitationPlus", "DoubleExcitation",
             "DoubleExcitationMinus", "DoubleExcitationPlus"]
+
+
+def _chain(lists):
+    return _itertools_chain.from_iterable(lists)
 
 
 def _i64(a):
@@ -206,30 +212,32 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
             n = len(names)
             if not (len(params) == n and len(wires) == n and len(inverses) == n):
                 raise PLException("Incompatible number of ops, params, wires and inverses")
-            self.names = [str(s) for s in names]
-            self.params = [np.array(p, dtype=np.float64).ravel() for p in params]
-            self.wires = [[int(w) for w in ws] for ws in wires]
+            # marshalling is on the e2e path of every apply(): flat numpy buffers, no per-gate arrays
+            self.names = [s if type(s) is str else str(s) for s in names]
+            self.params = [p if type(p) is list else np.asarray(p, dtype=np.float64).ravel().tolist()
+                           for p in params]
+            self.wires = [ws if type(ws) is list else [int(w) for w in ws] for ws in wires]
             self.inverses = [bool(i) for i in inverses]
-            mats = list(matrices) if matrices is not None else [None] * n
-            if len(mats) < n:
-                mats += [None] * (n - len(mats))
-            self._mats = [None if m is None or np.size(m) == 0
-                          else np.ascontiguousarray(m, dtype=np.complex128).ravel() for m in mats]
+            self._mats = None
+            mat_ptrs = None
+            if matrices is not None and any(m is not None and np.size(m) for m in matrices):
+                mats = list(matrices) + [None] * (n - len(matrices))
+                self._mats = [None if m is None or np.size(m) == 0
+                              else np.ascontiguousarray(m, dtype=np.complex128).ravel() for m in mats]
+                mat_ptrs = (_lib.dp * n)(*[
+                    m.ctypes.data_as(_lib.dp) if m is not None else C.cast(None, _lib.dp)
+                    for m in self._mats])
             c_names = (C.c_char_p * n)(*[s.encode() for s in self.names])
-            flat_p = np.concatenate(self.params) if n and sum(p.size for p in self.params) else \
-                np.zeros(0)
-            flat_p = np.ascontiguousarray(flat_p, dtype=np.float64)
-            nparams = (C.c_int * n)(*[int(p.size) for p in self.params])
-            flat_w = np.array([w for ws in self.wires for w in ws], dtype=np.int64)
-            nwires = (C.c_int * n)(*[len(ws) for ws in self.wires])
-            inv = (C.c_int * n)(*[int(i) for i in self.inverses])
-            mat_ptrs = (_lib.dp * n)(*[
-                m.ctypes.data_as(_lib.dp) if m is not None else C.cast(None, _lib.dp)
-                for m in self._mats])
+            flat_p = np.fromiter(_chain(self.params), dtype=np.float64)
+            nparams = np.fromiter(map(len, self.params), dtype=np.int32, count=n)
+            flat_w = np.fromiter(_chain(self.wires), dtype=np.int64)
+            nwires = np.fromiter(map(len, self.wires), dtype=np.int32, count=n)
+            inv = np.fromiter(self.inverses, dtype=np.int32, count=n)
             h = C.c_void_p()
-            check(lib.b2sv_ops_create(n, c_names, flat_p.ctypes.data_as(_lib.dp), nparams,
-                                      flat_w.ctypes.data_as(_lib.i64p), nwires, inv, mat_ptrs,
-                                      C.byref(h)))
+            check(lib.b2sv_ops_create(n, c_names, flat_p.ctypes.data_as(_lib.dp),
+                                      nparams.ctypes.data_as(_lib.ip), flat_w.ctypes.data_as(_lib.i64p),
+                                      nwires.ctypes.data_as(_lib.ip), inv.ctypes.data_as(_lib.ip),
+                                      mat_ptrs, C.byref(h)))
             self._h = h
 
         def __del__(self):
