@@ -4,6 +4,12 @@ executor / scheduler knobs, one subprocess per setting (the knobs are read once 
 Prints one JSON line per setting: ms per step, sweeps, ms per sweep, achieved GB/s per sweep and,
 with B2SV_TILE_PROF=1, the phase-timer breakdown (fractions of the lead threads' lifetime).
 
+Knobs (all read once per process): B2SV_MAX_HEAVY (arithmetic ops per pass, default automatic),
+B2SV_FACTOR (0: no factored rounds), B2SV_FUSE_STORE (0: store phase only), B2SV_TILE_LOW (contiguous
+low bits of a tile, 2..6, default 5), B2SV_TILE_FLAGS (1: lockstep worker groups, 2: free-running),
+B2SV_TILE_PROF (1: phase timers), B2SV_ADJOINT_RUNS (0: per-gate adjoint sweep), B2SV_LIB (path of an
+alternative libb2sv.so for A/B runs inside one box -- boxes differ by up to 15 %).
+
 usage: python benchmarks/tile_experiments.py [--qubits 30] [--layers 4] [--steps 3]
 """
 import argparse
@@ -16,16 +22,15 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SETTINGS = [
-    {"B2SV_MAX_HEAVY": "4", "B2SV_TILE_FLAGS": "4"},
-    {"B2SV_MAX_HEAVY": "4", "B2SV_TILE_FLAGS": "12"},
-    {"B2SV_MAX_HEAVY": "4", "B2SV_TILE_FLAGS": "8"},
-    {"B2SV_MAX_HEAVY": "4"},
-    {"B2SV_TILE_FLAGS": "12"},
-    {"B2SV_TILE_FLAGS": "4"},
-    {"B2SV_TILE_FLAGS": "8"},
-    {},
-    {"B2SV_TILE_FLAGS": "8", "B2SV_MAX_HEAVY": "12"},
+    {},                                   # defaults: automatic budget, factored rounds, fused stores
+    {"B2SV_TILE_PROF": "1"},              # + phase timers
+    {"B2SV_FACTOR": "0"},                 # unfactored dense rounds
+    {"B2SV_FUSE_STORE": "0"},             # always the store phase
+    {"B2SV_MAX_HEAVY": "4"},              # one round per pass (streaming ceiling of the executor)
     {"B2SV_MAX_HEAVY": "12"},
+    {"B2SV_TILE_LOW": "4"},               # 256-byte runs
+    {"B2SV_TILE_FLAGS": "1"},             # worker groups in lockstep
+    {"B2SV_TILE_FLAGS": "2"},             # worker groups free-running
 ]
 
 
@@ -78,8 +83,7 @@ def child(args):
                        "worker_cycles_per_tile": (p[0] + p[1]) / p[4], "worker_wait_cycles_per_tile": p[0] / p[4],
                        "cta_cycles_per_sweep": p[5] / (148.0 * st["sweeps"]),
                        "last_round_cycles_per_tile": p[6] / p[4], "other_rounds_cycles_per_tile": p[7] / p[4],
-                       "worker_prologue_cycles_per_tile": p[10] / p[4], "store_wait_per_tile": p[8] / p[4],
-                       "store_drain_per_tile": p[9] / p[4], "load_issue_per_tile": p[11] / p[4]}
+                       "worker_prologue_cycles_per_tile": p[10] / p[4], "load_issue_per_tile": p[11] / p[4]}
     print("RESULT " + json.dumps(out), flush=True)
 
 
