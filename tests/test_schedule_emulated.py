@@ -88,3 +88,25 @@ def test_every_gate_pattern():
 
 def test_sel_circuit():
     check(sel_circuit(13, 3), 13)
+
+
+def test_long_circuit_bounded_scan():
+    """Scheduling uses a bounded look-ahead window and gives up on a pass after 512 misses in a row;
+    a 3000-gate circuit (more pending ops than either bound) must still come out exact."""
+    n = 13
+    circ = random_circuit(n, 3000, seed=123)
+    st = check(circ, n, max_heavy=0, tol=5e-12)
+    assert st["passes"] < 1200
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_geometry_and_budget(seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(12, 15))
+    f32 = bool(rng.integers(2))
+    B = int(rng.integers(11, 13)) + (1 if f32 else 0)
+    low = int(rng.integers(2, 7))
+    mh = int(rng.choice([0, 3, 5, 9, 24]))
+    circ = random_circuit(n, 200, seed=seed) + layered_circuit(n, 1, seed=seed)
+    check(circ, n, f32=f32, B=B, low=low, max_heavy=mh, factor=bool(rng.integers(2)),
+          store_mode=int(rng.integers(2)), tol=1e-4 if f32 else None)
