@@ -359,7 +359,8 @@ def run_b200(args):
                 "note": "achieved = 2*16*2^n bytes per tile-kernel launch / (CUDA-event time of the "
                         "timed region / tile-kernel launches); the region holds only tile-kernel "
                         "launches (pass descriptors travel as kernel parameters). Sustained figure: "
-                        "the region is ~2 s of back-to-back launches under the 1 kW power cap.",
+                        "the region is steps x ~0.1 s of back-to-back launches under the 1 kW power cap "
+                        "(a single launch under ncu runs 13 % faster, profiles/r1_ncu_tile_v20.summary.txt).",
             },
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": blob_bytes,
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
