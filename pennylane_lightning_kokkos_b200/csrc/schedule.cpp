@@ -349,6 +349,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
     const int N = static_cast<int>(prims.size());
     std::vector<char> done(N, 0);
     std::vector<Pass> passes;
+    passes.reserve(static_cast<size_t>(N) / 4 + 8); // a Pass carries a 4 KB header: avoid regrowth copies
     const uint64_t low_mask = bit(low) - 1;
 
     int first = 0;
@@ -460,6 +461,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
             free_bits--;
         }
         std::vector<int> chosen;
+        chosen.reserve(kMaxOpsPerPass);
         // bounded look-ahead: ops further than kScanWindow pending ops away wait for a later pass
         // (skipping is always legal), which keeps scheduling linear in the circuit length
         constexpr int kScanWindow = 8192;
@@ -574,6 +576,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
             { // boundary: absorb every permutation that commutes back to here
                 Blocker lb;
                 std::vector<int> rest;
+                rest.reserve(remaining.size());
                 for (int i : remaining) {
                     const Prim &p = prims[i];
                     const int cls = lb.blocked(p) ? 0 : perm_class(p);
@@ -598,6 +601,8 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
             // in the first sweep was not blocked by anything before it, so it commutes with every
             // earlier op that is still waiting.
             std::vector<int> now, later;
+            now.reserve(remaining.size());
+            later.reserve(remaining.size());
             std::vector<char> taken(remaining.size(), 0);
             for (int sweep = cfg.fuse_store ? 0 : 1; sweep < 2; sweep++) {
                 Blocker rb;
@@ -634,6 +639,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
             B2_ASSERT(!now.empty());
             // register slots in order of first use by the round's ops, then the padding bits
             std::vector<int> slot_bits;
+            slot_bits.reserve(kMaxRegBits + 1);
             for (int i : now) {
                 const Prim &p = prims[i];
                 if (p.type != Prim::C1Q)
