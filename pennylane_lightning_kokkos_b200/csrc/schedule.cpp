@@ -348,6 +348,10 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
         factor ? split_antidiagonal(fuse_single_qubit(prims_in)) : fuse_single_qubit(prims_in);
     const int N = static_cast<int>(prims.size());
     std::vector<char> done(N, 0);
+    // permutation 2x2s (X, CNOT, Toffoli ...) that may be folded into the address map: classified once
+    std::vector<char> is_perm(N, 0);
+    for (int i = 0; i < N; i++)
+        is_perm[i] = prims[i].type == Prim::C1Q && prims[i].tag < 0 && classify(prims[i]) == KIND_PERM;
     std::vector<Pass> passes;
     passes.reserve(static_cast<size_t>(N) / 4 + 8); // a Pass carries a 4 KB header: avoid regrowth copies
     const uint64_t low_mask = bit(low) - 1;
@@ -384,8 +388,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                 const Prim &p = prims[i];
                 if (p.type == Prim::MATK)
                     break; // full barrier
-                const bool light = cfg.free_perms && p.type == Prim::C1Q && p.tag < 0 &&
-                                   classify(p) == KIND_PERM;
+                const bool light = cfg.free_perms && is_perm[i];
                 // balance: a pass is HBM-bound up to ~max_heavy gates; beyond that the arithmetic is
                 // the limit, so later passes (which stream the state anyway) should take the rest
                 bool fits = !blk.blocked(p) && (light || heavy < cfg.max_heavy);
@@ -528,9 +531,10 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
             return j;
         };
         // 0 = not absorbable, 1 = CNOT inside the tile, 2 = X toggled by CTA-uniform bits
-        auto perm_class = [&](const Prim &p) {
-            if (!cfg.free_perms || p.type != Prim::C1Q || p.tag >= 0 || classify(p) != KIND_PERM)
+        auto perm_class = [&](int i) {
+            if (!cfg.free_perms || !is_perm[i])
                 return 0;
+            const Prim &p = prims[i];
             const uint64_t in_tile = p.cmask & tile_mask;
             if (in_tile == 0)
                 return n_cx < kMaxCx ? 2 : 0;
@@ -579,7 +583,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                 rest.reserve(remaining.size());
                 for (int i : remaining) {
                     const Prim &p = prims[i];
-                    const int cls = lb.blocked(p) ? 0 : perm_class(p);
+                    const int cls = lb.blocked(p) ? 0 : perm_class(i);
                     if (cls) {
                         absorb(p, cls, n_rounds);
                     } else {
@@ -611,7 +615,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                         continue;
                     const Prim &p = prims[remaining[r]];
                     // an absorbable permutation waits for the next round boundary, where it is free
-                    bool fits = !rb.blocked(p) && perm_class(p) == 0;
+                    bool fits = !rb.blocked(p) && perm_class(remaining[r]) == 0;
                     if (fits && sweep == 0)
                         fits = p.type == Prim::C1Q && tile_pos(p.target) < 5;
                     if (fits && p.type == Prim::C1Q) {
