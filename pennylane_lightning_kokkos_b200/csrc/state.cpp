@@ -73,6 +73,18 @@ bool pool_give_state(int device, size_t bytes, void *p) { // caller: the buffer 
     g_spare_states.push_back({device, bytes, p});
     return true;
 }
+// gives every pooled state buffer back to the driver (called when an allocation fails)
+void pool_release_states() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (const SpareState &sp : g_spare_states) {
+        cudaSetDevice(sp.device);
+        cudaFree(sp.p);
+    }
+    g_spare_states.clear();
+    cudaSetDevice(cur);
+}
 bool pool_take_aux(int device, SpareAux *out) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     for (size_t i = 0; i < g_spare_aux.size(); i++)
@@ -182,6 +194,11 @@ void State::init_common(const void *nccl_id) {
     d_state_ = world_ > 1 ? nullptr : pool_take_state(device_, alloc_length() * amp_bytes());
     if (!d_state_) {
         e = cudaMalloc(&d_state_, alloc_length() * amp_bytes());
+        if (e != cudaSuccess) { // the pooled buffers of smaller states may be what is in the way
+            cudaGetLastError();
+            pool_release_states();
+            e = cudaMalloc(&d_state_, alloc_length() * amp_bytes());
+        }
         B2_ABORT_IF(e != cudaSuccess, std::string("cannot allocate the state vector: ") +
                                           cudaGetErrorString(e));
     }
@@ -327,6 +344,11 @@ void *State::acquire_scratch() const {
     if (p)
         return p;
     cudaError_t e = cudaMalloc(&p, alloc_length() * amp_bytes());
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_release_states();
+        e = cudaMalloc(&p, alloc_length() * amp_bytes());
+    }
     B2_ABORT_IF(e != cudaSuccess, std::string("cannot allocate a scratch state vector: ") +
                                       cudaGetErrorString(e));
     return p;
