@@ -65,6 +65,12 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
     auto flush = [&]() {
         if (batch.empty())
             return;
+        // wires are validated when the ops are lowered; an out-of-range wire must reach that check
+        // (and its error message) instead of indexing the tables below
+        for (const GateOp &op : batch)
+            for (auto w : op.wires)
+                if (w < 0 || w >= static_cast<int64_t>(sv.num_qubits()))
+                    run_segments.clear();
         // The single-qubit gates of a run commute across wires, so their order inside the batch is
         // free. Put them in the order in which the ops AFTER the run first act on their wires
         // (last wire of a multi-qubit gate = its target): the tile passes that carry the gates then
