@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Developer experiment: where the adjoint Jacobian time of BASELINE config 3 goes
 (Hamiltonian application vs per-layer reverse sweep)."""
-import json, os, sys, time
+import json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "benchmarks"))

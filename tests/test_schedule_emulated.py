@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import emu
-from cases import GATES, gate_cases, layered_circuit, random_circuit, random_state, sel_circuit
+from cases import gate_cases, layered_circuit, random_circuit, random_state, sel_circuit
 from oracle import np_oracle as npo
 
 
