@@ -20,6 +20,10 @@ pass this exceeds the HBM peak; the `roofline` object reports what the tile kern
             H2D) followed by ExpectationValue("PauliZ") read back to the host (D2H of the scalar).
             The state vector itself is device-resident by the reference's API contract
             (HostToDevice/DeviceToHost are explicit calls, StateVectorKokkos.hpp:1618-1628).
+  adjoint_jacobian
+            (N = 1 only) the second half of BASELINE.json's metric: BASELINE config 3, a 24-qubit
+            hardware-efficient ansatz with 504 parameters and a 100-term Pauli Hamiltonian, seconds
+            per adjoint Jacobian through AdjointJacobianKokkos_C128.adjoint_jacobian.
   cpu_baseline / --impl reference
             the UNMODIFIED reference functors (oracle/_ref/libref_oracle.so: reference headers over
             the OpenMP Kokkos stand-in) on the host cores, on a bounded sample of the same layer.
@@ -219,6 +223,22 @@ def cpu_baseline_sample(n, budget_s=20.0):
                 "sample": f"failed: {e}"}
 
 
+def adjoint_sample(ops_module):
+    """The second half of BASELINE.json's metric ("adjoint-Jacobian s/circuit"): BASELINE config 3
+    (24 qubits, 504 parameters, 100-term Pauli Hamiltonian) through the binding's adjoint_jacobian,
+    single GPU. Never allowed to break the bench line."""
+    try:
+        bdir = os.path.join(ROOT, "benchmarks")
+        if bdir not in sys.path:
+            sys.path.insert(0, bdir)
+        import configs as cfgs
+        r = cfgs.config3(ops_module, 3)
+        return {"s_per_jacobian": r["s_per_jacobian"], "s_forward": r["s_forward"],
+                "workload": r["workload"], "jac_norm": r["jac_norm"]}
+    except Exception as e:  # pragma: no cover
+        return {"s_per_jacobian": None, "error": str(e)[:200]}
+
+
 # --------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -373,6 +393,8 @@ def run_b200(args):
             line["comm"] = comm
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_adjoint:
+            line["adjoint_jacobian"] = adjoint_sample(ops)
         print(json.dumps(line))
     del sv
     if world > 1:
@@ -390,6 +412,7 @@ def main():
     ap.add_argument("--qubits", type=int, default=30, help="qubits per GPU (weak scaling)")
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-adjoint", action="store_true", help="skip the config-3 adjoint Jacobian sample")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
