@@ -496,6 +496,26 @@ def test_adjoint_vs_reference(ops, ref, dtype, n, layers):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_reference_param_gate_literals(ops, dtype):
+    """In/out state vectors written out in the reference's own tests
+    (src/tests/Test_StateVectorKokkos_Param.cpp, extracted into tests/golden/ref_param_literals.json)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_param_literals.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) >= 7
+    for c in cases:
+        ini = np.array([complex(a, b) for a, b in c["ini"]], dtype=dtype)
+        want = np.array([complex(a, b) for a, b in c["expected"]])
+        n = int(np.log2(ini.size))
+        sv = sv_class(ops, dtype)(n)
+        sv.HostToDevice(ini)
+        getattr(sv, c["gate"])(c["wires"], c["inverse"], c["params"])
+        # the literals carry ~7 digits (the reference compares them with Catch2 Approx, 1.2e-5 relative)
+        assert np.max(np.abs(to_host(sv, n, dtype) - want)) < 2e-6, c["gate"]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_adjoint_runs_equal_per_gate_path(ops, dtype, monkeypatch):
     """Runs of single-qubit gates are differentiated from batched transition sums (adjoint.cpp); the
     result must equal the per-gate sweep (B2SV_ADJOINT_RUNS=0) on a 20-qubit ansatz with inverse

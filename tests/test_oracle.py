@@ -192,3 +192,30 @@ def test_golden_fixtures_match_np_oracle():
     jac = npo.adjoint_jacobian(psi, 6, [ham], circ, [int(t) for t in g["tp"]])
     assert np.max(np.abs(jac - g["jac"])) < 1e-13
     assert npo.expval(psi, 6, ham) == pytest.approx(float(g["expval"]), abs=1e-13)
+
+
+def _ref_param_literals():
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_param_literals.json")
+    with open(path) as f:
+        return json.load(f)["cases"]
+
+
+def test_reference_param_gate_literals_pin_both_oracles():
+    """The literal in/out state vectors of the reference's own parametric-gate tests
+    (src/tests/Test_StateVectorKokkos_Param.cpp: IsingXY :24-62, SingleExcitation[Minus/Plus]
+    :960-1110, DoubleExcitation[Minus/Plus] :1127-1320; extracted by tests/golden/make_ref_literals.py)
+    pin the compiled reference over the Kokkos stand-in AND the NumPy restatement."""
+    cases = _ref_param_literals()
+    assert len(cases) >= 7
+    for c in cases:
+        ini = np.array([complex(a, b) for a, b in c["ini"]])
+        want = np.array([complex(a, b) for a, b in c["expected"]])
+        n = int(np.log2(ini.size))
+        got_np = npo.apply_gate(ini, n, c["gate"], c["wires"], c["inverse"], c["params"])
+        assert np.max(np.abs(got_np - want)) < 2e-6, (c["gate"], c["ref_line"])  # the literals carry ~7 digits
+        if ref.available():
+            sv = ref.RefStateVector(n)
+            sv.h2d(ini)
+            sv.apply(c["gate"], c["wires"], c["inverse"], c["params"])
+            assert np.max(np.abs(sv.d2h() - want)) < 2e-6, (c["gate"], c["ref_line"])
