@@ -110,3 +110,19 @@ def test_random_geometry_and_budget(seed):
     circ = random_circuit(n, 200, seed=seed) + layered_circuit(n, 1, seed=seed)
     check(circ, n, f32=f32, B=B, low=low, max_heavy=mh, factor=bool(rng.integers(2)),
           store_mode=int(rng.integers(2)), tol=1e-4 if f32 else None)
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_reference_param_gate_literals_through_the_scheduler(f32):
+    """The reference's own literal in/out vectors (tests/golden/ref_param_literals.json) through
+    lower -> schedule -> emulated passes, both table precisions."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_param_literals.json")) as f:
+        cases = json.load(f)["cases"]
+    for c in cases:
+        ini = np.array([complex(a, b) for a, b in c["ini"]])
+        want = np.array([complex(a, b) for a, b in c["expected"]])
+        n = int(np.log2(ini.size))
+        got, _ = emu.run([(c["gate"], c["wires"], c["inverse"], c["params"])], n, ini, f32=f32)
+        assert np.max(np.abs(got - want)) < 2e-6, c["gate"]  # the literals carry ~7 digits
