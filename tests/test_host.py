@@ -118,3 +118,30 @@ def test_plan_rejects_bad_input():
     ops = m.OpsStructKokkos_C128(["NotAGate"], [[]], [[0]], [False])
     with pytest.raises(m.PLException):
         ops.plan(4)  # neither a named gate nor a matrix
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` is CPU-only: one JSON line with impl/metric/e2e/cpu_baseline; under
+    torchrun with 2 ranks only rank 0 prints it and the other rank exits 0."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bench = os.path.join(root, "bench.py")
+    base = [sys.executable, bench, "--impl", "reference", "--qubits", "16", "--steps", "1", "--warmup", "1"]
+    out = subprocess.run(base, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    if "unavailable" in d:
+        pytest.skip("oracle/_ref not built")
+    assert d["impl"] == "reference" and d["unit"] == "GB/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    port = 29700 + (os.getpid() % 1000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port)] + base[1:] + ["--gpus", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0])["impl"] == "reference"
