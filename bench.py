@@ -5,31 +5,41 @@ One "step" = LAYERS (default 4) layers of [RX,RY,RZ on every wire + CNOT ring] =
 applied to a device-resident 2^n state (n = 30 on one GPU: 17.2 GB >> the 126 MB L2, so no L2
 flush is needed between steps).  The state is prepared by one Hadamard layer (untimed).
 
-Metric (both arms): "gate-layer GB/s" = reference-equivalent bytes per second, i.e. the bytes the
-reference's one-gate-per-sweep schedule (reference StateVectorKokkos.hpp:807-824) has to move for
-the same gates, sum_g touch(g) * 2*16*2^n with touch = 1 for RX/RY/RZ and 1/2 for CNOT
-(SURVEY.md section 8d), divided by the measured time.  Because the engine fuses many gates per HBM
-pass this exceeds the HBM peak; the `roofline` object reports what the tile kernel really moves:
-(sweeps executed) * 2*16*2^n bytes / time, against MEASURED_PEAKS.json.
+Metric (both arms): gate-layer throughput in reference-equivalent GB/s, i.e. the bytes the
+reference's one-gate-per-sweep schedule (reference StateVectorKokkos.hpp:807-824) moves for the
+same gates, sum_g touch(g) * 2*16*2^n with touch = 1 for RX/RY/RZ and 1/2 for CNOT (SURVEY.md
+section 8d), divided by the measured time.  For the reference arm this IS its memory traffic; the
+engine fuses many gates per HBM pass, so its figure exceeds the HBM peak -- what the tile kernel
+really moves is in `roofline` (algorithmic bytes of one pass / the pass's measured duration,
+against MEASURED_PEAKS.json) and repeated at top level as `hbm_gbs` / `hbm_frac`.
 
   value     b2sv_apply_ops on a pre-built op-list handle with the state resident in HBM (includes
-            the host-side fusion scheduling and the few-KB pass-descriptor upload), CUDA events on
-            the engine's stream.
+            the host-side fusion scheduling and the pass-descriptor upload), CUDA events on the
+            engine's stream, max over ranks.
+  roofline  every tile-kernel launch of two further steps is bracketed by its own pair of CUDA events
+            (b2sv_trace_begin/_end): `achieved` = 2*16*2^n bytes / mean launch duration; at N > 1 the
+            exchanges are timed the same way and reported against the NVLink peer-copy figure.
   e2e       the call a user of the reference API makes: LightningKokkos_C128.apply(names, wires,
             inverses, params) from HOST Python lists (marshalling, lowering, scheduling, descriptor
             H2D) followed by ExpectationValue("PauliZ") read back to the host (D2H of the scalar).
             The state vector itself is device-resident by the reference's API contract
             (HostToDevice/DeviceToHost are explicit calls, StateVectorKokkos.hpp:1618-1628).
+  parity    checked in the same run.  N = 1: the reference (oracle/_ref) applies one full layer to a
+            30-qubit |0..0> on the host cores (that is also the cpu_baseline timing), the engine does
+            the same on the GPU and 4096 sampled amplitudes + the norm are compared.  N > 1: 17..19
+            qubit layered and random circuits on sharded states against the NumPy oracle.
   adjoint_jacobian
-            (N = 1 only) the second half of BASELINE.json's metric: BASELINE config 3, a 24-qubit
+            (N = 1) the second half of BASELINE.json's metric: BASELINE config 3, a 24-qubit
             hardware-efficient ansatz with 504 parameters and a 100-term Pauli Hamiltonian, seconds
-            per adjoint Jacobian through AdjointJacobianKokkos_C128.adjoint_jacobian.
-  cpu_baseline / --impl reference
+            per adjoint Jacobian; the same ansatz at 20 qubits is run through the reference on the
+            host (cpu_baseline + parity of the full Jacobian).
+  --impl reference
             the UNMODIFIED reference functors (oracle/_ref/libref_oracle.so: reference headers over
-            the OpenMP Kokkos stand-in) on the host cores, on a bounded sample of the same layer.
+            the OpenMP Kokkos stand-in) on all host cores; one step = one full 120-gate layer of the
+            same circuit on a 30-qubit state.
 
-Multi-GPU (torchrun, one rank per GPU): weak scaling, n = 30 + log2(N) qubits, rank = top index
-bits; gates on global qubits trigger NVLink qubit swaps (csrc/comm.cpp).
+Multi-GPU (torchrun, one rank per GPU): weak scaling, n = qubits + log2(N), rank = top index
+bits; gates on global qubits trigger NVLink exchanges (csrc/comm.cpp).
 """
 from __future__ import annotations
 
@@ -49,7 +59,10 @@ if ROOT not in sys.path:
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 TOUCH = {"RX": 1.0, "RY": 1.0, "RZ": 1.0, "CNOT": 0.5}
-NCU_TRAFFIC_30Q = 34.328e9  # dram read + write bytes per tile-kernel launch (profiles/r1_ncu_tile_v20.summary.txt)
+METRIC = ("30q c128 gate-layer GB/s (reference-equivalent bytes: what one gate per HBM sweep moves "
+          "for the same gates; roofline.achieved is the HBM traffic rate vs peak)")
+NVLINK_PEER_GBS = 770.0  # measured peer-copy GB/s per direction, B200_PROFILING.md
+PARITY_SAMPLES = 4096
 
 
 def layer_circuit(n, layers, seed=42):
@@ -69,12 +82,41 @@ def ref_equiv_bytes(ops, n, amp_bytes=16):
     return sum(TOUCH[o[0]] for o in ops) * sweep
 
 
+def static_config(world, qubits_per_gpu, layers):
+    """The workload description: identical in both arms (the reference arm samples it)."""
+    g = world.bit_length() - 1
+    n = qubits_per_gpu + g
+    return {
+        "workload": f"{n}-qubit c128 RX/RY/RZ + CNOT-ring layers (BASELINE config 2), "
+                    f"{layers} layers = {4 * n * layers} gates per step",
+        "qubits": n, "qubits_per_gpu": qubits_per_gpu, "layers_per_step": layers,
+        "gates_per_step": 4 * n * layers,
+        "bytes": "reference-equivalent: sum_g touch(g)*2*16*2^n (touch 1 for RX/RY/RZ, 1/2 for CNOT)",
+        "l2": f"state {16 * (1 << qubits_per_gpu) / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
+        "parallelism": f"state sharded over {world} GPU(s), rank = top {g} index bits",
+    }
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f), "measured"
-    return {"hbm_gbs": 6650.0}, "fallback"
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(qubits_per_gpu):
+    """dram read + write bytes of one tile-kernel launch from the committed ncu capture of this
+    round (profiles/r2_ncu_tile.json, written by profiles/summarize_ncu.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_tile.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        if int(d.get("qubits", -1)) == qubits_per_gpu:
+            return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -137,49 +179,79 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def load_reference():
+    """oracle/_ref with every host core, whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1); must run before libgomp is initialised by the oracle's first call."""
+    nthr = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(nthr)
+    os.environ.setdefault("OMP_PROC_BIND", "true")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    from oracle import ref
+    if not ref.available():
+        return None, 0
+    ref.set_num_threads(nthr)
+    return ref, ref.num_threads()
+
+
+def sample_indices(n, count=PARITY_SAMPLES, seed=7):
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, 1 << n, size=count, dtype=np.uint64)
+    idx[:4] = (0, 1, (1 << n) - 1, 1 << (n - 1))
+    return idx
+
+
+def reference_layer_run(ref, n, steps, warmup, keep_amplitudes):
+    """One step = the first full layer (120 gates at n = 30) of the bench circuit on an n-qubit c128
+    state held by the reference.  Returns (seconds per step, sampled amplitudes after the FIRST
+    application to |0..0> or None, description)."""
+    layer = layer_circuit(n, 1, seed=42)
+    sv = ref.RefStateVector(n, np.complex128)
+    amps = None
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        sv.apply_ops(layer)
+        dt = time.perf_counter() - t0
+        if it == 0 and keep_amplitudes:
+            amps = sv.amplitudes(sample_indices(n).astype(np.int64))
+        if it >= warmup:
+            times.append(dt)
+    desc = (f"one full layer of the bench circuit ({len(layer)} gates: RX,RY,RZ on every wire + CNOT "
+            f"ring) per step on a {n}-qubit c128 state, reference functors over the OpenMP Kokkos "
+            f"stand-in, {len(times)} timed step(s)")
+    return float(np.mean(times)), amps, desc, layer
+
+
 def run_reference(args):
     """The reference's own CPU implementation (its functors over the OpenMP Kokkos stand-in)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import ref
-    if not ref.available():
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    ref, cores = load_reference()
+    if ref is None:
         print(json.dumps({"impl": "reference",
                           "unavailable": "oracle/_ref/libref_oracle.so missing (needs the build container)"}))
         return 0
-    n = args.qubits
-    cores = ref.num_threads()
-    # bounded sample of one layer: RX,RY,RZ on a low / middle / high wire + 3 CNOTs of the ring
-    rng = np.random.default_rng(42)
-    sample = []
-    for w in (0, n // 2, n - 1):
-        for g in ("RX", "RY", "RZ"):
-            sample.append((g, [w], False, [float(rng.uniform(0, 2 * np.pi))]))
-    for w in (0, n // 2, n - 1):
-        sample.append(("CNOT", [w, (w + 1) % n], False, []))
-    sv = ref.RefStateVector(n, np.complex128)
-    for w in (0, n - 1):
-        sv.apply("Hadamard", [w])
-    nbytes = ref_equiv_bytes(sample, n)
-    for _ in range(args.warmup):
-        sv.apply_ops(sample)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        sv.apply_ops(sample)
-    dt = (time.perf_counter() - t0) / args.steps
-    val = nbytes / dt / 1e9
-    desc = (f"{len(sample)} gates of one layer (RX,RY,RZ on wires 0,{n // 2},{n - 1} + 3 ring CNOTs) "
-            f"on the full {n}-qubit c128 state, {cores} OpenMP threads")
+    n = args.ref_qubits
+    dt, _, desc, layer = reference_layer_run(ref, n, args.steps, args.warmup, False)
+    val = ref_equiv_bytes(layer, n) / dt / 1e9
+    sample = desc + f"; {cores} OpenMP threads"
     line = {
-        "impl": "reference", "metric": "30q c128 gate-layer GB/s", "value": val, "unit": "GB/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)",
         "data": "synthetic",
-        "config": {"workload": f"{n}-qubit c128 RX/RY/RZ + CNOT-ring layers (BASELINE config 2)",
-                   "qubits": n, "sample": desc,
-                   "bytes": "reference-equivalent: sum_g touch(g)*2*16*2^n"},
+        "config": static_config(world, args.qubits, args.layers),
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "reference",
-                         "sample": desc},
+                         "sample": sample},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -187,54 +259,85 @@ def run_reference(args):
     return 0
 
 
-def cpu_baseline_sample(n, budget_s=20.0):
-    """Rank 0, N=1 only: time the reference on a bounded sample (see run_reference)."""
+def cpu_baseline_and_parity(sv, n):
+    """Rank 0, N = 1: the reference applies one full layer to |0..0> on the host (timed = the
+    cpu_baseline), the engine applies the same layer on the GPU; sampled amplitudes are compared."""
     try:
-        from oracle import ref
-        if not ref.available():
-            return {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference",
-                    "sample": "oracle/_ref missing"}
-        cores = ref.num_threads()
-        rng = np.random.default_rng(42)
-        sample = []
-        for w in (0, n // 2, n - 1):
-            for g in ("RX", "RY", "RZ"):
-                sample.append((g, [w], False, [float(rng.uniform(0, 2 * np.pi))]))
-        for w in (0, n // 2, n - 1):
-            sample.append(("CNOT", [w, (w + 1) % n], False, []))
-        sv = ref.RefStateVector(n, np.complex128)
-        sv.apply("Hadamard", [0])
-        sv.apply("Hadamard", [n - 1])
-        t0 = time.perf_counter()
-        reps = 0
-        while True:
-            sv.apply_ops(sample)
-            reps += 1
-            if time.perf_counter() - t0 > budget_s or reps >= 3:
-                break
-        dt = (time.perf_counter() - t0) / reps
-        return {"value": ref_equiv_bytes(sample, n) / dt / 1e9, "unit": "GB/s", "cores": cores,
-                "kind": "reference",
-                "sample": f"{len(sample)} gates of one layer (RX,RY,RZ on wires 0,{n // 2},{n - 1} + 3 "
-                          f"ring CNOTs) on the full {n}-qubit c128 state, {reps} repetition(s), "
-                          f"{dt:.2f} s each, reference functors over the OpenMP Kokkos stand-in"}
+        ref, cores = load_reference()
+        if ref is None:
+            return ({"value": None, "unit": "GB/s", "cores": 0, "kind": "reference",
+                     "sample": "oracle/_ref missing"}, None)
+        dt, amps_ref, desc, layer = reference_layer_run(ref, n, 1, 0, True)
+        cpu = {"value": ref_equiv_bytes(layer, n) / dt / 1e9, "unit": "GB/s", "cores": cores,
+               "kind": "reference", "sample": desc + f", {dt:.1f} s; {cores} OpenMP threads"}
+        sv.setBasisState(0)
+        sv.apply([c[0] for c in layer], [c[1] for c in layer], [c[2] for c in layer],
+                 [c[3] for c in layer])
+        amps = sv.amplitudes(sample_indices(n))
+        norm = sv.ExpectationValue("Identity", [0], [], np.zeros(0))
+        scale = float(np.max(np.abs(amps_ref)))
+        err = float(np.max(np.abs(amps - amps_ref)) / scale)
+        parity = {"max_rel_err": max(err, abs(norm - 1.0)), "amplitude_rel_err": err,
+                  "norm_err": abs(norm - 1.0), "n": n, "world": 1, "samples": int(amps.size),
+                  "tolerance": 1e-12, "ok": bool(err < 1e-12 and abs(norm - 1.0) < 1e-12),
+                  "against": "oracle/_ref (reference functors) on the same 120-gate layer from |0..0>"}
+        return cpu, parity
     except Exception as e:  # the baseline must never break the bench line
-        return {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference",
-                "sample": f"failed: {e}"}
+        return ({"value": None, "unit": "GB/s", "cores": 0, "kind": "reference",
+                 "sample": f"failed: {e}"}, {"ok": False, "error": str(e)[:200]})
+
+
+def sharded_parity(ops, b2dist, dist, torch, local_rank, world):
+    """N > 1, before timing: layered + random circuits on sharded states vs the NumPy oracle."""
+    from cases import layered_circuit, random_circuit
+    from oracle import np_oracle as npo
+
+    g = world.bit_length() - 1
+    worst, cases = 0.0, []
+    for n, circ, tag in ((16 + g, layered_circuit(16 + g, 2, seed=3), "layers"),
+                         (14 + g, random_circuit(14 + g, 120, seed=5), "random")):
+        sv = b2dist.create_sharded_state(ops, n, np.complex128, local_rank)
+        sv.apply([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ], [c[3] for c in circ])
+        ez = [sv.ExpectationValue("PauliZ", [w], [], np.zeros(0)) for w in (0, n - 1)]
+        mine = np.zeros(1 << (n - g), dtype=np.complex128)
+        sv.DeviceToHost(mine)
+        t = torch.from_numpy(mine.view(np.float64)).cuda()
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        full = np.concatenate([p.cpu().numpy() for p in parts]).view(np.complex128)
+        psi0 = np.zeros(1 << n, dtype=complex)
+        psi0[0] = 1
+        want = npo.apply_ops(psi0, n, circ)
+        err = float(np.max(np.abs(full - want)) / np.max(np.abs(want)))
+        ez_want = [npo.expval(want, n, ("named", "PauliZ", [w])) for w in (0, n - 1)]
+        err = max(err, max(abs(a - b) for a, b in zip(ez, ez_want)))
+        worst = max(worst, err)
+        cases.append(f"{tag} n={n}: {err:.1e}")
+        del sv
+        dist.barrier()
+    return {"max_rel_err": worst, "n": 16 + g, "world": world, "tolerance": 1e-12,
+            "ok": bool(worst < 1e-12), "cases": cases,
+            "against": "oracle/np_oracle.py (full state gathered from all ranks + <Z> on a global and a local wire)"}
 
 
 def adjoint_sample(ops_module):
     """The second half of BASELINE.json's metric ("adjoint-Jacobian s/circuit"): BASELINE config 3
-    (24 qubits, 504 parameters, 100-term Pauli Hamiltonian) through the binding's adjoint_jacobian,
-    single GPU. Never allowed to break the bench line."""
+    (24 qubits, 504 parameters, 100-term Pauli Hamiltonian) through the binding's adjoint_jacobian on
+    one GPU, plus the same ansatz at 20 qubits through the reference on the host cores (cpu baseline
+    and parity of the full Jacobian). Never allowed to break the bench line."""
     try:
         bdir = os.path.join(ROOT, "benchmarks")
         if bdir not in sys.path:
             sys.path.insert(0, bdir)
         import configs as cfgs
         r = cfgs.config3(ops_module, 3)
-        return {"s_per_jacobian": r["s_per_jacobian"], "s_forward": r["s_forward"],
-                "workload": r["workload"], "jac_norm": r["jac_norm"]}
+        out = {"s_per_jacobian": r["s_per_jacobian"], "s_forward": r["s_forward"],
+               "workload": r["workload"], "jac_norm": r["jac_norm"], "roofline": r.get("roofline")}
+        try:
+            out["parity_20q"] = cfgs.config3_vs_reference(ops_module, n=20, layers=7, terms=100)
+        except Exception as e:  # pragma: no cover
+            out["parity_20q"] = {"ok": False, "error": str(e)[:200]}
+        return out
     except Exception as e:  # pragma: no cover
         return {"s_per_jacobian": None, "error": str(e)[:200]}
 
@@ -263,11 +366,17 @@ def run_b200(args):
     names, wires = [c[0] for c in circ], [c[1] for c in circ]
     invs, params = [c[2] for c in circ], [c[3] for c in circ]
 
-    if world == 1:
-        sv = ops.LightningKokkos_C128(n)
-    else:
+    parity = None
+    if world > 1:
         from pennylane_lightning_kokkos_b200 import dist as b2dist
+        if not args.no_parity:
+            try:
+                parity = sharded_parity(ops, b2dist, dist, torch, local_rank, world)
+            except Exception as e:
+                parity = {"ok": False, "error": str(e)[:300], "world": world}
         sv = b2dist.create_sharded_state(ops, n, np.complex128, local_rank)
+    else:
+        sv = ops.LightningKokkos_C128(n)
     had = ops.OpsStructKokkos_C128(["Hadamard"] * n, [[] for _ in range(n)],
                                    [[w] for w in range(n)], [False] * n)
     sv.apply_ops(had)
@@ -280,6 +389,13 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
 
+    def reduce_max(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -291,11 +407,7 @@ def run_b200(args):
         sv.sync()
         torch.cuda.synchronize()
         t1 = time.time()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = reduce_max(e0.elapsed_time(e1))
         barrier()
         return ms, t0, t1
 
@@ -310,12 +422,25 @@ def run_b200(args):
         sampler.start()
         time.sleep(0.3)
     sv.reset_stats()
+    comm0 = sv.comm_stats() if world > 1 else {}
     ms_dev, t0, t1 = timed(step_dev, args.steps)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     st = sv.stats()
     sweeps_per_step = st["sweeps"] / args.steps
     launches = st["launches"]
-    comm = sv.comm_stats() if hasattr(sv, "comm_stats") else {}
+    comm = sv.comm_stats() if world > 1 else {}
+
+    # ---- per-kernel timing: every launch of two more steps between its own pair of CUDA events
+    barrier()
+    sv.trace_begin()
+    trace_steps = 2
+    for _ in range(trace_steps):
+        step_dev()
+    trace = sv.trace_end()
+    pass_ms = [d for k, _, d in trace if k == 0]
+    xchg_ms = [d for k, _, d in trace if k == 2]
+    step_ms_traced = (max(s + d for _, s, d in trace) - min(s for _, s, _ in trace)) / trace_steps if trace else None
+    barrier()
 
     # ---- end-to-end arm: host lists -> apply -> expval read back
     def step_e2e():
@@ -331,11 +456,7 @@ def run_b200(args):
         ez = step_e2e()
     sv.sync()
     tw1 = time.perf_counter()
-    ms_e2e = (tw1 - tw0) * 1e3
-    if world > 1:
-        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    ms_e2e = reduce_max((tw1 - tw0) * 1e3)
     blob_bytes = sv.last_upload_bytes() if hasattr(sv, "last_upload_bytes") else 0
     norm = sv.ExpectationValue("Identity", [0], [], np.zeros(0))
 
@@ -344,44 +465,41 @@ def run_b200(args):
     e2e_value = nbytes / (ms_e2e / args.steps * 1e-3) / 1e9
     peaks, which = measured_peaks()
     sweep_bytes = 2.0 * 16 * (1 << args.qubits)  # per GPU, per launch of the tile kernel
-    tile_launches = st["sweeps"]
-    avg_launch_ms = ms_dev / max(1, tile_launches) if not comm.get("swap_ms") else None
-    achieved = sweep_bytes / (ms_dev / max(1, tile_launches) * 1e-3) / 1e9
+    avg_pass_ms = float(np.mean(pass_ms)) if pass_ms else None
+    achieved = sweep_bytes / (avg_pass_ms * 1e-3) / 1e9 if avg_pass_ms else None
     line = None
     if rank == 0:
-        cpu = cpu_baseline_sample(args.qubits) if (world == 1 and not args.no_cpu_baseline) else None
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, parity = cpu_baseline_and_parity(sv, n)
+        cfg = static_config(world, args.qubits, args.layers)
+        roof = {
+            "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"] if achieved else None,
+            "traffic": ncu_traffic(args.qubits), "peak_source": which,
+            "kernel": "tile_exec_kernel<double,12,4,...> (persistent, one CTA per SM)",
+            "algorithmic_bytes_per_launch": sweep_bytes,
+            "avg_launch_ms": avg_pass_ms,
+            "launches_timed": len(pass_ms),
+            "kernel_share_of_step": (sum(pass_ms) / trace_steps) / step_ms_traced if step_ms_traced else None,
+            "note": "achieved = 2*16*2^n bytes / mean duration of the tile-kernel launches of "
+                    f"{trace_steps} steps, each launch bracketed by its own CUDA events on the engine's "
+                    "stream (b2sv_trace_begin/_end), back to back under the power cap; sustained-step "
+                    "figure = sweeps_per_step * bytes / ms_per_step in `hbm_gbs_step`.",
+        }
+        hbm_step = sweeps_per_step * sweep_bytes / (ms_dev / args.steps * 1e-3) / 1e9
         line = {
-            "metric": "30q c128 gate-layer GB/s", "value": value, "unit": "GB/s",
+            "metric": METRIC, "value": value, "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
-            "config": {
-                "workload": f"{n}-qubit c128 RX/RY/RZ + CNOT-ring layers (BASELINE config 2), "
-                            f"{args.layers} layers = {len(circ)} gates per step",
-                "qubits": n, "qubits_per_gpu": args.qubits, "layers_per_step": args.layers,
-                "gates_per_step": len(circ),
-                "bytes": "reference-equivalent: sum_g touch(g)*2*16*2^n (touch 1 for RX/RY/RZ, 1/2 for CNOT)",
-                "l2": f"state {16 * (1 << args.qubits) / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
-                "sweeps_per_step": sweeps_per_step,
-                "gates_per_s": len(circ) / (ms_dev / args.steps * 1e-3),
-                "parallelism": f"state sharded over {world} GPU(s), rank = top {g} index bits",
-                "checks": {"norm": norm, "expval_Z_last": ez},
-            },
-            "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                # (profiles/r1_ncu_tile_v20.summary.txt at n = 30)
-                "traffic": NCU_TRAFFIC_30Q if args.qubits == 30 else None, "peak_source": which,
-                "kernel": "tile_exec_kernel<double,12,4,256,2,3,FACT> (persistent, 148 CTAs x 640 threads)",
-                "algorithmic_bytes_per_launch": sweep_bytes,
-                "avg_launch_ms": avg_launch_ms,
-                "note": "achieved = 2*16*2^n bytes per tile-kernel launch / (CUDA-event time of the "
-                        "timed region / tile-kernel launches); the region holds only tile-kernel "
-                        "launches (pass descriptors travel as kernel parameters). Sustained figure: "
-                        "the region is steps x ~0.1 s of back-to-back launches under the 1 kW power cap "
-                        "(a single launch under ncu runs 13 % faster, profiles/r1_ncu_tile_v20.summary.txt).",
-            },
+            "config": cfg,
+            "hbm_gbs": achieved, "hbm_frac": roof["frac"], "hbm_gbs_step": hbm_step,
+            "schedule": {"sweeps_per_step": sweeps_per_step,
+                         "gates_per_s": len(circ) / (ms_dev / args.steps * 1e-3),
+                         "checks": {"norm": norm, "expval_Z_last": ez}},
+            "roofline": roof,
+            "parity": parity,
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": blob_bytes,
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
                     "call": "LightningKokkos_C128.apply(names, wires, inverses, params) from host "
@@ -389,8 +507,24 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if comm:
-            line["comm"] = comm
+        if world > 1:
+            nx = (comm.get("swaps", 0) - comm0.get("swaps", 0)) / args.steps
+            xb = (comm.get("swap_bytes_per_rank", 0) - comm0.get("swap_bytes_per_rank", 0)) / args.steps
+            x_ms = sum(xchg_ms) / trace_steps if xchg_ms else 0.0
+            x_gbs = xb / (x_ms * 1e-3) / 1e9 if x_ms > 0 else None
+            line["comm"] = dict(comm, exchanges_per_step=nx, bytes_per_rank_per_step=xb,
+                                exchange_ms_per_step=x_ms, pass_ms_per_step=sum(pass_ms) / trace_steps,
+                                traced_step_ms=step_ms_traced)
+            line["roofline_nvlink"] = {
+                "bound": "nvlink", "achieved": x_gbs, "peak": NVLINK_PEER_GBS, "unit": "GB/s per direction",
+                "frac": x_gbs / NVLINK_PEER_GBS if x_gbs else None,
+                "note": "bytes each rank sends per step / time of the exchange launches of the traced steps"}
+            # the step against max(HBM term, NVLink term) if the two overlapped perfectly
+            hbm_term = sweeps_per_step * sweep_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3
+            nvl_term = xb / (NVLINK_PEER_GBS * 1e9) * 1e3
+            line["roofline_step"] = {"hbm_ms": hbm_term, "nvlink_ms": nvl_term,
+                                     "frac_of_max": max(hbm_term, nvl_term) / (ms_dev / args.steps),
+                                     "frac_of_sum": (hbm_term + nvl_term) / (ms_dev / args.steps)}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if world == 1 and not args.no_adjoint:
@@ -410,8 +544,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--qubits", type=int, default=30, help="qubits per GPU (weak scaling)")
+    ap.add_argument("--ref-qubits", type=int, default=30, help="state size of the reference arm's sample")
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-adjoint", action="store_true", help="skip the config-3 adjoint Jacobian sample")
     args = ap.parse_args()
     if args.impl == "reference":

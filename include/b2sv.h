@@ -62,6 +62,9 @@ int b2sv_set_state_vector(b2sv_state *s, const uint64_t *indices, const double *
                           size_t n);                                     /* :503-521 */
 int b2sv_h2d(b2sv_state *s, const void *host, size_t length);            /* HostToDevice :1618 */
 int b2sv_d2h(const b2sv_state *s, void *host, size_t length);            /* DeviceToHost :1626 */
+/* sampled read (no reference counterpart; the reference copies the whole state, SV.hpp:1626):
+ * out_c128[k] = amplitude at global flat index indices[k]; collective on sharded states */
+int b2sv_get_amplitudes(const b2sv_state *s, const uint64_t *indices, size_t n, double *out_c128);
 int b2sv_num_qubits(const b2sv_state *s, int *n);
 int b2sv_data_length(const b2sv_state *s, uint64_t *len);                /* local length when sharded */
 int b2sv_device_ptr(const b2sv_state *s, void **ptr);                    /* getData :1603 */
@@ -83,6 +86,14 @@ int b2sv_set_fusion(b2sv_state *s, int fuse);
 /* counters since the last reset: full-state sweeps executed, kernels launched */
 int b2sv_get_stats(const b2sv_state *s, uint64_t *sweeps, uint64_t *launches);
 int b2sv_reset_stats(b2sv_state *s);
+/* algorithmic bytes the last b2sv_adjoint_jacobian / _vjp on this state moved over all its work
+ * vectors (tile passes 2S, read passes S per vector read, copies 2S, Hamiltonian application) */
+int b2sv_last_adjoint_traffic(const b2sv_state *s, uint64_t *bytes);
+/* measurement aid: CUDA events around every tile pass (kind 0), generic-matrix kernel (1) and
+ * global<->local exchange (2) launched on the state's stream between the two calls; trace_end
+ * synchronises and returns up to `cap` records (*n = how many there were). Times in ms. */
+int b2sv_trace_begin(b2sv_state *s);
+int b2sv_trace_end(b2sv_state *s, int *kinds, double *start_ms, double *dur_ms, int cap, int *n);
 /* developer aid: phase timers of the tile executor (all zero unless B2SV_TILE_PROF=1 is set in the
  * environment); reads and clears 16 cycle counters, see csrc/tile_kernel.cu g_tile_prof */
 int b2sv_debug_tile_prof(uint64_t *out16);

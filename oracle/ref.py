@@ -171,6 +171,13 @@ class RefStateVector:
         _chk(lib().ref_sv_d2h(self.h, out.ctypes.data_as(C.c_void_p), C.c_int64(out.size)))
         return out
 
+    def amplitudes(self, indices):
+        """Amplitudes at the given flat indices (sampled read, no full copy)."""
+        ia, ip, n = _wires(indices)
+        out = np.empty(n, dtype=np.complex128)
+        _chk(lib().ref_sv_get_amplitudes(self.h, ip, C.c_int64(n), out.ctypes.data_as(c_dp)))
+        return out
+
     # -- gates
     def apply(self, name, wires, inverse=False, params=()):
         _, wp, nw = _wires(wires)

@@ -231,6 +231,20 @@ int ref_sv_d2h(void *h, void *host, int64_t length) {
               sv_of<float>(h).DeviceToHost(static_cast<Kokkos::complex<float> *>(host), length);
           else sv_of<double>(h).DeviceToHost(static_cast<Kokkos::complex<double> *>(host), length))
 }
+// sampled read: out[2k], out[2k+1] = amplitude at indices[k] (parity checks on states too big to copy)
+int ref_sv_get_amplitudes(void *h, const int64_t *indices, int64_t n, double *out) {
+    GUARD(for (int64_t k = 0; k < n; k++) {
+        if (static_cast<Handle *>(h)->prec == 0) {
+            const auto v = sv_of<float>(h).getData().data()[indices[k]];
+            out[2 * k] = v.real();
+            out[2 * k + 1] = v.imag();
+        } else {
+            const auto v = sv_of<double>(h).getData().data()[indices[k]];
+            out[2 * k] = v.real();
+            out[2 * k + 1] = v.imag();
+        }
+    })
+}
 int ref_sv_apply(void *h, const char *name, const int64_t *wires, int nw, int inverse,
                  const double *params, int np) {
     GUARD(DISPATCH(h, apply_named, h, name, wires, nw, inverse, params, np))

@@ -48,6 +48,9 @@ PROTOTYPES = {
     "b2sv_set_state_vector": (C.c_int, [vp, u64p, dp, C.c_size_t]),
     "b2sv_h2d": (C.c_int, [vp, vp, C.c_size_t]),
     "b2sv_d2h": (C.c_int, [vp, vp, C.c_size_t]),
+    "b2sv_get_amplitudes": (C.c_int, [vp, u64p, C.c_size_t, dp]),
+    "b2sv_trace_begin": (C.c_int, [vp]),
+    "b2sv_trace_end": (C.c_int, [vp, ip, dp, dp, C.c_int, ip]),
     "b2sv_num_qubits": (C.c_int, [vp, ip]),
     "b2sv_data_length": (C.c_int, [vp, u64p]),
     "b2sv_device_ptr": (C.c_int, [vp, C.POINTER(vp)]),
@@ -64,6 +67,7 @@ PROTOTYPES = {
     "b2sv_last_upload_bytes": (C.c_int, [vp, u64p]),
     "b2sv_normalize_layout": (C.c_int, [vp]),
     "b2sv_reset_stats": (C.c_int, [vp]),
+    "b2sv_last_adjoint_traffic": (C.c_int, [vp, u64p]),
     "b2sv_debug_tile_prof": (C.c_int, [u64p]),
     "b2sv_ops_create": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), dp, ip, i64p, ip, ip,
                                   C.POINTER(dp), C.POINTER(vp)]),

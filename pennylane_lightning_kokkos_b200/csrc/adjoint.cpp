@@ -34,9 +34,27 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
     const size_t n_obs = obs.size(), tp_size = tp.size();
     for (size_t i = 0; i < n_obs * tp_size; i++)
         jac[i] = 0.0;
-    for (const GateOp &op : ops.ops) // ADJ.hpp:444-446 (checked up front: nothing is launched)
-        B2_ABORT_IF(op.params.size() > 1,
-                    "The operation is not supported using the adjoint differentiation method");
+    { // ADJ.hpp:444-453: the reference checks inside the reverse loop, so ops in front of the point
+      // where the trainable parameters run out are never looked at. Replay the loop's bookkeeping
+      // on the host first: exactly the ops the loop visits are validated, nothing is launched
+      // when one fails.
+        auto it = tp.rbegin();
+        long cur = static_cast<long>(ops.num_par_ops) - 1;
+        for (size_t i = ops.ops.size(); i-- > 0;) {
+            const GateOp &op = ops.ops[i];
+            B2_ABORT_IF(op.params.size() > 1,
+                        "The operation is not supported using the adjoint differentiation method");
+            if (op.name == "StatePrep" || op.name == "BasisState")
+                continue;
+            if (it == tp.rend())
+                break;
+            if (!op.params.empty()) {
+                if (cur == static_cast<long>(*it))
+                    ++it;
+                cur--;
+            }
+        }
+    }
     if (n_obs == 0)
         return;
     CUDA_CHECK(cudaSetDevice(sv.device()));
@@ -330,6 +348,9 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
     CUDA_CHECK(cudaStreamSynchronize(st));
     for (size_t i = 0; i < n_obs * tp_size; i++)
         jac[i] += jac_host[i];
+    sv.last_adjoint_bytes = lambda->bytes_moved + (mu ? mu->bytes_moved : 0);
+    for (const auto &h : H)
+        sv.last_adjoint_bytes += h->bytes_moved;
     CUDA_CHECK(cudaFreeAsync(d_jac, st));
     if (d_tr_scratch) {
         CUDA_CHECK(cudaFreeAsync(d_tr_scratch, st));

@@ -57,6 +57,18 @@ const State &st(const b2sv_state *s) {
     B2_ABORT_IF(!s || !s->s, "null state handle");
     return *s->s;
 }
+// number of complex entries of a matrix on nw wires; nw is bounded by what lower_matrix accepts, so a
+// bogus count can neither shift out of range nor make us read far beyond the caller's buffer
+constexpr int kMaxMatrixWires = 10;
+size_t matrix_len(int nw) {
+    B2_ABORT_IF(nw < 1 || nw > kMaxMatrixWires,
+                "matrix operations support between 1 and 10 wires");
+    return size_t(1) << (2 * nw);
+}
+std::string name_str(const char *name) {
+    B2_ABORT_IF(!name, "null operation name");
+    return std::string(name);
+}
 void copy_str(const std::string &s, char *buf, size_t cap) {
     B2_ABORT_IF(!buf || cap == 0, "invalid string buffer");
     const size_t n = std::min(cap - 1, s.size());
@@ -159,6 +171,30 @@ int b2sv_h2d(b2sv_state *s, const void *host, size_t length) {
 int b2sv_d2h(const b2sv_state *s, void *host, size_t length) {
     return guard([&] { st(s).d2h(host, length); });
 }
+int b2sv_get_amplitudes(const b2sv_state *s, const uint64_t *indices, size_t n, double *out) {
+    return guard([&] {
+        B2_ABORT_IF(n > 0 && (!indices || !out), "null buffer");
+        st(s).get_amplitudes(indices, n, reinterpret_cast<cplx *>(out));
+    });
+}
+int b2sv_trace_begin(b2sv_state *s) {
+    return guard([&] { st(s).trace_begin(); });
+}
+int b2sv_trace_end(b2sv_state *s, int *kinds, double *start_ms, double *dur_ms, int cap, int *n) {
+    return guard([&] {
+        B2_ABORT_IF(!n, "null output");
+        const auto recs = st(s).trace_end();
+        *n = static_cast<int>(recs.size());
+        for (int i = 0; i < cap && i < *n; i++) {
+            if (kinds)
+                kinds[i] = recs[i].kind;
+            if (start_ms)
+                start_ms[i] = recs[i].start_ms;
+            if (dur_ms)
+                dur_ms[i] = recs[i].dur_ms;
+        }
+    });
+}
 int b2sv_num_qubits(const b2sv_state *s, int *n) {
     return guard([&] { *n = st(s).num_qubits(); });
 }
@@ -179,9 +215,10 @@ int b2sv_apply(b2sv_state *s, const char *name, const int64_t *wires, int nw, in
                const double *params, int np) {
     return guard([&] {
         GateOp op;
-        op.name = name;
+        op.name = name_str(name);
         op.wires = wires_vec(wires, nw);
         op.inverse = inverse != 0;
+        B2_ABORT_IF(np < 0 || (np > 0 && !params), "invalid params argument");
         if (np > 0)
             op.params.assign(params, params + np);
         B2_ABORT_IF(op.name != "Identity" && !is_named_gate(op.name),
@@ -196,7 +233,7 @@ int b2sv_apply_matrix(b2sv_state *s, const int64_t *wires, int nw, int inverse,
         op.name = "__matrix__";
         op.wires = wires_vec(wires, nw);
         op.inverse = inverse != 0;
-        op.matrix = cplx_vec(matrix, size_t(1) << (2 * nw));
+        op.matrix = cplx_vec(matrix, matrix_len(nw));
         st(s).apply_gate(op);
     });
 }
@@ -209,7 +246,7 @@ int b2sv_apply_ops(b2sv_state *s, const b2sv_ops *ops, int adjoint) {
 int b2sv_apply_generator(b2sv_state *s, const char *name, const int64_t *wires, int nw, int adj,
                          double *scale) {
     (void)adj; // ignored by every generator of the reference
-    return guard([&] { *scale = st(s).apply_generator(name, wires_vec(wires, nw)); });
+    return guard([&] { *scale = st(s).apply_generator(name_str(name), wires_vec(wires, nw)); });
 }
 int b2sv_set_fusion(b2sv_state *s, int fuse) {
     return guard([&] { st(s).set_fusion(fuse != 0); });
@@ -220,6 +257,12 @@ int b2sv_get_stats(const b2sv_state *s, uint64_t *sweeps, uint64_t *launches) {
             *sweeps = st(s).sweeps;
         if (launches)
             *launches = st(s).launches + st(s).reduce_launches;
+    });
+}
+int b2sv_last_adjoint_traffic(const b2sv_state *s, uint64_t *bytes) {
+    return guard([&] {
+        B2_ABORT_IF(!bytes, "null output");
+        *bytes = st(s).last_adjoint_bytes;
     });
 }
 int b2sv_reset_stats(b2sv_state *s) {
@@ -317,14 +360,18 @@ int b2sv_ops_create(int nops, const char *const *names, const double *params, co
         size_t po = 0, wo = 0;
         for (int i = 0; i < nops; i++) {
             GateOp op;
-            op.name = names[i];
+            B2_ABORT_IF(!names || !nparams || !nwires || !inverses, "null argument");
+            op.name = name_str(names[i]);
+            B2_ABORT_IF(nparams[i] < 0 || nwires[i] < 0, "negative parameter or wire count");
+            B2_ABORT_IF((nparams[i] > 0 && !params) || (nwires[i] > 0 && !wires), "null argument");
             op.params.assign(params + po, params + po + nparams[i]);
             po += nparams[i];
             op.wires.assign(wires + wo, wires + wo + nwires[i]);
             wo += nwires[i];
             op.inverse = inverses[i] != 0;
-            if (matrices && matrices[i])
-                op.matrix = cplx_vec(matrices[i], size_t(1) << (2 * nwires[i]));
+            // named gates never use their matrix (reference StateVectorKokkos.hpp:585-600)
+            if (matrices && matrices[i] && op.name != "Identity" && !is_named_gate(op.name))
+                op.matrix = cplx_vec(matrices[i], matrix_len(nwires[i]));
             if (!op.params.empty())
                 h->d.num_par_ops++;
             h->d.ops.push_back(std::move(op));
@@ -347,12 +394,12 @@ int b2sv_ops_size(const b2sv_ops *ops, int *nops, int *n_par_ops) {
 
 int b2sv_expval_named(const b2sv_state *s, const char *name, const int64_t *wires, int nw,
                       double *out) {
-    return guard([&] { *out = st(s).expval_named(name, wires_vec(wires, nw)); });
+    return guard([&] { *out = st(s).expval_named(name_str(name), wires_vec(wires, nw)); });
 }
 int b2sv_expval_matrix(const b2sv_state *s, const int64_t *wires, int nw, const double *matrix,
                        double *out) {
     return guard([&] {
-        *out = st(s).expval_matrix(wires_vec(wires, nw), cplx_vec(matrix, size_t(1) << (2 * nw)));
+        *out = st(s).expval_matrix(wires_vec(wires, nw), cplx_vec(matrix, matrix_len(nw)));
     });
 }
 int b2sv_expval_csr(const b2sv_state *s, const double *data, const uint64_t *indices,
@@ -407,12 +454,12 @@ int b2sv_axpy(double ar, double ai, const b2sv_state *x, b2sv_state *y) {
 }
 
 int b2sv_obs_named(const char *name, const int64_t *wires, int nw, b2sv_obs **out) {
-    return guard([&] { *out = new b2sv_obs{make_named_obs(name, wires_vec(wires, nw))}; });
+    return guard([&] { *out = new b2sv_obs{make_named_obs(name_str(name), wires_vec(wires, nw))}; });
 }
 int b2sv_obs_hermitian(const double *matrix, const int64_t *wires, int nw, b2sv_obs **out) {
     return guard([&] {
         *out = new b2sv_obs{
-            make_hermitian_obs(cplx_vec(matrix, size_t(1) << (2 * nw)), wires_vec(wires, nw))};
+            make_hermitian_obs(cplx_vec(matrix, matrix_len(nw)), wires_vec(wires, nw))};
     });
 }
 int b2sv_obs_tensor(b2sv_obs *const *obs, int n, b2sv_obs **out) {

@@ -45,4 +45,25 @@ struct Error : public std::runtime_error {
 
 inline uint64_t bit(int p) { return uint64_t(1) << p; }
 
+// Per-device one-time setup (function attributes are per device, a process may hold states on
+// several): true the first time it is called for the current device with this `mask`.
+inline bool first_use_on_device(uint64_t &mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t b = uint64_t(1) << (dev & 63);
+    if (mask & b)
+        return false;
+    mask |= b;
+    return true;
+}
+inline int sm_count_current_device() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &n = cached[dev & 63];
+    if (!n)
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+
 } // namespace b2sv

@@ -118,6 +118,21 @@ __global__ void k_scatter(amp_t *__restrict__ state, const uint64_t *__restrict_
         state[idx[i]] = v;
     }
 }
+// out[k] = state[idx[k]] when the index belongs to this shard (idx >> n_local == rank), else 0
+template <typename amp_t>
+__global__ void k_gather(const amp_t *__restrict__ state, const uint64_t *__restrict__ idx, size_t n,
+                         int n_local, uint64_t rank, double2 *__restrict__ out) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint64_t g = idx[i];
+        double2 v = make_double2(0.0, 0.0);
+        if ((n_local >= 64 ? 0 : (g >> n_local)) == rank) {
+            const amp_t a = state[g & ((uint64_t(1) << n_local) - 1)];
+            v = make_double2(a.x, a.y);
+        }
+        out[i] = v;
+    }
+}
 template <typename amp_t, typename real>
 __global__ void k_axpy(real ar, real ai, const amp_t *__restrict__ x, amp_t *__restrict__ y,
                        uint64_t len) {
@@ -842,6 +857,15 @@ void launch_scatter(int dtype, void *state, const uint64_t *d_idx, const double2
                    (k_scatter<float2><<<grid, 256, 0, st>>>(static_cast<float2 *>(state), d_idx, d_val, n)),
                    (k_scatter<double2><<<grid, 256, 0, st>>>(static_cast<double2 *>(state), d_idx, d_val, n)));
 }
+void launch_gather(int dtype, const void *state, const uint64_t *d_idx, size_t n, int n_local,
+                   uint64_t rank, double2 *d_out, cudaStream_t st) {
+    if (n == 0)
+        return;
+    const int grid = static_cast<int>((n + 255) / 256);
+    DISPATCH_DTYPE(dtype,
+                   (k_gather<float2><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), d_idx, n, n_local, rank, d_out)),
+                   (k_gather<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), d_idx, n, n_local, rank, d_out)));
+}
 void launch_axpy(int dtype, double ar, double ai, const void *x, void *y, uint64_t len,
                  cudaStream_t st) {
     const int grid = reduce_grid(len);
@@ -1024,17 +1048,14 @@ void launch_transition_tile(int dtype, const void *bra, const void *ket, int n_b
             if (tt.tile_pos[k] == h_bits[j])
                 tt.wire_tpos[j] = k;
     const uint64_t n_tiles = uint64_t(1) << (n_bits - tt.n_tile);
-    int dev = 0, sms = 148;
-    CUDA_CHECK(cudaGetDevice(&dev));
-    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = sm_count_current_device();
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(sms)));
     const bool f32 = dtype != 1;
     const size_t smem = (f32 ? sizeof(float2) : sizeof(double2)) * 4 * (size_t(1) << tt.n_tile); // 2 stages x 2 vectors
-    static bool configured = false;
-    if (!configured) {
+    static uint64_t configured = 0; // one bit per device
+    if (first_use_on_device(configured)) {
         CUDA_CHECK(cudaFuncSetAttribute(k_transition_tile<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
         CUDA_CHECK(cudaFuncSetAttribute(k_transition_tile<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
-        configured = true;
     }
     if (grid < static_cast<unsigned>(kReduceBlocks)) // finalize sums kReduceBlocks rows
         CUDA_CHECK(cudaMemsetAsync(d_partials, 0, sizeof(double) * kReduceBlocks * kTransitionVals, st));

@@ -22,6 +22,9 @@ void tile_prof_read(unsigned long long out[16]);
 void launch_set_basis(int dtype, void *state, uint64_t len, uint64_t index, cudaStream_t st);
 void launch_scatter(int dtype, void *state, const uint64_t *d_idx, const double2 *d_val, size_t n,
                     cudaStream_t st);
+// sampled read: d_out[k] = state[d_idx[k]] as complex128 (zero where the index is another rank's)
+void launch_gather(int dtype, const void *state, const uint64_t *d_idx, size_t n, int n_local,
+                   uint64_t rank, double2 *d_out, cudaStream_t st);
 void launch_axpy(int dtype, double ar, double ai, const void *x, void *y, uint64_t len,
                  cudaStream_t st);
 // generic k-qubit matrix (row-major, device, complex128), bits[0] = MSB of the local index

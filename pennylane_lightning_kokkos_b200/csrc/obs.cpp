@@ -130,6 +130,7 @@ class TensorProdObs final : public Obs {
             std::vector<std::pair<double, PauliWord>> one;
             if (!ob->pauli_terms(n, 1.0, one) || one.size() != 1)
                 return false;
+            coef *= one[0].first;     // a factor may be a one-term Hamiltonian with its own weight
             acc.x |= one[0].second.x; // wires are disjoint
             acc.z |= one[0].second.z;
             acc.ny += one[0].second.ny;
@@ -214,6 +215,7 @@ class SparseHamiltonianObs final : public Obs {
             CUDA_CHECK(cudaMemsetAsync(y, 0, sv.alloc_length() * sv.amp_bytes(), sv.stream()));
         launch_csr_spmv(sv.dtype(), sv.data(), y, m.data, m.ind, m.ptr, m.nrows, m.lanes, sv.stream());
         sv.launches++;
+        sv.bytes_moved += m.nnz * 20 + 2 * sv.state_bytes();
         sv.swap_buffer(y);
         sv.release_scratch(y);
     }
@@ -252,6 +254,12 @@ void pauli_sum_into(const State &sv, const void *in, void *out,
                                cudaMemcpyHostToDevice, sv.stream()));
     launch_pauli_sum_apply(sv.dtype(), in, out, sv.local_length(), d_terms,
                            static_cast<int>(h.size()), sv.stream());
+    { // one read of the input per distinct x mask (the others hit the same lines) + one write
+        std::set<uint64_t> xs;
+        for (const PauliTerm &t : h)
+            xs.insert(t.x);
+        sv.bytes_moved += (xs.size() + 1) * sv.state_bytes();
+    }
     CUDA_CHECK(cudaFreeAsync(d_terms, sv.stream()));
     CUDA_CHECK(cudaStreamSynchronize(sv.stream())); // `h` goes out of scope
 }

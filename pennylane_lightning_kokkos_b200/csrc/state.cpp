@@ -225,9 +225,17 @@ State::~State() {
     cudaSetDevice(device_);
     if (stream_)
         cudaStreamSynchronize(stream_);
+    for (const TraceRec &r : trace_) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    if (trace_t0_)
+        cudaEventDestroy(trace_t0_);
     if (comm_) {
-        comm_barrier(comm_.get(), stream_); // nobody is still swapping through this shard
-        cudaStreamSynchronize(stream_);
+        // Not collective (destruction order is up to the garbage collector and to exceptions, and
+        // need not be the same on every rank): every exchange ends with a barrier that this rank's
+        // stream has passed, so once the stream is idle no peer is still reading or writing this
+        // shard, and peers only ever touch it inside an exchange all ranks take part in.
         comm_unmap_peers(comm_.get(), peers_);
     }
     comm_.reset();
@@ -311,6 +319,72 @@ void State::d2h(void *host, size_t length) const {
     CUDA_CHECK(cudaMemcpyAsync(host, d_state_, length * amp_bytes(), cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
+void State::get_amplitudes(const uint64_t *indices, size_t n, cplx *out) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    if (n == 0)
+        return;
+    for (size_t i = 0; i < n; i++)
+        B2_ABORT_IF(n_ < 64 && indices[i] >= (uint64_t(1) << n_), "state index out of range");
+    normalize_layout();
+    uint64_t *d_idx;
+    double2 *d_val;
+    CUDA_CHECK(cudaMallocAsync(&d_idx, sizeof(uint64_t) * n, stream_));
+    CUDA_CHECK(cudaMallocAsync(&d_val, sizeof(double2) * n, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(d_idx, indices, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, stream_));
+    launch_gather(dtype_, d_state_, d_idx, n, n_local_, static_cast<uint64_t>(rank_), d_val, stream_);
+    if (comm_)
+        comm_allreduce_sum(comm_.get(), reinterpret_cast<double *>(d_val), static_cast<int>(2 * n), stream_);
+    CUDA_CHECK(cudaMemcpyAsync(out, d_val, sizeof(double2) * n, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaFreeAsync(d_idx, stream_));
+    CUDA_CHECK(cudaFreeAsync(d_val, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+// ---- tracing ---------------------------------------------------------------------------------------
+State::TraceScope::TraceScope(const State &state, int k, cudaStream_t stream)
+    : s(state), kind(k), st(stream ? stream : state.stream_) {
+    if (!s.tracing_)
+        return;
+    cudaEventCreate(&e0);
+    cudaEventRecord(e0, st);
+}
+State::TraceScope::~TraceScope() {
+    if (!e0)
+        return;
+    cudaEvent_t e1;
+    cudaEventCreate(&e1);
+    cudaEventRecord(e1, st);
+    s.trace_.push_back({kind, e0, e1});
+}
+void State::trace_begin() {
+    CUDA_CHECK(cudaSetDevice(device_));
+    for (const TraceRec &r : trace_) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    trace_.clear();
+    if (!trace_t0_)
+        CUDA_CHECK(cudaEventCreate(&trace_t0_));
+    CUDA_CHECK(cudaEventRecord(trace_t0_, stream_));
+    tracing_ = true;
+}
+std::vector<State::TraceOut> State::trace_end() {
+    CUDA_CHECK(cudaSetDevice(device_));
+    tracing_ = false;
+    CUDA_CHECK(cudaDeviceSynchronize());
+    std::vector<TraceOut> out;
+    for (const TraceRec &r : trace_) {
+        float a = 0.f, d = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&a, trace_t0_, r.e0));
+        CUDA_CHECK(cudaEventElapsedTime(&d, r.e0, r.e1));
+        out.push_back({r.kind, a, d});
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    trace_.clear();
+    return out;
+}
+
 void State::copy_from(const State &o) {
     CUDA_CHECK(cudaSetDevice(device_));
     B2_ABORT_IF(o.n_ != n_ || o.dtype_ != dtype_ || o.world_ != world_ || o.device_ != device_,
@@ -320,6 +394,7 @@ void State::copy_from(const State &o) {
                                cudaMemcpyDeviceToDevice, stream_));
     order_after(o.stream_, stream_);
     l2p_ = o.l2p_;
+    bytes_moved += 2 * state_bytes();
 }
 std::unique_ptr<State> State::clone() const {
     // sharded: collective (every rank clones in the same order); shares communicator and stream
@@ -392,7 +467,10 @@ Prim State::to_physical(const Prim &p) const {
 }
 void State::swap_phys(int gpos, int lpos) const {
     B2_ASSERT(comm_ && gpos >= n_local_ && lpos < n_local_);
-    comm_swap_bits(comm_.get(), d_state_, peers_, dtype_, n_local_, gpos - n_local_, lpos, stream_);
+    {
+        TraceScope ts(*this, 2);
+        comm_swap_bits(comm_.get(), d_state_, peers_, dtype_, n_local_, gpos - n_local_, lpos, stream_);
+    }
     int qa = -1, qb = -1;
     for (int q = 0; q < n_; q++) {
         if (l2p_[q] == gpos)
@@ -655,7 +733,10 @@ void State::upload_and_run(const std::vector<Pass> &passes) {
             const size_t bytes = sizeof(double2) * ps.matk.mat.size();
             CUDA_CHECK(cudaMallocAsync(&d_mat, bytes, stream_));
             CUDA_CHECK(cudaMemcpyAsync(d_mat, ps.matk.mat.data(), bytes, cudaMemcpyHostToDevice, stream_));
-            launch_matk(dtype_, d_state_, n_eff_, d_mat, ps.matk.bits.data(), k, stream_);
+            {
+                TraceScope ts(*this, 1);
+                launch_matk(dtype_, d_state_, n_eff_, d_mat, ps.matk.bits.data(), k, stream_);
+            }
             CUDA_CHECK(cudaFreeAsync(d_mat, stream_));
             CUDA_CHECK(cudaStreamSynchronize(stream_)); // the host matrix lives in `passes`
             last_upload_bytes_ += bytes;
@@ -666,12 +747,16 @@ void State::upload_and_run(const std::vector<Pass> &passes) {
             B2_ASSERT(ps.dense.size() <= static_cast<size_t>(kMaxDense));
             if (!ps.dense.empty())
                 std::memcpy(params->dense, ps.dense.data(), sizeof(DevDense) * ps.dense.size());
-            launch_tile_pass(dtype_, d_state_, *params, n_eff_, rank_bits, stream_);
+            {
+                TraceScope ts(*this, 0);
+                launch_tile_pass(dtype_, d_state_, *params, n_eff_, rank_bits, stream_);
+            }
             last_upload_bytes_ += sizeof(DevPassHeader) + sizeof(DevOp) * ps.ops.size() +
                                   sizeof(DevDense) * ps.dense.size();
         }
         sweeps++;
         launches++;
+        bytes_moved += 2 * state_bytes();
     }
 }
 
@@ -689,6 +774,7 @@ void State::finish_reduce(int nv, double *out) const {
 double State::norm2() const {
     CUDA_CHECK(cudaSetDevice(device_));
     launch_norm2(dtype_, d_state_, local_length(), d_partials_, stream_);
+    bytes_moved += state_bytes();
     double r;
     finish_reduce(1, &r);
     return r;
@@ -696,6 +782,7 @@ double State::norm2() const {
 void State::inner_product_buf(const void *x, const void *y, double *re, double *im) const {
     CUDA_CHECK(cudaSetDevice(device_));
     launch_dot(dtype_, x, y, local_length(), d_partials_, stream_);
+    bytes_moved += 2 * state_bytes();
     double r[2];
     finish_reduce(2, r);
     if (re)
@@ -832,6 +919,7 @@ void State::pauli_dot_im_to(const State &bra, uint64_t x, uint64_t z, cplx ph, d
     launch_finalize_scaled(d_partials_, kReduceBlocks, 2, 1, factor, d_dst, stream_);
     order_after(bra.stream_, stream_);
     reduce_launches += 2;
+    bytes_moved += 2 * state_bytes();
 }
 void State::transition_1q_to(const State &bra, const int *bits, int nb, double *d_scratch,
                              double *d_dst) const {
@@ -847,6 +935,7 @@ void State::transition_1q_to(const State &bra, const int *bits, int nb, double *
     launch_finalize(d_scratch, kReduceBlocks, kTransitionVals, d_dst, stream_);
     order_after(bra.stream_, stream_);
     reduce_launches += 2;
+    bytes_moved += 2 * state_bytes();
 }
 void State::dot_im_to(const State &bra, double factor, double *d_dst) const {
     CUDA_CHECK(cudaSetDevice(device_));
@@ -861,6 +950,7 @@ void State::dot_im_to(const State &bra, double factor, double *d_dst) const {
     launch_finalize_scaled(d_partials_, kReduceBlocks, 2, 1, factor, d_dst, stream_);
     order_after(bra.stream_, stream_);
     reduce_launches += 2;
+    bytes_moved += 2 * state_bytes();
 }
 void State::allreduce_device(double *d_buf, int n) const {
     if (comm_)
@@ -875,6 +965,7 @@ void State::axpy(cplx alpha, const State &x) {
     order_after(stream_, x.stream_);
     launch_axpy(dtype_, alpha.real(), alpha.imag(), x.d_state_, d_state_, local_length(), stream_);
     launches++;
+    bytes_moved += 3 * state_bytes();
     order_after(x.stream_, stream_);
 }
 

@@ -66,6 +66,8 @@ class State {
     void set_state_vector(const uint64_t *indices, const cplx *values, size_t n);
     void h2d(const void *host, size_t length);
     void d2h(void *host, size_t length) const;
+    // amplitudes at global flat indices, as complex128 (sampled read; sharded: all-reduced)
+    void get_amplitudes(const uint64_t *indices, size_t n, cplx *out) const;
     void copy_from(const State &other);
     std::unique_ptr<State> clone() const;
     void swap_buffer(void *&other_buffer); // exchange the device buffer with a scratch buffer
@@ -123,9 +125,23 @@ class State {
     void probs(const std::vector<int64_t> &wires, double *out) const;
     void generate_samples(size_t shots, uint64_t seed, uint64_t *out) const;
 
+    // ---- tracing: CUDA events around every pass / exchange launched on this state's stream
+    struct TraceOut {
+        int kind;        // 0 tile pass, 1 generic matrix kernel, 2 global<->local exchange
+        double start_ms; // relative to trace_begin
+        double dur_ms;
+    };
+    void trace_begin();
+    std::vector<TraceOut> trace_end();
+
     // ---- bookkeeping
     uint64_t sweeps = 0, launches = 0;
     mutable uint64_t reduce_launches = 0;
+    // algorithmic bytes the kernels launched on this state have moved (passes 2S, read passes S per
+    // vector, copies 2S, ...) and, on the state an adjoint Jacobian was taken of, the bytes that call
+    // moved over all its work vectors
+    mutable uint64_t bytes_moved = 0, last_adjoint_bytes = 0;
+    uint64_t state_bytes() const { return local_length() * amp_bytes(); }
 
     int tile_bits() const { return B_; }
     size_t last_upload_bytes() const { return last_upload_bytes_; }
@@ -140,6 +156,22 @@ class State {
     void swap_phys(int gpos, int lpos) const;             // rank bit position <-> local position
     void reset_layout() const;
     void init_common(const void *nccl_id);
+
+    struct TraceRec {
+        int kind;
+        cudaEvent_t e0, e1;
+    };
+    struct TraceScope { // records a pair of events around the launches made while it is alive
+        const State &s;
+        cudaEvent_t e0 = nullptr;
+        int kind;
+        cudaStream_t st;
+        TraceScope(const State &state, int k, cudaStream_t stream = nullptr);
+        ~TraceScope();
+    };
+    mutable bool tracing_ = false;
+    mutable cudaEvent_t trace_t0_ = nullptr;
+    mutable std::vector<TraceRec> trace_;
 
     int n_, n_local_, n_eff_, dtype_, device_;
     int rank_, world_, gbits_;

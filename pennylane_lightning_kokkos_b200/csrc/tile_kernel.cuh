@@ -824,15 +824,7 @@ template <typename real, int B, int NB> constexpr size_t tile_smem_bytes() {
     return NB * sizeof(typename AmpT<real>::type) * (size_t(1) << B) +
            sizeof(DevOp) * kMaxOpsPerPass + sizeof(uint64_t) * (size_t(1) << (B - kMinLow));
 }
-int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        CUDA_CHECK(cudaGetDevice(&dev));
-        CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    }
-    return n;
-}
+int sm_count() { return sm_count_current_device(); }
 int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -848,12 +840,10 @@ void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_
     using amp_t = typename AmpT<real>::type;
     auto kern = tile_exec_kernel<real, B, R, GT, NG, NB, FACT, INTERP, DENSEK, PROF>;
     constexpr size_t smem = tile_smem_bytes<real, B, NB>();
-    static bool configured = false;
-    if (!configured) {
+    static uint64_t configured = 0; // one bit per device: the attribute is per device
+    if (first_use_on_device(configured))
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-        configured = true;
-    }
     const uint32_t n_tiles = 1u << (n_eff - B);
     // one persistent CTA per SM; with fewer than 2 tiles per SM spread them one per CTA
     const unsigned grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(sm_count()));

@@ -123,6 +123,10 @@ class _ObservableBase:
         check(lib.b2sv_obs_wires(self._h, arr.ctypes.data_as(_lib.i64p), 64, C.byref(n)))
         return [int(x) for x in arr[: n.value]]
 
+    def apply_in_place(self, sv):
+        """ObservableKokkos::applyInPlace (ObservablesKokkos.hpp:41): sv <- O sv."""
+        check(lib.b2sv_obs_apply(self._h, sv._h))
+
     def __eq__(self, other):  # Bindings.cpp:608-619: same type and same description
         return type(self) is type(other) and self._key() == other._key()
 
@@ -444,6 +448,27 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
                                             out.ctypes.data_as(_lib.u64p)))
             return out.reshape(int(num_shots), int(num_wires))
 
+        # -- linear algebra (util/LinearAlgebraKokkos.hpp:30-61,155-236) and copies (SV.hpp:550-554,1596)
+        def clone(self):
+            new = type(self).__new__(type(self))
+            new._h = C.c_void_p()
+            check(lib.b2sv_clone(self._h, C.byref(new._h)))
+            return new
+
+        def updateData(self, other):
+            check(lib.b2sv_copy(self._h, other._h))
+
+        def inner_product(self, other) -> complex:
+            """<self|other>"""
+            re, im = C.c_double(), C.c_double()
+            check(lib.b2sv_inner_product(self._h, other._h, C.byref(re), C.byref(im)))
+            return complex(re.value, im.value)
+
+        def axpy(self, alpha, x):
+            """self += alpha * x"""
+            a = complex(alpha)
+            check(lib.b2sv_axpy(a.real, a.imag, x._h, self._h))
+
         # -- extras used by tests / bench
         def set_fusion(self, fuse: bool):
             check(lib.b2sv_set_fusion(self._h, int(bool(fuse))))
@@ -452,6 +477,11 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
             s, l = C.c_uint64(), C.c_uint64()
             check(lib.b2sv_get_stats(self._h, C.byref(s), C.byref(l)))
             return {"sweeps": s.value, "launches": l.value}
+
+        def last_adjoint_traffic(self):
+            b = C.c_uint64()
+            check(lib.b2sv_last_adjoint_traffic(self._h, C.byref(b)))
+            return b.value
 
         def reset_stats(self):
             check(lib.b2sv_reset_stats(self._h))
@@ -466,6 +496,28 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
             b = C.c_uint64()
             check(lib.b2sv_last_upload_bytes(self._h, C.byref(b)))
             return b.value
+
+        def amplitudes(self, indices):
+            """Sampled read: complex128 amplitudes at the given global flat indices."""
+            _, ip_, n = _u64(indices)
+            out = np.zeros(n, dtype=np.complex128)
+            check(lib.b2sv_get_amplitudes(self._h, ip_, n, out.ctypes.data_as(_lib.dp)))
+            return out
+
+        def trace_begin(self):
+            check(lib.b2sv_trace_begin(self._h))
+
+        def trace_end(self, cap=65536):
+            """[(kind, start_ms, dur_ms)]: kind 0 tile pass, 1 matrix kernel, 2 exchange."""
+            kinds = np.zeros(cap, dtype=np.int32)
+            t0 = np.zeros(cap, dtype=np.float64)
+            dt = np.zeros(cap, dtype=np.float64)
+            n = C.c_int(0)
+            check(lib.b2sv_trace_end(self._h, kinds.ctypes.data_as(_lib.ip),
+                                     t0.ctypes.data_as(_lib.dp), dt.ctypes.data_as(_lib.dp), cap,
+                                     C.byref(n)))
+            m = min(n.value, cap)
+            return [(int(kinds[i]), float(t0[i]), float(dt[i])) for i in range(m)]
 
         def normalize_layout(self):
             check(lib.b2sv_normalize_layout(self._h))
