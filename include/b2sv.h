@@ -105,6 +105,8 @@ int b2sv_last_upload_bytes(const b2sv_state *s, uint64_t *bytes);
 /* sharded states keep swapped-in qubits where they are (lazy layout); this restores the identity
  * layout (wire w <-> bit n-1-w, top bits = rank). d2h does it implicitly. */
 int b2sv_normalize_layout(b2sv_state *s);
+/* current logical -> physical index-bit map (identity for single-GPU states); *n = number of bits */
+int b2sv_layout(const b2sv_state *s, int *l2p, int cap, int *n);
 
 /* ---- op lists (OpsData ADJ.hpp:40-56; create_ops_list Bindings.cpp:772-805) ---------- */
 /* params / wires are concatenated; nparams[i] / nwires[i] give the split. matrices may be NULL;
@@ -121,6 +123,12 @@ int b2sv_ops_size(const b2sv_ops *ops, int *nops, int *n_par_ops);
 int b2sv_plan_ops(const b2sv_ops *ops, int num_qubits, int dtype, uint64_t *passes,
                   uint64_t *rounds, uint64_t *arithmetic_ops, uint64_t *absorbed_perms,
                   uint64_t *fused_stores);
+
+/* Host-only: the same for a state sharded over `world` ranks (no reference counterpart): runs of
+ * shard-local work and global<->local exchanges. stats5: runs, exchanges, tile passes, exchanged bits,
+ * bytes each rank sends (at 16 B per amplitude). buf (may be NULL) receives the plan as text. */
+int b2sv_plan_sharded(const b2sv_ops *ops, int num_qubits, int world, int dtype, uint64_t *stats5,
+                      char *buf, size_t cap);
 
 /* ---- measurements (MeasuresKokkos.hpp) ----------------------------------------------- */
 int b2sv_expval_named(const b2sv_state *s, const char *name, const int64_t *wires, int nw,

@@ -63,9 +63,11 @@ PROTOTYPES = {
     "b2sv_set_fusion": (C.c_int, [vp, C.c_int]),
     "b2sv_get_stats": (C.c_int, [vp, u64p, u64p]),
     "b2sv_plan_ops": (C.c_int, [vp, C.c_int, C.c_int, u64p, u64p, u64p, u64p, u64p]),
+    "b2sv_plan_sharded": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, u64p, C.c_char_p, C.c_size_t]),
     "b2sv_comm_stats": (C.c_int, [vp, u64p, u64p, ip]),
     "b2sv_last_upload_bytes": (C.c_int, [vp, u64p]),
     "b2sv_normalize_layout": (C.c_int, [vp]),
+    "b2sv_layout": (C.c_int, [vp, ip, C.c_int, ip]),
     "b2sv_reset_stats": (C.c_int, [vp]),
     "b2sv_last_adjoint_traffic": (C.c_int, [vp, u64p]),
     "b2sv_debug_tile_prof": (C.c_int, [u64p]),

@@ -4,7 +4,10 @@
 #include "adjoint.hpp"
 #include "comm.hpp"
 #include "obs.hpp"
+#include "shard_plan.hpp"
 #include "state.hpp"
+
+#include <iomanip>
 
 #include <cstring>
 
@@ -297,6 +300,14 @@ int b2sv_comm_stats(const b2sv_state *s, uint64_t *swaps, uint64_t *swap_bytes, 
 int b2sv_last_upload_bytes(const b2sv_state *s, uint64_t *bytes) {
     return guard([&] { *bytes = st(s).last_upload_bytes(); });
 }
+int b2sv_layout(const b2sv_state *s, int *l2p, int cap, int *n) {
+    return guard([&] {
+        B2_ABORT_IF(!n, "null output");
+        *n = st(s).num_qubits();
+        for (int q = 0; q < *n && q < cap; q++)
+            l2p[q] = st(s).phys_bit(q);
+    });
+}
 int b2sv_normalize_layout(b2sv_state *s) {
     return guard([&] { st(s).normalize_layout(); });
 }
@@ -348,6 +359,99 @@ int b2sv_plan_ops(const b2sv_ops *ops, int num_qubits, int dtype, uint64_t *pass
             *absorbed_perms = nabs;
         if (fused_stores)
             *fused_stores = nf;
+    });
+}
+
+// Host-only: how `ops` would run on a state sharded over `world` ranks -- the runs and exchanges of
+// shard_plan.cpp, the tile passes of every run. stats: [0] runs, [1] exchanges, [2] tile passes,
+// [3] exchanged bits in total, [4] bytes each rank sends (complex128: 16 B per amplitude).
+// If buf != NULL the plan is written as text (one line per step / primitive) for emulation in tests,
+// followed by a line "L2P ..." with the final logical -> physical bit map.
+int b2sv_plan_sharded(const b2sv_ops *ops, int num_qubits, int world, int dtype, uint64_t *stats5,
+                      char *buf, size_t cap) {
+    return guard([&] {
+        B2_ABORT_IF(!ops, "null op list");
+        int g = 0;
+        while ((1 << g) < world)
+            g++;
+        B2_ABORT_IF((1 << g) != world || num_qubits - g < 1, "invalid world size");
+        std::vector<Prim> prims;
+        for (const GateOp &op : ops->d.ops) {
+            if (op.name == "Identity")
+                continue;
+            const std::vector<int> bits = wires_to_bits(op.wires, num_qubits);
+            if (!lower_gate(op.name, bits, op.inverse, op.params, prims)) {
+                B2_ABORT_IF(op.matrix.empty(), "operation '" + op.name +
+                                                   "' is not a named gate and no matrix was provided");
+                lower_matrix(bits, op.inverse, op.matrix, prims);
+            }
+        }
+        ShardPlanConfig pc;
+        pc.n = num_qubits;
+        pc.n_local = num_qubits - g;
+        pc.min_victim_pos = std::min(5, std::max(0, pc.n_local - g - 1));
+        std::vector<int> l2p(num_qubits);
+        for (int q = 0; q < num_qubits; q++)
+            l2p[q] = q;
+        const std::vector<ShardStep> steps = plan_sharded(prims, l2p, pc);
+        SchedConfig cfg;
+        tile_config(dtype, &cfg.B, &cfg.R);
+        cfg.SW = dtype == 1 ? 3 : 4;
+        cfg.f32 = dtype != 1;
+        cfg.n_local = pc.n_local;
+        cfg.n_alloc = std::max(pc.n_local, cfg.B);
+        uint64_t st[5] = {0, 0, 0, 0, 0};
+        std::ostringstream os;
+        os << std::setprecision(17);
+        for (const ShardStep &sp : steps) {
+            if (sp.is_exchange) {
+                st[1]++;
+                st[3] += sp.swaps.size();
+                st[4] += ((uint64_t(1) << pc.n_local) - (uint64_t(1) << (pc.n_local - sp.swaps.size()))) * 16;
+                if (buf) {
+                    os << "EXCH";
+                    for (const auto &pr : sp.swaps)
+                        os << ' ' << pr.first << ' ' << pr.second;
+                    os << '\n';
+                }
+                continue;
+            }
+            st[0]++;
+            st[2] += build_schedule(sp.prims, cfg).size();
+            if (!buf)
+                continue;
+            os << "RUN " << sp.prims.size() << '\n';
+            for (const Prim &p : sp.prims) {
+                if (p.type == Prim::C1Q) {
+                    os << "C1Q " << p.target << ' ' << p.cmask << ' ' << p.cval;
+                    for (int i = 0; i < 4; i++)
+                        os << ' ' << p.m[i].real() << ' ' << p.m[i].imag();
+                } else if (p.type == Prim::DIAG) {
+                    os << "DIAG " << p.pmask << ' ' << p.cmask << ' ' << p.cval;
+                    for (int i = 0; i < 2; i++)
+                        os << ' ' << p.m[i].real() << ' ' << p.m[i].imag();
+                } else {
+                    os << "MATK " << p.bits.size();
+                    for (int b : p.bits)
+                        os << ' ' << b;
+                    for (const cplx &c : p.mat)
+                        os << ' ' << c.real() << ' ' << c.imag();
+                }
+                os << '\n';
+            }
+        }
+        if (buf) {
+            os << "L2P";
+            for (int q = 0; q < num_qubits; q++)
+                os << ' ' << l2p[q];
+            os << '\n';
+            const std::string str = os.str();
+            B2_ABORT_IF(str.size() + 1 > cap, "plan text does not fit the buffer");
+            std::memcpy(buf, str.c_str(), str.size() + 1);
+        }
+        if (stats5)
+            for (int i = 0; i < 5; i++)
+                stats5[i] = st[i];
     });
 }
 

@@ -80,7 +80,13 @@ struct Comm {
     double *d_token = nullptr; // one double used for stream-ordered barriers
     bool use_peer = true;      // NVLink peer-memory swap kernel (CUDA IPC); else NCCL send/recv
     uint64_t swaps = 0, swap_bytes = 0;
+    // cross-rank barriers through IPC-mapped flag words (kernels.cu k_flag_barrier): kFlagChannels
+    // independent channels of `world` words each, so barriers on different streams cannot mix up
+    unsigned long long *flags = nullptr;
+    std::vector<void *> flag_peers; // flag arrays of all ranks
+    unsigned long long epoch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+constexpr int kFlagChannels = 8;
 
 void comm_unique_id(void *out128) {
     NcclId id;
@@ -108,6 +114,10 @@ void comm_destroy(Comm *c) {
     if (!c)
         return;
     cudaSetDevice(c->device);
+    if (c->flags) {
+        comm_unmap_peers(c, c->flag_peers);
+        cudaFree(c->flags);
+    }
     if (c->staging)
         cudaFree(c->staging);
     if (c->d_token)
@@ -120,9 +130,36 @@ void comm_allreduce_sum(Comm *c, double *d_buf, int n, cudaStream_t stream) {
     NCCL_CHECK(nccl().AllReduce(d_buf, d_buf, static_cast<size_t>(n), kNcclFloat64, kNcclSum,
                                 c->comm, stream));
 }
-void comm_barrier(Comm *c, cudaStream_t stream) {
+void comm_barrier(Comm *c, cudaStream_t stream, int channel) {
+    if (c->use_peer && c->flags && c->world <= 32) {
+        B2_ASSERT(channel >= 0 && channel < kFlagChannels);
+        FlagPeers fp{};
+        for (int r = 0; r < c->world; r++)
+            fp.p[r] = static_cast<unsigned long long *>(c->flag_peers[r]) + channel * c->world;
+        launch_flag_barrier(c->flags + channel * c->world, fp, c->rank, c->world, ++c->epoch[channel],
+                            stream);
+        return;
+    }
     NCCL_CHECK(nccl().AllReduce(c->d_token, c->d_token + 1, 1, kNcclFloat64, kNcclSum, c->comm,
                                 stream));
+}
+// Collective, once per communicator: the flag words of every rank, IPC-mapped.
+void comm_setup_flags(Comm *c, cudaStream_t stream) {
+    if (c->flags || !c->use_peer)
+        return;
+    CUDA_CHECK(cudaSetDevice(c->device));
+    // a 2 MiB allocation of its own: IPC handles map whole driver blocks, small cudaMallocs share one
+    const size_t bytes = size_t(2) << 20;
+    B2_ASSERT(sizeof(unsigned long long) * kFlagChannels * c->world <= bytes);
+    CUDA_CHECK(cudaMalloc(&c->flags, bytes));
+    CUDA_CHECK(cudaMemset(c->flags, 0, bytes));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    comm_map_peers(c, c->flags, c->flag_peers, stream);
+    if (!c->use_peer) { // mapping failed somewhere: every rank is on the NCCL path now
+        cudaFree(c->flags);
+        c->flags = nullptr;
+        c->flag_peers.clear();
+    }
 }
 int comm_rank(const Comm *c) { return c->rank; }
 int comm_world(const Comm *c) { return c->world; }
@@ -193,6 +230,54 @@ void comm_unmap_peers(Comm *c, std::vector<void *> &ptrs) {
         }
 }
 
+// One exchange of k rank bits with k local bits (all-to-all inside the 2^k-rank group), in place.
+void comm_exchange(Comm *c, void *data, const std::vector<void *> &peers, int dtype, int n_local,
+                   const std::vector<std::pair<int, int>> &jl, cudaStream_t st, int channel,
+                   int max_ctas) {
+    CUDA_CHECK(cudaSetDevice(c->device));
+    const int k = static_cast<int>(jl.size());
+    if (k == 0)
+        return;
+    bool peer_ok = c->use_peer && k <= kMaxExchangeBits && n_local - k - 1 >= 0;
+    for (int r = 0; r < c->world && peer_ok; r++)
+        peer_ok = peers[r] != nullptr;
+    if (!peer_ok) { // NCCL path: one bit at a time through the staging buffer
+        for (const auto &p : jl)
+            comm_swap_bits(c, data, peers, dtype, n_local, p.first, p.second, st);
+        return;
+    }
+    const size_t ab = dtype == 1 ? 16 : 8;
+    c->swaps++;
+    c->swap_bytes += ((uint64_t(1) << n_local) - (uint64_t(1) << (n_local - k))) * ab;
+    ExchangeParams p{};
+    p.k = k;
+    p.n_local = n_local;
+    uint64_t lmask = 0;
+    for (int i = 0; i < k; i++) {
+        p.lpos[i] = jl[i].second;
+        lmask |= bit(jl[i].second);
+        p.a |= static_cast<uint32_t>((c->rank >> jl[i].first) & 1) << i;
+    }
+    // selector: the highest local bit that is not exchanged (keeps warps on contiguous runs)
+    p.selbit = n_local - 1;
+    while (lmask & bit(p.selbit))
+        p.selbit--;
+    B2_ASSERT(p.selbit >= 0);
+    const uint64_t fix = lmask | bit(p.selbit);
+    for (int b = 0; b < n_local; b++)
+        if (fix & bit(b))
+            p.fixpos[p.nfix++] = b;
+    for (uint32_t b = 0; b < (1u << k); b++) {
+        int r = c->rank;
+        for (int i = 0; i < k; i++)
+            r = (r & ~(1 << jl[i].first)) | (static_cast<int>((b >> i) & 1u) << jl[i].first);
+        p.peer[b] = peers[r];
+    }
+    comm_barrier(c, st, channel); // every rank has finished what it queued on its shard
+    launch_exchange(dtype, data, p, max_ctas, st);
+    comm_barrier(c, st, channel); // every rank's exchange kernel has finished writing into this shard
+}
+
 // Exchange rank bit j with local bit l: amplitudes with (rank_bit, local_bit) = (0,1) on the lower
 // rank trade places with (1,0) on the partner rank r ^ (1<<j).
 //   peer path : one kernel per rank swaps its half of the pairs in place through the partner's
@@ -208,9 +293,9 @@ void comm_swap_bits(Comm *c, void *data, const std::vector<void *> &peers, int d
     c->swaps++;
     c->swap_bytes += (uint64_t(1) << (n_local - 1)) * ab;
     if (c->use_peer && peers[partner]) {
-        comm_barrier(c, st); // the partner has finished everything queued on its shard
+        comm_barrier(c, st, 0); // the partner has finished everything queued on its shard
         launch_peer_swap(dtype, data, peers[partner], n_local, l, my_bit, st);
-        comm_barrier(c, st); // the partner's kernel has finished writing into this shard
+        comm_barrier(c, st, 0); // the partner's kernel has finished writing into this shard
         return;
     }
     const uint64_t run = uint64_t(1) << l;                  // amplitudes per run

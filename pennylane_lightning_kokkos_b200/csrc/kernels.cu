@@ -842,6 +842,104 @@ void launch_peer_swap(int dtype, void *mine, void *peer, int n_local, int lbit, 
     CUDA_CHECK(cudaGetLastError());
 }
 
+// ---- k-bit global<->local exchange: an all-to-all inside a group of 2^k ranks, in place ---------
+// Rank bits j_1..j_k trade places with local bits l_1..l_k. With a = this rank's value on the rank
+// bits and b != a a partner's, the sub-block of this shard whose local bits spell b and the sub-block
+// of the partner's shard whose local bits spell a swap contents element by element (the sub-block
+// with local bits = a stays). For every unordered pair {a, b} each of the two ranks moves half of the
+// elements (selector bit = a < b on one side, b < a on the other), reading both sides and writing
+// both sides through the partner's IPC-mapped shard, so every NVLink direction of every rank carries
+// (1 - 2^-k) S / 2 of loads and as much of stores. Chunks of 1024 elements go round-robin over the
+// partners, starting at a + 1, so at any moment the ranks of a group talk to distinct peers.
+template <typename amp_t>
+__global__ void __launch_bounds__(256)
+    k_exchange(amp_t *__restrict__ mine, ExchangeParams p, uint64_t nrest, uint64_t nchunks) {
+    constexpr int U = 4;
+    const uint32_t nparts = (1u << p.k) - 1u;
+    for (uint64_t c = blockIdx.x; c < nchunks * nparts; c += gridDim.x) {
+        const uint32_t pi = static_cast<uint32_t>(c % nparts);
+        const uint64_t chunk = c / nparts;
+        const uint32_t b = (p.a + 1u + pi) & nparts; // nparts = 2^k - 1 is also the group mask
+        amp_t *__restrict__ peer = static_cast<amp_t *>(p.peer[b]);
+        uint64_t dep_a = 0, dep_b = 0;
+#pragma unroll 4
+        for (int i = 0; i < p.k; i++) {
+            dep_a |= static_cast<uint64_t>((p.a >> i) & 1u) << p.lpos[i];
+            dep_b |= static_cast<uint64_t>((b >> i) & 1u) << p.lpos[i];
+        }
+        const uint64_t sel = static_cast<uint64_t>(p.a < b ? 0 : 1) << p.selbit;
+        uint64_t im[U], ip[U];
+        amp_t x[U], y[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t e = chunk * (256 * U) + u * 256 + threadIdx.x;
+            ok[u] = e < nrest;
+            uint64_t i = ok[u] ? e : 0;
+            for (int f = 0; f < p.nfix; f++)
+                i = insert_zero(i, p.fixpos[f]);
+            i |= sel;
+            im[u] = i | dep_b;
+            ip[u] = i | dep_a;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            y[u] = peer[ip[u]];
+            x[u] = mine[im[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (ok[u]) {
+                peer[ip[u]] = x[u];
+                mine[im[u]] = y[u];
+            }
+        }
+    }
+}
+void launch_exchange(int dtype, void *mine, const ExchangeParams &p, int max_ctas, cudaStream_t st) {
+    const uint64_t nrest = uint64_t(1) << (p.n_local - p.k - 1);
+    const uint64_t nchunks = (nrest + 1023) / 1024;
+    const uint64_t work = nchunks * ((uint64_t(1) << p.k) - 1);
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(work, static_cast<uint64_t>(max_ctas)));
+    if (dtype == 1)
+        k_exchange<double2><<<grid, 256, 0, st>>>(static_cast<double2 *>(mine), p, nrest, nchunks);
+    else
+        k_exchange<float2><<<grid, 256, 0, st>>>(static_cast<float2 *>(mine), p, nrest, nchunks);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ---- cross-rank barrier through IPC-mapped flag words (one block, one thread per rank) ------------
+// Thread r publishes `epoch` into rank r's flag array (slot = this rank) and then waits until rank r's
+// value in this rank's own array reaches `epoch`. Stream order makes everything queued before the
+// barrier on this rank complete (remote stores included) before the flag goes out. A peer that never
+// arrives must not hang the GPU: after `timeout_ns` the kernel traps (a CUDA error on the host).
+__global__ void k_flag_barrier(unsigned long long *mine, FlagPeers peers, int rank, int world,
+                               unsigned long long epoch, unsigned long long timeout_ns) {
+    const int r = threadIdx.x;
+    if (r >= world)
+        return;
+    __threadfence_system();
+    unsigned long long *dst = peers.p[r] + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+    unsigned long long t0, t1, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (true) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + r) : "memory");
+        if (v >= epoch)
+            break;
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns)
+            __trap();
+    }
+    __threadfence_system();
+}
+void launch_flag_barrier(unsigned long long *mine, const FlagPeers &peers, int rank, int world,
+                         unsigned long long epoch, cudaStream_t st) {
+    k_flag_barrier<<<1, 32, 0, st>>>(mine, peers, rank, world, epoch, 20ull * 1000 * 1000 * 1000);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_set_basis(int dtype, void *state, uint64_t len, uint64_t index, cudaStream_t st) {
     const int grid = reduce_grid(len);
     DISPATCH_DTYPE(dtype,

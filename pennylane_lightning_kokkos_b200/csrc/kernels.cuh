@@ -38,6 +38,25 @@ void launch_matk(int dtype, void *state, int n_eff, const double2 *d_mat, const 
 void launch_peer_swap(int dtype, void *mine, void *peer, int n_local, int lbit, int my_bit,
                       cudaStream_t st);
 
+// k-bit exchange (all-to-all inside a group of 2^k ranks), see kernels.cu k_exchange
+constexpr int kMaxExchangeBits = 4;
+struct ExchangeParams {
+    int k;                          // bits exchanged (1..kMaxExchangeBits)
+    int n_local;                    // local index bits
+    int nfix;                       // k + 1
+    int fixpos[kMaxExchangeBits + 1]; // the k local bits and the selector bit, ascending
+    int lpos[kMaxExchangeBits];     // local bit paired with group-value bit i
+    int selbit;                     // which half of a pair of sub-blocks this rank moves
+    uint32_t a;                     // this rank's value on the k rank bits
+    void *peer[1 << kMaxExchangeBits]; // shard of the rank with group value b (entry a unused)
+};
+void launch_exchange(int dtype, void *mine, const ExchangeParams &p, int max_ctas, cudaStream_t st);
+struct FlagPeers {
+    unsigned long long *p[64];
+};
+void launch_flag_barrier(unsigned long long *mine, const FlagPeers &peers, int rank, int world,
+                         unsigned long long epoch, cudaStream_t st);
+
 // ---- reductions: every kernel writes kReduceBlocks x nv partials; finalize sums them (fixed order)
 void launch_norm2(int dtype, const void *state, uint64_t len, double *d_partials, cudaStream_t st);
 void launch_dot(int dtype, const void *x, const void *y, uint64_t len, double *d_partials,

@@ -3,6 +3,7 @@
 
 #include <mutex>
 #include "comm.hpp"
+#include "shard_plan.hpp"
 
 #include <algorithm>
 #include <cstdlib>
@@ -217,6 +218,7 @@ void State::init_common(const void *nccl_id) {
             comm_ = std::shared_ptr<Comm>(comm_create(rank_, world_, nccl_id, device_), comm_destroy);
         l2p_.resize(n_);
         comm_map_peers(comm_.get(), d_state_, peers_, stream_);
+        comm_setup_flags(comm_.get(), stream_);
     }
     reset();
 }
@@ -454,60 +456,74 @@ uint64_t State::phys_mask(uint64_t m) const {
     }
     return r;
 }
-Prim State::to_physical(const Prim &p) const {
-    Prim q = p;
-    if (p.type == Prim::C1Q)
-        q.target = l2p_[p.target];
-    q.cmask = phys_mask(p.cmask);
-    q.cval = phys_mask(p.cval);
-    q.pmask = phys_mask(p.pmask);
-    for (int &b : q.bits)
-        b = l2p_[b];
-    return q;
-}
-void State::swap_phys(int gpos, int lpos) const {
-    B2_ASSERT(comm_ && gpos >= n_local_ && lpos < n_local_);
+// One exchange: rank-bit positions <-> local positions, all pairs at once (comm.cpp comm_exchange).
+void State::exchange_phys(const std::vector<std::pair<int, int>> &pairs) const {
+    if (pairs.empty())
+        return;
+    B2_ASSERT(comm_);
+    std::vector<std::pair<int, int>> jl;
+    for (const auto &pr : pairs) {
+        B2_ASSERT(pr.first >= n_local_ && pr.first < n_ && pr.second >= 0 && pr.second < n_local_);
+        jl.emplace_back(pr.first - n_local_, pr.second);
+    }
     {
         TraceScope ts(*this, 2);
-        comm_swap_bits(comm_.get(), d_state_, peers_, dtype_, n_local_, gpos - n_local_, lpos, stream_);
+        comm_exchange(comm_.get(), d_state_, peers_, dtype_, n_local_, jl, stream_, 0, exchange_ctas());
     }
-    int qa = -1, qb = -1;
-    for (int q = 0; q < n_; q++) {
-        if (l2p_[q] == gpos)
-            qa = q;
-        if (l2p_[q] == lpos)
-            qb = q;
-    }
-    std::swap(l2p_[qa], l2p_[qb]);
+    std::vector<int> p2l(n_);
+    for (int q = 0; q < n_; q++)
+        p2l[l2p_[q]] = q;
+    for (const auto &pr : pairs)
+        std::swap(l2p_[p2l[pr.first]], l2p_[p2l[pr.second]]);
+}
+int State::exchange_ctas() const {
+    const char *e = getenv("B2SV_EXCHANGE_CTAS"); // read on every call: benchmarks sweep it
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : sm_count_current_device() * 8;
+}
+ShardPlanConfig State::shard_plan_config() const {
+    ShardPlanConfig cfg;
+    cfg.n = n_;
+    cfg.n_local = n_local_;
+    cfg.min_victim_pos = std::min(5, std::max(0, n_local_ - gbits_ - 1));
+    if (const char *e = getenv("B2SV_EXCHANGE_BATCH"))
+        cfg.batch = atoi(e) != 0;
+    return cfg;
 }
 void State::ensure_local(uint64_t logical_mask) const {
     if (!comm_)
         return;
     CUDA_CHECK(cudaSetDevice(device_));
+    std::vector<std::pair<int, int>> pairs;
+    uint64_t used = 0; // local positions already chosen as victims
     for (int q = 0; q < n_; q++) {
         if (!((logical_mask >> q) & 1) || l2p_[q] < n_local_)
             continue;
         // victim: the highest local position whose logical owner is not wanted
         int victim = -1;
-        for (int pos = n_local_ - 1; pos >= 0 && victim < 0; pos--)
+        for (int pos = n_local_ - 1; pos >= 0 && victim < 0; pos--) {
+            if ((used >> pos) & 1)
+                continue;
             for (int o = 0; o < n_; o++)
                 if (l2p_[o] == pos && !((logical_mask >> o) & 1))
                     victim = pos;
+        }
         B2_ABORT_IF(victim < 0, "operation acts on more qubits than one shard holds");
-        swap_phys(l2p_[q], victim);
+        used |= bit(victim);
+        pairs.emplace_back(l2p_[q], victim);
     }
+    exchange_phys(pairs);
 }
 void State::normalize_layout() const {
     if (!comm_)
         return;
     CUDA_CHECK(cudaSetDevice(device_));
     // rank bits first: logical bit P must sit at physical position P for P >= n_local
-    for (int P = n_local_; P < n_; P++) {
-        if (l2p_[P] == P)
-            continue;
-        if (l2p_[P] >= n_local_)
-            ensure_local(bit(P)); // it sits on another rank bit: bring it into the shard first
-        swap_phys(P, l2p_[P]);
+    {
+        std::vector<int> l2p = l2p_;
+        for (const ShardStep &stp : plan_normalize(l2p, shard_plan_config()))
+            exchange_phys(stp.swaps);
+        B2_ASSERT(l2p == l2p_);
     }
     // then sort the local positions with SWAPs (free address-map permutations inside tile passes)
     std::vector<Prim> prims;
@@ -537,75 +553,19 @@ void State::comm_stats(uint64_t *swaps, uint64_t *bytes, int *peer) const {
     }
 }
 
-// Sharded gate application. Ops are taken in order as long as their non-diagonal targets are
-// shard-local (controls and phases on rank bits are CTA-uniform predicates, they never move data);
-// when the frontier needs a rank bit, that qubit is swapped with the local qubit whose next use as a
-// target lies farthest in the future, and the walk continues in the new layout.
+// Sharded gate application (planner: shard_plan.cpp): runs of primitives whose non-diagonal targets are
+// shard-local, separated by exchanges that bring every global qubit with pending work into the shard
+// at once.
 void State::apply_prims_sharded(std::vector<Prim> pending) {
-    while (!pending.empty()) {
-        std::vector<Prim> seg, rest;
-        uint64_t T = 0, D = 0; // logical bits touched non-diagonally / diagonally by skipped ops
-        for (const Prim &p : pending) {
-            const uint64_t tm = p.target_mask(), dm = p.support() & ~tm;
-            const bool blocked = (tm & (T | D)) || (dm & T);
-            const bool local = (phys_mask(tm) >> n_local_) == 0;
-            if (!blocked && local) {
-                seg.push_back(to_physical(p));
-            } else {
-                T |= tm;
-                D |= dm;
-                rest.push_back(p);
-            }
-        }
-        if (!seg.empty())
-            run_local(seg);
-        if (rest.empty())
-            break;
-        // rank bits wanted by the frontier, in order of first appearance
-        std::vector<int> need;
-        uint64_t need_mask = 0;
-        for (const Prim &p : rest) {
-            uint64_t tm = p.target_mask();
-            while (tm && static_cast<int>(need.size()) < gbits_) {
-                const int q = __builtin_ctzll(tm);
-                tm &= tm - 1;
-                if (l2p_[q] >= n_local_ && !((need_mask >> q) & 1)) {
-                    need.push_back(q);
-                    need_mask |= bit(q);
-                }
-            }
-            if (static_cast<int>(need.size()) >= gbits_)
-                break;
-        }
-        B2_ASSERT(!need.empty());
-        std::vector<size_t> next_use(n_, rest.size() + 1);
-        for (size_t i = rest.size(); i-- > 0;) {
-            uint64_t tm = rest[i].target_mask();
-            while (tm) {
-                next_use[__builtin_ctzll(tm)] = i;
-                tm &= tm - 1;
-            }
-        }
-        for (int q : need) {
-            // victim: farthest next use (Belady), but not a qubit that sits on one of the low index
-            // bits -- swapping those moves 16..256-byte pieces and halves the NVLink efficiency
-            int victim = -1;
-            for (int min_pos : {5, 0}) {
-                for (int o = 0; o < n_; o++) {
-                    if (l2p_[o] >= n_local_ || l2p_[o] < min_pos || ((need_mask >> o) & 1))
-                        continue;
-                    if (victim < 0 || next_use[o] > next_use[victim] ||
-                        (next_use[o] == next_use[victim] && l2p_[o] > l2p_[victim]))
-                        victim = o;
-                }
-                if (victim >= 0)
-                    break;
-            }
-            B2_ASSERT(victim >= 0);
-            swap_phys(l2p_[q], l2p_[victim]);
-        }
-        pending.swap(rest);
+    std::vector<int> l2p = l2p_; // the plan works on a copy; exchange_phys moves l2p_ step by step
+    const std::vector<ShardStep> steps = plan_sharded(std::move(pending), l2p, shard_plan_config());
+    for (const ShardStep &stp : steps) {
+        if (stp.is_exchange)
+            exchange_phys(stp.swaps);
+        else
+            run_local(stp.prims);
     }
+    B2_ASSERT(l2p_ == l2p);
 }
 
 // ---- gates ----------------------------------------------------------------------------------------

@@ -152,8 +152,10 @@ class State {
     SchedConfig sched_config() const;
     void run_local(const std::vector<Prim> &prims);       // prims in PHYSICAL bits, all targets local
     void apply_prims_sharded(std::vector<Prim> prims);    // prims in logical bits
-    Prim to_physical(const Prim &p) const;
-    void swap_phys(int gpos, int lpos) const;             // rank bit position <-> local position
+    // rank-bit positions <-> local positions, all pairs in ONE exchange
+    void exchange_phys(const std::vector<std::pair<int, int>> &pairs) const;
+    int exchange_ctas() const;
+    struct ShardPlanConfig shard_plan_config() const;
     void reset_layout() const;
     void init_common(const void *nccl_id);
 

@@ -259,6 +259,19 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
             return dict(zip(("passes", "rounds", "arithmetic_ops", "absorbed_perms", "fused_stores"),
                             (x.value for x in v)))
 
+        def plan_sharded(self, num_qubits, world, with_text=False):
+            """Host-only: runs / exchanges / tile passes of this op list on a state sharded over
+            ``world`` ranks (b2sv_plan_sharded). Works without a GPU."""
+            v = (C.c_uint64 * 5)()
+            buf = C.create_string_buffer(64 << 20) if with_text else None
+            check(lib.b2sv_plan_sharded(self._h, int(num_qubits), int(world), dtype_flag, v, buf,
+                                        len(buf) if buf else 0))
+            out = dict(zip(("runs", "exchanges", "passes", "exchanged_bits", "bytes_per_rank"),
+                           (int(x) for x in v)))
+            if with_text:
+                out["text"] = buf.value.decode()
+            return out
+
         def __len__(self):
             return len(self.names)
 
@@ -518,6 +531,14 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
                                      C.byref(n)))
             m = min(n.value, cap)
             return [(int(kinds[i]), float(t0[i]), float(dt[i])) for i in range(m)]
+
+        def layout(self):
+            """Logical index bit q currently lives at physical bit layout()[q] (sharded states move
+            qubits between rank bits and shard-local bits lazily)."""
+            arr = np.zeros(64, dtype=np.int32)
+            n = C.c_int(0)
+            check(lib.b2sv_layout(self._h, arr.ctypes.data_as(_lib.ip), 64, C.byref(n)))
+            return [int(x) for x in arr[: n.value]]
 
         def normalize_layout(self):
             check(lib.b2sv_normalize_layout(self._h))

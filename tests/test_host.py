@@ -127,7 +127,7 @@ def test_bench_reference_arm_contract():
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     bench = os.path.join(root, "bench.py")
-    base = [sys.executable, bench, "--impl", "reference", "--qubits", "16", "--steps", "1", "--warmup", "1"]
+    base = [sys.executable, bench, "--impl", "reference", "--ref-qubits", "16", "--steps", "1", "--warmup", "1"]
     out = subprocess.run(base, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
