@@ -295,7 +295,14 @@ def sharded_parity(ops, b2dist, dist, torch, local_rank, world):
     g = world.bit_length() - 1
     worst, cases = 0.0, []
     for n, circ, tag in ((16 + g, layered_circuit(16 + g, 2, seed=3), "layers"),
-                         (14 + g, random_circuit(14 + g, 120, seed=5), "random")):
+                         (14 + g, random_circuit(14 + g, 120, seed=5), "random"),
+                         (19 + g, layered_circuit(19 + g, 3, seed=8), "layers, sliced + overlapped")):
+        # the last case forces the pipelined path (shard cut into slices, exchanges on a second
+        # stream beside the passes) that the timed 30-qubit-per-GPU run takes
+        if "sliced" in tag:
+            os.environ["B2SV_PIPE_MIN_SUB"] = "0"
+        else:
+            os.environ.pop("B2SV_PIPE_MIN_SUB", None)
         sv = b2dist.create_sharded_state(ops, n, np.complex128, local_rank)
         sv.apply([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ], [c[3] for c in circ])
         ez = [sv.ExpectationValue("PauliZ", [w], [], np.zeros(0)) for w in (0, n - 1)]
@@ -315,6 +322,7 @@ def sharded_parity(ops, b2dist, dist, torch, local_rank, world):
         cases.append(f"{tag} n={n}: {err:.1e}")
         del sv
         dist.barrier()
+    os.environ.pop("B2SV_PIPE_MIN_SUB", None)
     return {"max_rel_err": worst, "n": 16 + g, "world": world, "tolerance": 1e-12,
             "ok": bool(worst < 1e-12), "cases": cases,
             "against": "oracle/np_oracle.py (full state gathered from all ranks + <Z> on a global and a local wire)"}

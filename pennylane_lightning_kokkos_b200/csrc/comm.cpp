@@ -168,6 +168,7 @@ void comm_stats(const Comm *c, uint64_t *swaps, uint64_t *bytes) {
     *bytes = c->swap_bytes;
 }
 void comm_reset_stats(Comm *c) { c->swaps = c->swap_bytes = 0; }
+void comm_count_exchange(Comm *c) { c->swaps++; }
 bool comm_uses_peer(const Comm *c) { return c->use_peer; }
 
 // Maps every rank's buffer into this process (CUDA IPC): out[r] = pointer usable in kernels here.
@@ -233,7 +234,7 @@ void comm_unmap_peers(Comm *c, std::vector<void *> &ptrs) {
 // One exchange of k rank bits with k local bits (all-to-all inside the 2^k-rank group), in place.
 void comm_exchange(Comm *c, void *data, const std::vector<void *> &peers, int dtype, int n_local,
                    const std::vector<std::pair<int, int>> &jl, cudaStream_t st, int channel,
-                   int max_ctas) {
+                   int max_ctas, bool fat, size_t sub_offset_bytes) {
     CUDA_CHECK(cudaSetDevice(c->device));
     const int k = static_cast<int>(jl.size());
     if (k == 0)
@@ -247,7 +248,8 @@ void comm_exchange(Comm *c, void *data, const std::vector<void *> &peers, int dt
         return;
     }
     const size_t ab = dtype == 1 ? 16 : 8;
-    c->swaps++;
+    if (channel == 0) // exchanges done slice by slice are counted by the caller (comm_count_exchange)
+        c->swaps++;
     c->swap_bytes += ((uint64_t(1) << n_local) - (uint64_t(1) << (n_local - k))) * ab;
     ExchangeParams p{};
     p.k = k;
@@ -271,10 +273,10 @@ void comm_exchange(Comm *c, void *data, const std::vector<void *> &peers, int dt
         int r = c->rank;
         for (int i = 0; i < k; i++)
             r = (r & ~(1 << jl[i].first)) | (static_cast<int>((b >> i) & 1u) << jl[i].first);
-        p.peer[b] = peers[r];
+        p.peer[b] = static_cast<char *>(peers[r]) + sub_offset_bytes;
     }
     comm_barrier(c, st, channel); // every rank has finished what it queued on its shard
-    launch_exchange(dtype, data, p, max_ctas, st);
+    launch_exchange(dtype, static_cast<char *>(data) + sub_offset_bytes, p, max_ctas, fat, st);
     comm_barrier(c, st, channel); // every rank's exchange kernel has finished writing into this shard
 }
 

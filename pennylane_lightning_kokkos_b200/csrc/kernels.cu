@@ -851,8 +851,8 @@ void launch_peer_swap(int dtype, void *mine, void *peer, int n_local, int lbit, 
 // both sides through the partner's IPC-mapped shard, so every NVLink direction of every rank carries
 // (1 - 2^-k) S / 2 of loads and as much of stores. Chunks of 1024 elements go round-robin over the
 // partners, starting at a + 1, so at any moment the ranks of a group talk to distinct peers.
-template <typename amp_t>
-__global__ void __launch_bounds__(256)
+template <typename amp_t, int T>
+__global__ void __launch_bounds__(T)
     k_exchange(amp_t *__restrict__ mine, ExchangeParams p, uint64_t nrest, uint64_t nchunks) {
     constexpr int U = 4;
     const uint32_t nparts = (1u << p.k) - 1u;
@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(256)
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const uint64_t e = chunk * (256 * U) + u * 256 + threadIdx.x;
+            const uint64_t e = chunk * (T * U) + u * T + threadIdx.x;
             ok[u] = e < nrest;
             uint64_t i = ok[u] ? e : 0;
             for (int f = 0; f < p.nfix; f++)
@@ -896,15 +896,24 @@ __global__ void __launch_bounds__(256)
         }
     }
 }
-void launch_exchange(int dtype, void *mine, const ExchangeParams &p, int max_ctas, cudaStream_t st) {
+void launch_exchange(int dtype, void *mine, const ExchangeParams &p, int max_ctas, bool fat,
+                     cudaStream_t st) {
     const uint64_t nrest = uint64_t(1) << (p.n_local - p.k - 1);
-    const uint64_t nchunks = (nrest + 1023) / 1024;
+    const uint64_t per_chunk = (fat ? 1024 : 256) * 4;
+    const uint64_t nchunks = (nrest + per_chunk - 1) / per_chunk;
     const uint64_t work = nchunks * ((uint64_t(1) << p.k) - 1);
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(work, static_cast<uint64_t>(max_ctas)));
-    if (dtype == 1)
-        k_exchange<double2><<<grid, 256, 0, st>>>(static_cast<double2 *>(mine), p, nrest, nchunks);
-    else
-        k_exchange<float2><<<grid, 256, 0, st>>>(static_cast<float2 *>(mine), p, nrest, nchunks);
+    if (dtype == 1) {
+        if (fat)
+            k_exchange<double2, 1024><<<grid, 1024, 0, st>>>(static_cast<double2 *>(mine), p, nrest, nchunks);
+        else
+            k_exchange<double2, 256><<<grid, 256, 0, st>>>(static_cast<double2 *>(mine), p, nrest, nchunks);
+    } else {
+        if (fat)
+            k_exchange<float2, 1024><<<grid, 1024, 0, st>>>(static_cast<float2 *>(mine), p, nrest, nchunks);
+        else
+            k_exchange<float2, 256><<<grid, 256, 0, st>>>(static_cast<float2 *>(mine), p, nrest, nchunks);
+    }
     CUDA_CHECK(cudaGetLastError());
 }
 

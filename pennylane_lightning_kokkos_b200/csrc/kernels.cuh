@@ -14,8 +14,10 @@ constexpr int kMaxReduceVals = 8;
 // ---- tile executor (tile_kernel.cu)
 void tile_config(int dtype, int *B, int *R);
 struct PassParams;
+// state / n_eff may describe a sub-range of a shard (its top index bits fixed, supplied through
+// rank_bits); max_ctas > 0 caps the persistent grid (SMs left to a concurrent exchange kernel)
 void launch_tile_pass(int dtype, void *state, const PassParams &pass, int n_eff,
-                      uint64_t rank_bits, cudaStream_t stream);
+                      uint64_t rank_bits, cudaStream_t stream, int max_ctas = 0);
 void tile_prof_read(unsigned long long out[16]);
 
 // ---- state management
@@ -50,7 +52,10 @@ struct ExchangeParams {
     uint32_t a;                     // this rank's value on the k rank bits
     void *peer[1 << kMaxExchangeBits]; // shard of the rank with group value b (entry a unused)
 };
-void launch_exchange(int dtype, void *mine, const ExchangeParams &p, int max_ctas, cudaStream_t st);
+// fat = true: CTAs of 1024 threads, one per SM, max_ctas of them (an exchange that runs beside tile
+// passes occupies exactly max_ctas SMs); false: 256-thread CTAs, up to max_ctas
+void launch_exchange(int dtype, void *mine, const ExchangeParams &p, int max_ctas, bool fat,
+                     cudaStream_t st);
 struct FlagPeers {
     unsigned long long *p[64];
 };

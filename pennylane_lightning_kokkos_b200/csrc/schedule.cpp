@@ -617,7 +617,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                     // an absorbable permutation waits for the next round boundary, where it is free
                     bool fits = !rb.blocked(p) && perm_class(remaining[r]) == 0;
                     if (fits && sweep == 0)
-                        fits = p.type == Prim::C1Q && tile_pos(p.target) < 5;
+                        fits = p.type == Prim::C1Q && tile_pos(p.target) < low;
                     if (fits && p.type == Prim::C1Q) {
                         const int j = tile_pos(p.target);
                         if (!(reg_mask & (1u << j))) {
@@ -766,14 +766,17 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                 if (!(reg_mask & (1u << j)))
                     free_js.push_back(j);
             {
-                // Direct store from registers: possible when five thread-id bits of the last round can
-                // be given free tile bits whose images under the trailing permutations stay inside
-                // logical bits 0..4 and span them -- then every warp-wide store covers whole runs.
+                // Direct store from registers: possible when `low` thread-id bits of the last round can
+                // be given free tile bits whose images under the trailing permutations stay inside the
+                // contiguous low index bits and span them -- then the 32 lanes of a warp (the five
+                // lowest thread-id bits: those `low` plus any 5 - low other free bits) always cover
+                // whole runs of 2^low amplitudes.
                 std::vector<int> lanes, others;
                 std::vector<uint32_t> basis;
+                const int n_lane = std::min(low, 5);
                 for (int j : free_js) {
                     uint32_t v = Lcol[j];
-                    bool ok = v < 32u && lanes.size() < 5;
+                    bool ok = v < (1u << n_lane) && static_cast<int>(lanes.size()) < n_lane;
                     if (ok) {
                         for (uint32_t b : basis)
                             v = std::min(v, v ^ b);
@@ -787,7 +790,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                         others.push_back(j);
                     }
                 }
-                if (lanes.size() == 5) {
+                if (static_cast<int>(lanes.size()) == n_lane) {
                     lanes.insert(lanes.end(), others.begin(), others.end());
                     commit(lanes, 1);
                 }

@@ -82,7 +82,8 @@ std::vector<ShardStep> plan_sharded(std::vector<Prim> pending, std::vector<int> 
         for (int min_pos : {cfg.min_victim_pos, 0}) {
             cand.clear();
             for (int o = 0; o < n; o++)
-                if (l2p[o] < n_local && l2p[o] >= min_pos && !((need_mask >> o) & 1))
+                if (l2p[o] < n_local && l2p[o] >= min_pos && l2p[o] < cfg.max_victim_pos &&
+                    !((need_mask >> o) & 1))
                     cand.push_back(o);
             if (cand.size() >= need.size())
                 break;

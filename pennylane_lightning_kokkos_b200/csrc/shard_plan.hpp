@@ -26,6 +26,8 @@ struct ShardPlanConfig {
     int n = 0;          // logical = physical index bits in total
     int n_local = 0;    // physical bits below n_local are shard-local
     int min_victim_pos = 5; // local positions below this are not sent out (short HBM / NVLink runs)
+    int max_victim_pos = 64; // local positions from here up are never sent out (the bits that slice a
+                             // shard for pipelined execution must stay put)
     bool batch = true;  // false: one bit per exchange, as many exchanges as needed (A/B measurements)
 };
 

@@ -253,6 +253,10 @@ State::~State() {
         if (h_out_)
             cudaFreeHost(h_out_);
     }
+    if (xstream_) {
+        cudaStreamSynchronize(xstream_);
+        cudaStreamDestroy(xstream_);
+    }
     if (stream_ && owns_stream_)
         cudaStreamDestroy(stream_);
 }
@@ -486,6 +490,7 @@ ShardPlanConfig State::shard_plan_config() const {
     cfg.n = n_;
     cfg.n_local = n_local_;
     cfg.min_victim_pos = std::min(5, std::max(0, n_local_ - gbits_ - 1));
+    cfg.max_victim_pos = n_local_ - pipeline_bits();
     if (const char *e = getenv("B2SV_EXCHANGE_BATCH"))
         cfg.batch = atoi(e) != 0;
     return cfg;
@@ -557,15 +562,235 @@ void State::comm_stats(uint64_t *swaps, uint64_t *bytes, int *peer) const {
 // shard-local, separated by exchanges that bring every global qubit with pending work into the shard
 // at once.
 void State::apply_prims_sharded(std::vector<Prim> pending) {
-    std::vector<int> l2p = l2p_; // the plan works on a copy; exchange_phys moves l2p_ step by step
+    std::vector<int> l2p = l2p_; // the plan works on a copy; the layout moves step by step below
     const std::vector<ShardStep> steps = plan_sharded(std::move(pending), l2p, shard_plan_config());
-    for (const ShardStep &stp : steps) {
-        if (stp.is_exchange)
-            exchange_phys(stp.swaps);
-        else
-            run_local(stp.prims);
+    const int c = pipeline_bits();
+    bool any_exchange = false;
+    for (const ShardStep &stp : steps)
+        any_exchange = any_exchange || stp.is_exchange;
+    if (c > 0 && any_exchange) {
+        run_sharded_pipelined(steps, c);
+    } else {
+        for (const ShardStep &stp : steps) {
+            if (stp.is_exchange)
+                exchange_phys(stp.swaps);
+            else
+                run_local(stp.prims);
+        }
     }
     B2_ASSERT(l2p_ == l2p);
+}
+
+// Slices only pay when a slice is still a long stream for the persistent tile kernel.
+int State::pipeline_bits() const {
+    if (!comm_ || !comm_uses_peer(comm_.get()) || !fuse_)
+        return 0;
+    int c = 2;
+    if (const char *e = getenv("B2SV_PIPE_BITS"))
+        c = std::max(0, std::min(4, atoi(e)));
+    int min_sub = 24; // B2SV_PIPE_MIN_SUB: tests force slicing on small states
+    if (const char *e = getenv("B2SV_PIPE_MIN_SUB"))
+        min_sub = atoi(e);
+    if (n_local_ - c < min_sub || n_local_ - c < B_ + gbits_ + 1 || n_eff_ != n_local_)
+        return 0;
+    return c;
+}
+
+void State::run_sharded_pipelined(const std::vector<ShardStep> &steps, int c) {
+    const int Q = 1 << c;
+    const int n_sub = n_local_ - c;
+    const uint64_t selmask = (bit(n_local_) - 1) & ~(bit(n_sub) - 1);
+    const uint64_t rank_bits = uint64_t(rank_) << n_local_;
+    const size_t sub_bytes = (size_t(1) << n_sub) * amp_bytes();
+    if (!xstream_)
+        CUDA_CHECK(cudaStreamCreateWithFlags(&xstream_, cudaStreamNonBlocking));
+    int x_sms = 20; // SMs the exchange kernel occupies while tile passes run beside it
+    if (const char *e = getenv("B2SV_EXCHANGE_SMS"))
+        x_sms = std::max(4, std::min(64, atoi(e)));
+    const int pass_ctas = sm_count_current_device() - x_sms;
+
+    // ---- tasks: the tile passes of every run and the exchanges, in program order
+    struct Task {
+        const Pass *pass = nullptr;      // tile pass / generic-matrix pass
+        const ShardStep *xchg = nullptr; // exchange
+        bool split = false;
+    };
+    std::vector<std::vector<Pass>> schedules;
+    schedules.reserve(steps.size());
+    std::vector<Task> tasks;
+    const SchedConfig cfg = sched_config();
+    for (const ShardStep &stp : steps) {
+        Task t;
+        if (stp.is_exchange) {
+            t.xchg = &stp;
+            t.split = true;
+            for (const auto &pr : stp.swaps)
+                t.split = t.split && !(selmask & bit(pr.second));
+            tasks.push_back(t);
+            continue;
+        }
+        schedules.push_back(build_schedule(stp.prims, cfg));
+        for (const Pass &ps : schedules.back()) {
+            t.pass = &ps;
+            t.split = false;
+            if (!ps.is_matk) {
+                uint64_t tile_mask = 0;
+                for (int j = 0; j < B_; j++)
+                    tile_mask |= bit(ps.hdr.tile_bits[j]);
+                t.split = (tile_mask & selmask) == 0;
+            }
+            tasks.push_back(t);
+        }
+    }
+
+    // ---- issue machinery: which event guards each slice, and on which stream it was recorded
+    std::vector<cudaEvent_t> events;
+    struct Guard {
+        cudaEvent_t ev = nullptr;
+        cudaStream_t st = nullptr;
+    };
+    std::vector<Guard> last(Q);
+    auto wait_for = [&](cudaStream_t st, int q) {
+        if (last[q].ev && last[q].st != st)
+            CUDA_CHECK(cudaStreamWaitEvent(st, last[q].ev, 0));
+    };
+    auto mark = [&](cudaStream_t st, int q0, int q1) {
+        cudaEvent_t ev;
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(ev, st));
+        events.push_back(ev);
+        for (int q = q0; q < q1; q++)
+            last[q] = {ev, st};
+    };
+    auto params = std::make_unique<PassParams>();
+    auto load_params = [&](const Pass &ps) {
+        params->hdr = ps.hdr;
+        std::memcpy(params->ops, ps.ops.data(), sizeof(DevOp) * ps.ops.size());
+        if (!ps.dense.empty())
+            std::memcpy(params->dense, ps.dense.data(), sizeof(DevDense) * ps.dense.size());
+    };
+    // a tile pass over slice q (q < 0: the whole shard)
+    auto issue_pass = [&](const Pass &ps, int q, bool beside_exchange) {
+        if (ps.is_matk) {
+            B2_ASSERT(q < 0);
+            for (int s = 0; s < Q; s++)
+                wait_for(stream_, s);
+            upload_and_run(std::vector<Pass>{ps});
+            mark(stream_, 0, Q);
+            return;
+        }
+        load_params(ps);
+        TraceScope ts(*this, 0);
+        if (q < 0) {
+            for (int s = 0; s < Q; s++)
+                wait_for(stream_, s);
+            launch_tile_pass(dtype_, d_state_, *params, n_local_, rank_bits, stream_, 0);
+        } else {
+            wait_for(stream_, q);
+            launch_tile_pass(dtype_, static_cast<char *>(d_state_) + size_t(q) * sub_bytes, *params, n_sub,
+                             rank_bits | (uint64_t(q) << n_sub), stream_, beside_exchange ? pass_ctas : 0);
+        }
+        launches++;
+    };
+    auto count_pass = [&]() {
+        sweeps++;
+        bytes_moved += 2 * state_bytes();
+    };
+    auto to_jl = [&](const ShardStep &x) {
+        std::vector<std::pair<int, int>> jl;
+        for (const auto &pr : x.swaps)
+            jl.emplace_back(pr.first - n_local_, pr.second);
+        return jl;
+    };
+    auto advance_layout = [&](const ShardStep &x) {
+        std::vector<int> p2l(n_);
+        for (int q = 0; q < n_; q++)
+            p2l[l2p_[q]] = q;
+        for (const auto &pr : x.swaps)
+            std::swap(l2p_[p2l[pr.first]], l2p_[p2l[pr.second]]);
+    };
+
+    size_t i = 0;
+    while (i < tasks.size()) {
+        if (!tasks[i].split) { // a pass that needs the whole shard (or an exchange that cannot be cut)
+            if (tasks[i].pass) {
+                issue_pass(*tasks[i].pass, -1, false);
+                if (!tasks[i].pass->is_matk) {
+                    mark(stream_, 0, Q);
+                    count_pass();
+                }
+            } else {
+                for (int s = 0; s < Q; s++)
+                    wait_for(stream_, s);
+                exchange_phys(tasks[i].xchg->swaps); // sequential, on the state's stream
+                mark(stream_, 0, Q);
+            }
+            i++;
+            continue;
+        }
+        size_t j = i;
+        bool has_exchange = false;
+        while (j < tasks.size() && tasks[j].split) {
+            has_exchange = has_exchange || tasks[j].xchg != nullptr;
+            j++;
+        }
+        if (!has_exchange) { // nothing to overlap with: whole-shard launches
+            for (; i < j; i++) {
+                issue_pass(*tasks[i].pass, -1, false);
+                mark(stream_, 0, Q);
+                count_pass();
+            }
+            continue;
+        }
+        // phases of passes separated by exchanges; slice q runs phase p at step q + p (skewed), so the
+        // exchange of a slice is in flight while the passes of the neighbouring slices run
+        std::vector<std::vector<const Pass *>> phase(1);
+        std::vector<const ShardStep *> xafter; // exchange that follows phase p (nullptr for the last)
+        for (size_t t = i; t < j; t++) {
+            if (tasks[t].xchg) {
+                xafter.push_back(tasks[t].xchg);
+                phase.emplace_back();
+            } else {
+                phase.back().push_back(tasks[t].pass);
+            }
+        }
+        xafter.push_back(nullptr);
+        const int P = static_cast<int>(phase.size());
+        for (int step = 0; step < Q + P - 1; step++) {
+            for (int p = 0; p < P; p++) { // earlier phases first: their passes cover the exchange the
+                                          // later phase of the neighbouring slice is waiting for
+                const int q = step - p;
+                if (q < 0 || q >= Q)
+                    continue;
+                for (const Pass *ps : phase[p]) {
+                    issue_pass(*ps, q, true);
+                    mark(stream_, q, q + 1);
+                }
+                if (xafter[p]) {
+                    wait_for(xstream_, q);
+                    {
+                        TraceScope ts(*this, 2, xstream_);
+                        comm_exchange(comm_.get(), d_state_, peers_, dtype_, n_sub, to_jl(*xafter[p]), xstream_,
+                                      1, x_sms, true, size_t(q) * sub_bytes);
+                    }
+                    mark(xstream_, q, q + 1);
+                }
+            }
+        }
+        for (int p = 0; p < P; p++) {
+            for (size_t k = 0; k < phase[p].size(); k++)
+                count_pass();
+            if (xafter[p]) {
+                comm_count_exchange(comm_.get());
+                advance_layout(*xafter[p]);
+            }
+        }
+        i = j;
+    }
+    for (int s = 0; s < Q; s++) // whatever follows on the state's stream sees the finished state
+        wait_for(stream_, s);
+    for (cudaEvent_t ev : events)
+        cudaEventDestroy(ev);
 }
 
 // ---- gates ----------------------------------------------------------------------------------------

@@ -152,6 +152,12 @@ class State {
     SchedConfig sched_config() const;
     void run_local(const std::vector<Prim> &prims);       // prims in PHYSICAL bits, all targets local
     void apply_prims_sharded(std::vector<Prim> prims);    // prims in logical bits
+    // pipelined execution of a sharded plan: the shard is cut into 2^c slices by its top c local
+    // bits; passes whose tile holds none of those bits and the exchanges run slice by slice, passes
+    // on the state's stream and exchanges on a second one, so that the NVLink transfer of one slice
+    // overlaps the HBM passes over the others
+    void run_sharded_pipelined(const std::vector<struct ShardStep> &steps, int c);
+    int pipeline_bits() const;
     // rank-bit positions <-> local positions, all pairs in ONE exchange
     void exchange_phys(const std::vector<std::pair<int, int>> &pairs) const;
     int exchange_ctas() const;
@@ -181,6 +187,7 @@ class State {
     bool fuse_ = true;
     void *d_state_ = nullptr;
     cudaStream_t stream_ = nullptr;
+    mutable cudaStream_t xstream_ = nullptr; // exchanges of pipelined sharded runs
     size_t last_upload_bytes_ = 0; // descriptor bytes handed to the device by the last apply
     // reductions
     double *d_partials_ = nullptr, *d_out_ = nullptr, *h_out_ = nullptr;

@@ -4,7 +4,7 @@
 namespace b2sv {
 
 void launch_tile_pass_c64(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
-                          cudaStream_t stream); // tile_kernel_c64.cu
+                          cudaStream_t stream, int max_ctas); // tile_kernel_c64.cu
 
 // Tile geometry per dtype: complex128 -> 2^12 amps (64 KiB), complex64 -> 2^13 amps (64 KiB);
 // three buffers per CTA (192 KiB of the 227 KiB an sm_100 CTA may use).
@@ -14,11 +14,11 @@ void tile_config(int dtype, int *B, int *R) {
 }
 
 void launch_tile_pass(int dtype, void *state, const PassParams &pp, int n_eff,
-                      uint64_t rank_bits, cudaStream_t stream) {
+                      uint64_t rank_bits, cudaStream_t stream, int max_ctas) {
     if (dtype == 1)
-        launch_tile_pass_t<double, 12, 4>(state, pp, n_eff, rank_bits, stream);
+        launch_tile_pass_t<double, 12, 4>(state, pp, n_eff, rank_bits, stream, max_ctas);
     else
-        launch_tile_pass_c64(state, pp, n_eff, rank_bits, stream);
+        launch_tile_pass_c64(state, pp, n_eff, rank_bits, stream, max_ctas);
 }
 
 // Reads and clears the phase timers (zeros unless B2SV_TILE_PROF=1; complex128 kernels only).

@@ -836,7 +836,7 @@ bool tile_prof() {
 template <typename real, int B, int R, int GT, int NG, int NB, bool FACT, bool INTERP, bool DENSEK,
           bool PROF>
 void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, int max_ctas) {
     using amp_t = typename AmpT<real>::type;
     auto kern = tile_exec_kernel<real, B, R, GT, NG, NB, FACT, INTERP, DENSEK, PROF>;
     constexpr size_t smem = tile_smem_bytes<real, B, NB>();
@@ -846,7 +846,9 @@ void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_
                                         static_cast<int>(smem)));
     const uint32_t n_tiles = 1u << (n_eff - B);
     // one persistent CTA per SM; with fewer than 2 tiles per SM spread them one per CTA
-    const unsigned grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(sm_count()));
+    // (max_ctas > 0: leave SMs to a kernel running beside this one, e.g. an exchange between shards)
+    const unsigned grid = std::min<uint32_t>(
+        n_tiles, static_cast<uint32_t>(max_ctas > 0 ? std::min(max_ctas, sm_count()) : sm_count()));
     // the descriptor is copied into the launch's parameter buffer by the runtime at this call
     constexpr int nthreads = NG * GT + kLoadThreads;
     static const uint32_t flags = static_cast<uint32_t>(env_int("B2SV_TILE_FLAGS", 0));
@@ -857,7 +859,7 @@ void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_
 // Picks the leanest kernel variant that covers the rounds of the pass.
 template <typename real, int B, int R>
 void launch_tile_pass_t(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int max_ctas) {
     bool fact = false, interp = false, densek = false;
     for (int rd = 0; rd < pp.hdr.n_rounds; rd++) {
         const int kind = pp.hdr.round_kind[rd];
@@ -866,15 +868,15 @@ void launch_tile_pass_t(void *state, const PassParams &pp, int n_eff, uint64_t r
         densek |= kind >= 2 && kind < 8;
     }
     if (tile_prof())
-        launch_variant<real, B, R, 256, 2, 3, true, true, true, true>(state, pp, n_eff, rank_bits, stream);
+        launch_variant<real, B, R, 256, 2, 3, true, true, true, true>(state, pp, n_eff, rank_bits, stream, max_ctas);
     else if (fact && !interp && !densek) // layered circuits: factored rounds (+ single gates)
-        launch_variant<real, B, R, 256, 2, 3, true, false, false, false>(state, pp, n_eff, rank_bits, stream);
+        launch_variant<real, B, R, 256, 2, 3, true, false, false, false>(state, pp, n_eff, rank_bits, stream, max_ctas);
     else if (!fact && !interp)           // unfactored dense rounds, single gates, permutation-only passes
-        launch_variant<real, B, R, 256, 2, 3, false, false, true, false>(state, pp, n_eff, rank_bits, stream);
+        launch_variant<real, B, R, 256, 2, 3, false, false, true, false>(state, pp, n_eff, rank_bits, stream, max_ctas);
     else if (!fact)                      // controlled / diagonal ops through the interpreter
-        launch_variant<real, B, R, 256, 2, 3, false, true, true, false>(state, pp, n_eff, rank_bits, stream);
+        launch_variant<real, B, R, 256, 2, 3, false, true, true, false>(state, pp, n_eff, rank_bits, stream, max_ctas);
     else
-        launch_variant<real, B, R, 256, 2, 3, true, true, true, false>(state, pp, n_eff, rank_bits, stream);
+        launch_variant<real, B, R, 256, 2, 3, true, true, true, false>(state, pp, n_eff, rank_bits, stream, max_ctas);
 }
 } // namespace
 

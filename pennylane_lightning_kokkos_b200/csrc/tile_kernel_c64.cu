@@ -4,8 +4,8 @@
 namespace b2sv {
 
 void launch_tile_pass_c64(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
-                          cudaStream_t stream) {
-    launch_tile_pass_t<float, 13, 5>(state, pp, n_eff, rank_bits, stream);
+                          cudaStream_t stream, int max_ctas) {
+    launch_tile_pass_t<float, 13, 5>(state, pp, n_eff, rank_bits, stream, max_ctas);
 }
 
 } // namespace b2sv

@@ -32,14 +32,27 @@ def main():
     g = world.bit_length() - 1
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 12 + 2 * g + 1
     worst = 0.0
-    for dtype, tol in ((np.complex128, 1e-12), (np.complex64, 1e-5)):
-        n_eff = n if dtype == np.complex128 else n + 1
-        for case, circ in (("layers", layered_circuit(n_eff, 2, seed=3)),
+    sliced_runs = 0
+    # every case twice: whole-shard execution, and the pipelined path (shard cut into 4 slices, exchanges
+    # on a second stream) forced on these small states through B2SV_PIPE_MIN_SUB
+    for mode, dtype, tol in (("plain", np.complex128, 1e-12), ("plain", np.complex64, 1e-5),
+                             ("sliced", np.complex128, 1e-12), ("sliced", np.complex64, 1e-5)):
+        if mode == "sliced":
+            os.environ["B2SV_PIPE_MIN_SUB"] = "0"
+            n_eff = 18 + g + (0 if dtype == np.complex128 else 1)
+        else:
+            os.environ.pop("B2SV_PIPE_MIN_SUB", None)
+            n_eff = n if dtype == np.complex128 else n + 1
+        for case, circ in (("layers", layered_circuit(n_eff, 3 if mode == "sliced" else 2, seed=3)),
                            ("random", random_circuit(n_eff, 120, seed=5))):
             sv = b2dist.create_sharded_state(ops, n_eff, dtype, local_rank)
+            sv.reset_stats()
             sv.apply([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ],
                      [c[3] for c in circ])
             stats = sv.comm_stats()
+            st = sv.stats()
+            if st["launches"] > st["sweeps"]:
+                sliced_runs += 1
             # expectation values before normalising the layout (exercise the remapped reductions)
             ez = [sv.ExpectationValue("PauliZ", [w], [], np.zeros(0)) for w in (0, g, n_eff - 1)]
             ex = [sv.ExpectationValue("PauliX", [w], [], np.zeros(0)) for w in (0, n_eff - 1)]
@@ -59,7 +72,7 @@ def main():
             e2 = max(abs(a - b) for a, b in zip(ez + ex, ez_want + ex_want))
             worst = max(worst, err / tol, e2 / tol)
             if rank == 0:
-                print(f"  {case} {np.dtype(dtype).name} n={n_eff} world={world}: amp err {err:.2e} "
+                print(f"  {mode} {case} {np.dtype(dtype).name} n={n_eff} world={world}: amp err {err:.2e} "
                       f"expval err {e2:.2e} swaps {stats['swaps']} path {stats['path']}", flush=True)
             assert err < tol and e2 < tol, (case, dtype, err, e2)
             # marginal probabilities over global + local wires (all-reduced histograms) and sampling
@@ -90,6 +103,8 @@ def main():
                 del single
             del sv
             dist.barrier()
+    os.environ.pop("B2SV_PIPE_MIN_SUB", None)
+    assert sliced_runs >= 2, f"the pipelined path never ran ({sliced_runs})"
     # adjoint Jacobian on a sharded state (all-reduced inner products)
     n_a = 12 + 2 * g
     circ = [c for c in layered_circuit(n_a, 1, seed=7)]
@@ -114,7 +129,8 @@ def main():
     del sv
     dist.barrier()
     if rank == 0:
-        print(f"MGPU_OK world={world} worst_err_over_tol={worst:.3f} adjoint_rel_err={ej:.2e}", flush=True)
+        print(f"MGPU_OK world={world} worst_err_over_tol={worst:.3f} adjoint_rel_err={ej:.2e} "
+              f"sliced_runs={sliced_runs}", flush=True)
     dist.destroy_process_group()
 
 
