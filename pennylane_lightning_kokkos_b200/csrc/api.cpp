@@ -336,6 +336,7 @@ int b2sv_plan_ops(const b2sv_ops *ops, int num_qubits, int dtype, uint64_t *pass
         cfg.f32 = dtype != 1;
         cfg.n_local = num_qubits;
         cfg.n_alloc = std::max(num_qubits, cfg.B);
+        cfg.low = default_tile_low();
         uint64_t np = 0, nr = 0, na = 0, nabs = 0, nf = 0;
         if (!prims.empty())
             for (const Pass &ps : build_schedule(prims, cfg)) {
@@ -400,6 +401,7 @@ int b2sv_plan_sharded(const b2sv_ops *ops, int num_qubits, int world, int dtype,
         cfg.f32 = dtype != 1;
         cfg.n_local = pc.n_local;
         cfg.n_alloc = std::max(pc.n_local, cfg.B);
+        cfg.low = default_tile_low();
         uint64_t st[5] = {0, 0, 0, 0, 0};
         std::ostringstream os;
         os << std::setprecision(17);

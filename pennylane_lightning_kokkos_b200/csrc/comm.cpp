@@ -234,12 +234,14 @@ void comm_unmap_peers(Comm *c, std::vector<void *> &ptrs) {
 // One exchange of k rank bits with k local bits (all-to-all inside the 2^k-rank group), in place.
 void comm_exchange(Comm *c, void *data, const std::vector<void *> &peers, int dtype, int n_local,
                    const std::vector<std::pair<int, int>> &jl, cudaStream_t st, int channel,
-                   int max_ctas, bool fat, size_t sub_offset_bytes) {
+                   int max_ctas, bool fat, uint64_t slice_mask, uint64_t slice_value) {
     CUDA_CHECK(cudaSetDevice(c->device));
     const int k = static_cast<int>(jl.size());
     if (k == 0)
         return;
-    bool peer_ok = c->use_peer && k <= kMaxExchangeBits && n_local - k - 1 >= 0;
+    const int n_slice = __builtin_popcountll(slice_mask);
+    bool peer_ok = c->use_peer && k <= kMaxExchangeBits && n_slice <= 4 && n_local - k - 1 - n_slice >= 0;
+    B2_ASSERT(peer_ok || slice_mask == 0);
     for (int r = 0; r < c->world && peer_ok; r++)
         peer_ok = peers[r] != nullptr;
     if (!peer_ok) { // NCCL path: one bit at a time through the staging buffer
@@ -250,7 +252,7 @@ void comm_exchange(Comm *c, void *data, const std::vector<void *> &peers, int dt
     const size_t ab = dtype == 1 ? 16 : 8;
     if (channel == 0) // exchanges done slice by slice are counted by the caller (comm_count_exchange)
         c->swaps++;
-    c->swap_bytes += ((uint64_t(1) << n_local) - (uint64_t(1) << (n_local - k))) * ab;
+    c->swap_bytes += ((uint64_t(1) << (n_local - n_slice)) - (uint64_t(1) << (n_local - n_slice - k))) * ab;
     ExchangeParams p{};
     p.k = k;
     p.n_local = n_local;
@@ -260,15 +262,17 @@ void comm_exchange(Comm *c, void *data, const std::vector<void *> &peers, int dt
         lmask |= bit(jl[i].second);
         p.a |= static_cast<uint32_t>((c->rank >> jl[i].first) & 1) << i;
     }
-    // selector: the highest local bit that is not exchanged (keeps warps on contiguous runs)
+    // selector: the highest local bit that is neither exchanged nor a slice bit
     p.selbit = n_local - 1;
-    while (lmask & bit(p.selbit))
+    while (p.selbit >= 0 && ((lmask | slice_mask) & bit(p.selbit)))
         p.selbit--;
-    B2_ASSERT(p.selbit >= 0);
-    const uint64_t fix = lmask | bit(p.selbit);
+    B2_ASSERT(p.selbit >= 0 && (lmask & slice_mask) == 0);
+    const uint64_t fix = lmask | bit(p.selbit) | slice_mask;
     for (int b = 0; b < n_local; b++)
         if (fix & bit(b))
             p.fixpos[p.nfix++] = b;
+    p.nfree = n_local - p.nfix;
+    const size_t sub_offset_bytes = static_cast<size_t>(slice_value) * ab; // slice bits as an index offset
     for (uint32_t b = 0; b < (1u << k); b++) {
         int r = c->rank;
         for (int i = 0; i < k; i++)

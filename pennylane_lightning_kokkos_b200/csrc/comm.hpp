@@ -34,8 +34,9 @@ void comm_swap_bits(Comm *c, void *data, const std::vector<void *> &peers, int d
 // jl[i] = (rank bit j_i, local bit l_i). max_ctas bounds the SMs the exchange kernel may occupy.
 void comm_exchange(Comm *c, void *data, const std::vector<void *> &peers, int dtype, int n_local,
                    const std::vector<std::pair<int, int>> &jl, cudaStream_t stream, int channel,
-                   int max_ctas, bool fat = false, size_t sub_offset_bytes = 0);
-// (n_local and sub_offset_bytes may describe a sub-range of every shard: the same slice on all ranks)
+                   int max_ctas, bool fat = false, uint64_t slice_mask = 0, uint64_t slice_value = 0);
+// (slice_mask / slice_value: work only on the amplitudes whose local index has these bits at these
+//  values -- the same slice of every shard; the caller walks the slices)
 void comm_stats(const Comm *c, uint64_t *swaps, uint64_t *bytes);
 void comm_reset_stats(Comm *c);
 void comm_count_exchange(Comm *c);

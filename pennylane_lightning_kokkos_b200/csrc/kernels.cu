@@ -898,7 +898,7 @@ __global__ void __launch_bounds__(T)
 }
 void launch_exchange(int dtype, void *mine, const ExchangeParams &p, int max_ctas, bool fat,
                      cudaStream_t st) {
-    const uint64_t nrest = uint64_t(1) << (p.n_local - p.k - 1);
+    const uint64_t nrest = uint64_t(1) << p.nfree;
     const uint64_t per_chunk = (fat ? 1024 : 256) * 4;
     const uint64_t nchunks = (nrest + per_chunk - 1) / per_chunk;
     const uint64_t work = nchunks * ((uint64_t(1) << p.k) - 1);

@@ -45,8 +45,10 @@ constexpr int kMaxExchangeBits = 4;
 struct ExchangeParams {
     int k;                          // bits exchanged (1..kMaxExchangeBits)
     int n_local;                    // local index bits
-    int nfix;                       // k + 1
-    int fixpos[kMaxExchangeBits + 1]; // the k local bits and the selector bit, ascending
+    int nfix;                       // k + 1 + number of slice bits
+    int nfree;                      // local index bits that are enumerated: n_local - nfix
+    int fixpos[kMaxExchangeBits + 1 + 4]; // the k local bits, the selector bit and the bits that select
+                                    // the slice of the shard this launch works on, ascending
     int lpos[kMaxExchangeBits];     // local bit paired with group-value bit i
     int selbit;                     // which half of a pair of sub-blocks this rank moves
     uint32_t a;                     // this rank's value on the k rank bits

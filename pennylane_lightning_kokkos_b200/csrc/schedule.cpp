@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace b2sv {
@@ -299,6 +300,38 @@ DevOp make_devop(const Prim &p, const uint8_t *tile_bits, int B, const uint8_t *
 
 } // namespace
 
+// tile-id deposit segments: one per run of consecutive index bits below `top` that are not excluded
+void fill_tile_id_segments(DevPassHeader &hdr, uint64_t excluded_mask, int top) {
+    int n_seg = 0, id_bit = 0, below = 0; // below = excluded bits under the current position
+    int b = 0;
+    while (b < top) {
+        if (excluded_mask & bit(b)) {
+            below++;
+            b++;
+            continue;
+        }
+        int len = 0;
+        while (b + len < top && !(excluded_mask & bit(b + len)))
+            len++;
+        B2_ASSERT(n_seg <= kMaxTileBits);
+        hdr.seg_mask[n_seg] = static_cast<uint32_t>(((uint64_t(1) << len) - 1) << id_bit);
+        hdr.seg_shift[n_seg] = static_cast<uint8_t>(below);
+        n_seg++;
+        id_bit += len;
+        b += len;
+    }
+    for (int k = n_seg; k <= kMaxTileBits; k++) {
+        hdr.seg_mask[k] = 0;
+        hdr.seg_shift[k] = 0;
+    }
+    hdr.n_seg = static_cast<uint8_t>(n_seg);
+}
+
+int default_tile_low() {
+    const char *e = getenv("B2SV_TILE_LOW"); // read on every call: experiments sweep it
+    return e ? std::max(2, std::min(6, atoi(e))) : kDefaultTileLow;
+}
+
 double schedule_cost(const std::vector<Pass> &passes) {
     // measured (profiles/r1_tile_ablation.md): 1 round 6.3-6.6 ms, +0.8-1.0 ms per further round
     double c = 0.0;
@@ -496,28 +529,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                     off |= bit(ps.hdr.tile_bits[j]);
             ps.hdr.load_off[e] = off;
         }
-        { // tile-id deposit segments: runs of consecutive non-tile bits
-            int n_seg = 0, id_bit = 0, below = 0; // below = tile bits under the current position
-            const int top = std::max(cfg.n_alloc, cfg.n_local);
-            int b = 0;
-            while (b < top) {
-                if (tile_mask & bit(b)) {
-                    below++;
-                    b++;
-                    continue;
-                }
-                int len = 0;
-                while (b + len < top && !(tile_mask & bit(b + len)))
-                    len++;
-                B2_ASSERT(n_seg <= kMaxTileBits);
-                ps.hdr.seg_mask[n_seg] = static_cast<uint32_t>(((uint64_t(1) << len) - 1) << id_bit);
-                ps.hdr.seg_shift[n_seg] = static_cast<uint8_t>(below);
-                n_seg++;
-                id_bit += len;
-                b += len;
-            }
-            ps.hdr.n_seg = static_cast<uint8_t>(n_seg);
-        }
+        fill_tile_id_segments(ps.hdr, tile_mask, std::max(cfg.n_alloc, cfg.n_local));
         // ---- rounds, with permutation primitives folded into the address map at round boundaries
         uint32_t Mcol[kMaxTileBits]; // storage index (before the swizzle) of logical basis vector e_j
         uint32_t McolLast[kMaxTileBits] = {0}; // Mcol as the most recent round saw it

@@ -23,7 +23,8 @@ constexpr int kMaxTileBits = 16;
 constexpr int kMaxRegBits = 5;
 constexpr int kMaxFreeBits = 12; // tile bits that are not register bits (= log2 threads)
 constexpr int kMaxCx = 32;       // conditional address toggles per pass
-constexpr int kMaxDense = 6;     // rounds 0 .. kMaxDense-1 of a pass may run in factored form
+constexpr int kMaxDense = 6;
+constexpr int kDefaultTileLow = 5; // 512-byte HBM runs (complex128)     // rounds 0 .. kMaxDense-1 of a pass may run in factored form
 
 enum OpKind : uint8_t { KIND_GENERAL = 0, KIND_REAL = 1, KIND_PERM = 2, KIND_DIAG = 3 };
 // flag bits stored in DevOp::kind above the OpKind
@@ -145,6 +146,9 @@ struct SchedConfig {
     bool lookahead = false;
 };
 
+// contiguous low index bits kept in every tile (2^low amplitudes per HBM run); B2SV_TILE_LOW overrides
+int default_tile_low();
+
 // Shared-memory swizzle (same function as tile_kernel.cu phys<B,SW>): XOR-folds every higher
 // SW-bit group of the index into its low SW bits. GF(2)-linear.
 inline uint32_t phys_slot(uint32_t i, int B, int SW) {
@@ -158,6 +162,10 @@ inline uint32_t phys_slot(uint32_t i, int B, int SW) {
 std::vector<Prim> fuse_single_qubit(const std::vector<Prim> &prims);
 // Main entry.
 std::vector<Pass> build_schedule(const std::vector<Prim> &prims, const SchedConfig &cfg);
+// Tile id -> index of the tile's first amplitude: the id's bits are deposited into the index bits
+// below `top` that are not in `excluded_mask` (the tile bits; for a pass over one slice of a shard
+// also the bits that select the slice, whose values then come with the base pointer).
+void fill_tile_id_segments(DevPassHeader &hdr, uint64_t excluded_mask, int top);
 // Cost model (arbitrary units, fitted on 30-qubit complex128 sweeps on a B200): a pass costs what
 // streaming the state costs, plus a smaller amount for every register round it runs on the tile.
 double schedule_cost(const std::vector<Pass> &passes);

@@ -21,15 +21,6 @@ void order_after(cudaStream_t waiter, cudaStream_t signaler) {
     CUDA_CHECK(cudaStreamWaitEvent(waiter, ev, 0));
     CUDA_CHECK(cudaEventDestroy(ev));
 }
-// contiguous low index bits kept in every tile (2^low amplitudes per HBM run); B2SV_TILE_LOW overrides
-int tile_low_bits() {
-    static int low = 0;
-    if (!low) {
-        const char *e = getenv("B2SV_TILE_LOW");
-        low = e ? std::max(2, std::min(6, atoi(e))) : 5;
-    }
-    return low;
-}
 int log2_exact(int x) {
     int g = 0;
     while ((1 << g) < x)
@@ -490,7 +481,6 @@ ShardPlanConfig State::shard_plan_config() const {
     cfg.n = n_;
     cfg.n_local = n_local_;
     cfg.min_victim_pos = std::min(5, std::max(0, n_local_ - gbits_ - 1));
-    cfg.max_victim_pos = n_local_ - pipeline_bits();
     if (const char *e = getenv("B2SV_EXCHANGE_BATCH"))
         cfg.batch = atoi(e) != 0;
     return cfg;
@@ -596,15 +586,20 @@ int State::pipeline_bits() const {
     return c;
 }
 
+// Pipelined execution of a sharded plan. Around every exchange a REGION of tasks is formed: the
+// exchange(s) and the tile passes next to them that leave at least c local index bits untouched
+// (not in their tile, not exchanged). Those c bits cut the shard into 2^c slices; inside the region
+// every task runs slice by slice -- passes on the state's stream, exchanges on a second stream --
+// in skewed order (slice q runs phase p at step q + p), so the NVLink transfer of one slice is in
+// flight while the HBM passes of the neighbouring slices run. The slice bits are chosen per region,
+// so the pass that needs a given qubit never has to wait for a whole-shard exchange next to it.
+// Tasks outside regions are whole-shard launches on the state's stream.
 void State::run_sharded_pipelined(const std::vector<ShardStep> &steps, int c) {
     const int Q = 1 << c;
-    const int n_sub = n_local_ - c;
-    const uint64_t selmask = (bit(n_local_) - 1) & ~(bit(n_sub) - 1);
     const uint64_t rank_bits = uint64_t(rank_) << n_local_;
-    const size_t sub_bytes = (size_t(1) << n_sub) * amp_bytes();
     if (!xstream_)
         CUDA_CHECK(cudaStreamCreateWithFlags(&xstream_, cudaStreamNonBlocking));
-    int x_sms = 20; // SMs the exchange kernel occupies while tile passes run beside it
+    int x_sms = 16; // SMs the exchange kernel occupies while tile passes run beside it
     if (const char *e = getenv("B2SV_EXCHANGE_SMS"))
         x_sms = std::max(4, std::min(64, atoi(e)));
     const int pass_ctas = sm_count_current_device() - x_sms;
@@ -613,54 +608,113 @@ void State::run_sharded_pipelined(const std::vector<ShardStep> &steps, int c) {
     struct Task {
         const Pass *pass = nullptr;      // tile pass / generic-matrix pass
         const ShardStep *xchg = nullptr; // exchange
-        bool split = false;
+        uint64_t bits = 0;               // local index bits the task must see whole
+        int region = -1;
     };
     std::vector<std::vector<Pass>> schedules;
     schedules.reserve(steps.size());
     std::vector<Task> tasks;
     const SchedConfig cfg = sched_config();
+    const uint64_t all_local = bit(n_local_) - 1;
     for (const ShardStep &stp : steps) {
         Task t;
         if (stp.is_exchange) {
             t.xchg = &stp;
-            t.split = true;
             for (const auto &pr : stp.swaps)
-                t.split = t.split && !(selmask & bit(pr.second));
+                t.bits |= bit(pr.second);
             tasks.push_back(t);
             continue;
         }
         schedules.push_back(build_schedule(stp.prims, cfg));
         for (const Pass &ps : schedules.back()) {
             t.pass = &ps;
-            t.split = false;
+            t.bits = all_local; // generic-matrix kernels are never sliced
             if (!ps.is_matk) {
-                uint64_t tile_mask = 0;
+                t.bits = 0;
                 for (int j = 0; j < B_; j++)
-                    tile_mask |= bit(ps.hdr.tile_bits[j]);
-                t.split = (tile_mask & selmask) == 0;
+                    t.bits |= bit(ps.hdr.tile_bits[j]);
             }
             tasks.push_back(t);
         }
     }
+    // ---- regions
+    struct Region {
+        size_t begin, end;
+        uint64_t slice_mask;
+    };
+    std::vector<Region> regions;
+    {
+        // slice bits above the contiguous low bits every tile holds: a slice is made of whole runs
+        const int min_slice_pos = std::min(cfg.low, std::max(0, n_local_ - c - 1));
+        const uint64_t cand0 = all_local & ~(bit(min_slice_pos) - 1);
+        constexpr int kMaxSide = 5; // passes taken on either side of an exchange
+        size_t prev_end = 0;
+        for (size_t x = 0; x < tasks.size(); x++) {
+            if (!tasks[x].xchg || tasks[x].region >= 0)
+                continue;
+            uint64_t mask = cand0 & ~tasks[x].bits;
+            if (__builtin_popcountll(mask) < c)
+                continue;
+            size_t lo = x, hi = x + 1;
+            int left_n = 0, right_n = 0;
+            bool progress = true;
+            while (progress) {
+                progress = false;
+                if (hi < tasks.size() && right_n < kMaxSide) {
+                    const uint64_t m2 = mask & ~tasks[hi].bits;
+                    if (__builtin_popcountll(m2) >= c) {
+                        mask = m2;
+                        right_n = tasks[hi].xchg ? 0 : right_n + 1;
+                        hi++;
+                        progress = true;
+                    } else {
+                        right_n = kMaxSide;
+                    }
+                }
+                if (lo > prev_end && left_n < kMaxSide && !tasks[lo - 1].xchg) {
+                    const uint64_t m2 = mask & ~tasks[lo - 1].bits;
+                    if (__builtin_popcountll(m2) >= c) {
+                        mask = m2;
+                        left_n++;
+                        lo--;
+                        progress = true;
+                    } else {
+                        left_n = kMaxSide;
+                    }
+                }
+            }
+            // drop trailing passes that follow the last exchange by more than kMaxSide (none by
+            // construction) and keep the c highest remaining bits as the slice bits
+            uint64_t slice = 0;
+            for (int b = n_local_ - 1, k = 0; b >= 0 && k < c; b--)
+                if (mask & bit(b)) {
+                    slice |= bit(b);
+                    k++;
+                }
+            for (size_t t = lo; t < hi; t++)
+                tasks[t].region = static_cast<int>(regions.size());
+            regions.push_back({lo, hi, slice});
+            prev_end = hi;
+        }
+    }
 
-    // ---- issue machinery: which event guards each slice, and on which stream it was recorded
+    // ---- issue machinery
     std::vector<cudaEvent_t> events;
     struct Guard {
         cudaEvent_t ev = nullptr;
         cudaStream_t st = nullptr;
     };
     std::vector<Guard> last(Q);
-    auto wait_for = [&](cudaStream_t st, int q) {
-        if (last[q].ev && last[q].st != st)
-            CUDA_CHECK(cudaStreamWaitEvent(st, last[q].ev, 0));
-    };
-    auto mark = [&](cudaStream_t st, int q0, int q1) {
+    auto new_event = [&](cudaStream_t st) {
         cudaEvent_t ev;
         CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventRecord(ev, st));
         events.push_back(ev);
-        for (int q = q0; q < q1; q++)
-            last[q] = {ev, st};
+        return ev;
+    };
+    auto wait_for = [&](cudaStream_t st, int q) {
+        if (last[q].ev && last[q].st != st)
+            CUDA_CHECK(cudaStreamWaitEvent(st, last[q].ev, 0));
     };
     auto params = std::make_unique<PassParams>();
     auto load_params = [&](const Pass &ps) {
@@ -669,32 +723,16 @@ void State::run_sharded_pipelined(const std::vector<ShardStep> &steps, int c) {
         if (!ps.dense.empty())
             std::memcpy(params->dense, ps.dense.data(), sizeof(DevDense) * ps.dense.size());
     };
-    // a tile pass over slice q (q < 0: the whole shard)
-    auto issue_pass = [&](const Pass &ps, int q, bool beside_exchange) {
-        if (ps.is_matk) {
-            B2_ASSERT(q < 0);
-            for (int s = 0; s < Q; s++)
-                wait_for(stream_, s);
-            upload_and_run(std::vector<Pass>{ps});
-            mark(stream_, 0, Q);
-            return;
-        }
-        load_params(ps);
-        TraceScope ts(*this, 0);
-        if (q < 0) {
-            for (int s = 0; s < Q; s++)
-                wait_for(stream_, s);
-            launch_tile_pass(dtype_, d_state_, *params, n_local_, rank_bits, stream_, 0);
-        } else {
-            wait_for(stream_, q);
-            launch_tile_pass(dtype_, static_cast<char *>(d_state_) + size_t(q) * sub_bytes, *params, n_sub,
-                             rank_bits | (uint64_t(q) << n_sub), stream_, beside_exchange ? pass_ctas : 0);
-        }
-        launches++;
-    };
-    auto count_pass = [&]() {
-        sweeps++;
-        bytes_moved += 2 * state_bytes();
+    auto deposit = [&](int q, uint64_t slice_mask) { // slice number -> index offset
+        uint64_t v = 0;
+        int k = 0;
+        for (int b = 0; b < n_local_; b++)
+            if (slice_mask & bit(b)) {
+                if ((q >> k) & 1)
+                    v |= bit(b);
+                k++;
+            }
+        return v;
     };
     auto to_jl = [&](const ShardStep &x) {
         std::vector<std::pair<int, int>> jl;
@@ -712,41 +750,20 @@ void State::run_sharded_pipelined(const std::vector<ShardStep> &steps, int c) {
 
     size_t i = 0;
     while (i < tasks.size()) {
-        if (!tasks[i].split) { // a pass that needs the whole shard (or an exchange that cannot be cut)
-            if (tasks[i].pass) {
-                issue_pass(*tasks[i].pass, -1, false);
-                if (!tasks[i].pass->is_matk) {
-                    mark(stream_, 0, Q);
-                    count_pass();
-                }
-            } else {
-                for (int s = 0; s < Q; s++)
-                    wait_for(stream_, s);
-                exchange_phys(tasks[i].xchg->swaps); // sequential, on the state's stream
-                mark(stream_, 0, Q);
-            }
+        if (tasks[i].region < 0) { // whole-shard launch on the state's stream
+            if (tasks[i].pass)
+                upload_and_run(std::vector<Pass>{*tasks[i].pass});
+            else
+                exchange_phys(tasks[i].xchg->swaps);
             i++;
             continue;
         }
-        size_t j = i;
-        bool has_exchange = false;
-        while (j < tasks.size() && tasks[j].split) {
-            has_exchange = has_exchange || tasks[j].xchg != nullptr;
-            j++;
-        }
-        if (!has_exchange) { // nothing to overlap with: whole-shard launches
-            for (; i < j; i++) {
-                issue_pass(*tasks[i].pass, -1, false);
-                mark(stream_, 0, Q);
-                count_pass();
-            }
-            continue;
-        }
-        // phases of passes separated by exchanges; slice q runs phase p at step q + p (skewed), so the
-        // exchange of a slice is in flight while the passes of the neighbouring slices run
+        const Region &rg = regions[tasks[i].region];
+        B2_ASSERT(rg.begin == i);
+        // phases of passes separated by exchanges
         std::vector<std::vector<const Pass *>> phase(1);
         std::vector<const ShardStep *> xafter; // exchange that follows phase p (nullptr for the last)
-        for (size_t t = i; t < j; t++) {
+        for (size_t t = rg.begin; t < rg.end; t++) {
             if (tasks[t].xchg) {
                 xafter.push_back(tasks[t].xchg);
                 phase.emplace_back();
@@ -756,39 +773,56 @@ void State::run_sharded_pipelined(const std::vector<ShardStep> &steps, int c) {
         }
         xafter.push_back(nullptr);
         const int P = static_cast<int>(phase.size());
+        { // everything queued so far precedes every slice of the region
+            cudaEvent_t e0 = new_event(stream_);
+            for (int q = 0; q < Q; q++)
+                last[q] = {e0, stream_};
+        }
         for (int step = 0; step < Q + P - 1; step++) {
             for (int p = 0; p < P; p++) { // earlier phases first: their passes cover the exchange the
                                           // later phase of the neighbouring slice is waiting for
                 const int q = step - p;
                 if (q < 0 || q >= Q)
                     continue;
+                const uint64_t off = deposit(q, rg.slice_mask);
                 for (const Pass *ps : phase[p]) {
-                    issue_pass(*ps, q, true);
-                    mark(stream_, q, q + 1);
+                    load_params(*ps);
+                    uint64_t tile_mask = 0;
+                    for (int j = 0; j < B_; j++)
+                        tile_mask |= bit(ps->hdr.tile_bits[j]);
+                    fill_tile_id_segments(params->hdr, tile_mask | rg.slice_mask, n_local_);
+                    wait_for(stream_, q);
+                    {
+                        TraceScope ts(*this, 0);
+                        launch_tile_pass(dtype_, static_cast<char *>(d_state_) + off * amp_bytes(), *params,
+                                         n_local_ - c, rank_bits | off, stream_, pass_ctas);
+                    }
+                    launches++;
+                    last[q] = {new_event(stream_), stream_};
                 }
                 if (xafter[p]) {
                     wait_for(xstream_, q);
                     {
                         TraceScope ts(*this, 2, xstream_);
-                        comm_exchange(comm_.get(), d_state_, peers_, dtype_, n_sub, to_jl(*xafter[p]), xstream_,
-                                      1, x_sms, true, size_t(q) * sub_bytes);
+                        comm_exchange(comm_.get(), d_state_, peers_, dtype_, n_local_, to_jl(*xafter[p]),
+                                      xstream_, 1, x_sms, true, rg.slice_mask, off);
                     }
-                    mark(xstream_, q, q + 1);
+                    last[q] = {new_event(xstream_), xstream_};
                 }
             }
         }
+        for (int q = 0; q < Q; q++) // whatever follows on the state's stream sees the finished region
+            wait_for(stream_, q);
         for (int p = 0; p < P; p++) {
-            for (size_t k = 0; k < phase[p].size(); k++)
-                count_pass();
+            sweeps += phase[p].size();
+            bytes_moved += 2 * state_bytes() * phase[p].size();
             if (xafter[p]) {
                 comm_count_exchange(comm_.get());
                 advance_layout(*xafter[p]);
             }
         }
-        i = j;
+        i = rg.end;
     }
-    for (int s = 0; s < Q; s++) // whatever follows on the state's stream sees the finished state
-        wait_for(stream_, s);
     for (cudaEvent_t ev : events)
         cudaEventDestroy(ev);
 }
@@ -883,7 +917,7 @@ SchedConfig State::sched_config() const {
     SchedConfig cfg;
     cfg.B = B_;
     cfg.R = R_;
-    cfg.low = tile_low_bits();
+    cfg.low = default_tile_low();
     if (const char *e = getenv("B2SV_MAX_HEAVY"))
         cfg.max_heavy = std::max(1, atoi(e));
     cfg.SW = dtype_ == 1 ? 3 : 4;
