@@ -295,7 +295,7 @@ def sharded_parity(ops, b2dist, dist, torch, local_rank, world):
     g = world.bit_length() - 1
     worst, cases = 0.0, []
     for n, circ, tag in ((16 + g, layered_circuit(16 + g, 2, seed=3), "layers"),
-                         (14 + g, random_circuit(14 + g, 120, seed=5), "random"),
+                         (13 + 2 * g, random_circuit(13 + 2 * g, 120, seed=5), "random"),
                          (19 + g, layered_circuit(19 + g, 3, seed=8), "layers, sliced + overlapped")):
         # the last case forces the pipelined path (shard cut into slices, exchanges on a second
         # stream beside the passes) that the timed 30-qubit-per-GPU run takes

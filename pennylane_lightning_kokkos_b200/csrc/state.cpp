@@ -599,10 +599,14 @@ void State::run_sharded_pipelined(const std::vector<ShardStep> &steps, int c) {
     const uint64_t rank_bits = uint64_t(rank_) << n_local_;
     if (!xstream_)
         CUDA_CHECK(cudaStreamCreateWithFlags(&xstream_, cudaStreamNonBlocking));
-    int x_sms = 16; // SMs the exchange kernel occupies while tile passes run beside it
+    // SMs the exchange kernel occupies while tile passes run beside it. The passes are the longer
+    // stream at every world size measured (profiles/r2_trace*.json), and their speed follows the
+    // number of SMs they keep, so the exchange gets just enough SMs to stay hidden behind them.
+    int x_sms = 12;
     if (const char *e = getenv("B2SV_EXCHANGE_SMS"))
         x_sms = std::max(4, std::min(64, atoi(e)));
-    const int pass_ctas = sm_count_current_device() - x_sms;
+    const int x_sms_extra = 4; // exchanges of two or more bits move more data per pass beside them
+    const int pass_ctas = sm_count_current_device() - x_sms - (gbits_ >= 2 ? x_sms_extra : 0);
 
     // ---- tasks: the tile passes of every run and the exchanges, in program order
     struct Task {
@@ -778,12 +782,16 @@ void State::run_sharded_pipelined(const std::vector<ShardStep> &steps, int c) {
             for (int q = 0; q < Q; q++)
                 last[q] = {e0, stream_};
         }
-        for (int step = 0; step < Q + P - 1; step++) {
-            for (int p = 0; p < P; p++) { // earlier phases first: their passes cover the exchange the
-                                          // later phase of the neighbouring slice is waiting for
-                const int q = step - p;
-                if (q < 0 || q >= Q)
-                    continue;
+        // Phase-major order: all slices of phase 0, then all slices of phase 1, ... The exchange of
+        // slice q (second stream) starts as soon as the passes of phase p on q are done and runs
+        // while the state's stream works through the remaining slices of that phase; by the time
+        // phase p + 1 reaches slice q its exchange has had Q - 1 slice-times to finish. The exchange
+        // stream never waits behind passes of a later phase.
+        for (int p = 0; p < P; p++) {
+            int k_bits = 0;
+            if (xafter[p])
+                k_bits = static_cast<int>(xafter[p]->swaps.size());
+            for (int q = 0; q < Q; q++) {
                 const uint64_t off = deposit(q, rg.slice_mask);
                 for (const Pass *ps : phase[p]) {
                     load_params(*ps);
@@ -805,7 +813,8 @@ void State::run_sharded_pipelined(const std::vector<ShardStep> &steps, int c) {
                     {
                         TraceScope ts(*this, 2, xstream_);
                         comm_exchange(comm_.get(), d_state_, peers_, dtype_, n_local_, to_jl(*xafter[p]),
-                                      xstream_, 1, x_sms, true, rg.slice_mask, off);
+                                      xstream_, 1, x_sms + (k_bits >= 2 ? x_sms_extra : 0), true,
+                                      rg.slice_mask, off);
                     }
                     last[q] = {new_event(xstream_), xstream_};
                 }
