@@ -60,6 +60,11 @@ int b2sv_init_zeros(b2sv_state *s);                                      /* init
 int b2sv_set_basis_state(b2sv_state *s, uint64_t index);                 /* :492 */
 int b2sv_set_state_vector(b2sv_state *s, const uint64_t *indices, const double *values_c128,
                           size_t n);                                     /* :503-521 */
+/* state preparation on a subset of wires with the index table built on the device: all zeros, then
+ * amplitude v of values_c128 (2^nw entries, wires[0] = MSB of v) lands on the basis state that has v
+ * on `wires` and 0 elsewhere. Replaces the host-side itertools.product table of
+ * lightning_kokkos.py:293-327 (_apply_state_vector_kokkos) + setStateVector. */
+int b2sv_set_state_on_wires(b2sv_state *s, const int64_t *wires, int nw, const double *values_c128);
 int b2sv_h2d(b2sv_state *s, const void *host, size_t length);            /* HostToDevice :1618 */
 int b2sv_d2h(const b2sv_state *s, void *host, size_t length);            /* DeviceToHost :1626 */
 /* sampled read (no reference counterpart; the reference copies the whole state, SV.hpp:1626):
@@ -133,6 +138,11 @@ int b2sv_plan_sharded(const b2sv_ops *ops, int num_qubits, int world, int dtype,
 /* ---- measurements (MeasuresKokkos.hpp) ----------------------------------------------- */
 int b2sv_expval_named(const b2sv_state *s, const char *name, const int64_t *wires, int nw,
                       double *out);                                     /* MK.hpp:80-101,167-271 */
+/* <Z_w> for every wire w in ONE read pass (the Python device asks for them one by one,
+ * lightning_kokkos.py:554-559; b2sv_expval_named("PauliZ") is served from the same cached pass). */
+int b2sv_expval_z_all(const b2sv_state *s, double *out, int cap);
+/* drop cached measurements after writing through a pointer obtained from b2sv_device_ptr */
+int b2sv_invalidate(b2sv_state *s);
 int b2sv_expval_matrix(const b2sv_state *s, const int64_t *wires, int nw,
                        const double *matrix_c128, double *out);         /* MK.hpp:112-121,283-346 */
 int b2sv_expval_csr(const b2sv_state *s, const double *data_c128, const uint64_t *indices,

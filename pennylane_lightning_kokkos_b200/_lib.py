@@ -46,6 +46,7 @@ PROTOTYPES = {
     "b2sv_init_zeros": (C.c_int, [vp]),
     "b2sv_set_basis_state": (C.c_int, [vp, C.c_uint64]),
     "b2sv_set_state_vector": (C.c_int, [vp, u64p, dp, C.c_size_t]),
+    "b2sv_set_state_on_wires": (C.c_int, [vp, i64p, C.c_int, dp]),
     "b2sv_h2d": (C.c_int, [vp, vp, C.c_size_t]),
     "b2sv_d2h": (C.c_int, [vp, vp, C.c_size_t]),
     "b2sv_get_amplitudes": (C.c_int, [vp, u64p, C.c_size_t, dp]),
@@ -76,6 +77,8 @@ PROTOTYPES = {
     "b2sv_ops_destroy": (C.c_int, [vp]),
     "b2sv_ops_size": (C.c_int, [vp, ip, ip]),
     "b2sv_expval_named": (C.c_int, [vp, C.c_char_p, i64p, C.c_int, dp]),
+    "b2sv_expval_z_all": (C.c_int, [vp, dp, C.c_int]),
+    "b2sv_invalidate": (C.c_int, [vp]),
     "b2sv_expval_matrix": (C.c_int, [vp, i64p, C.c_int, dp, dp]),
     "b2sv_expval_csr": (C.c_int, [vp, dp, u64p, u64p, C.c_size_t, C.c_size_t, dp]),
     "b2sv_csr_create": (C.c_int, [vp, dp, u64p, u64p, C.c_size_t, C.c_size_t, C.POINTER(vp)]),

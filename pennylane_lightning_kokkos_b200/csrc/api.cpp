@@ -168,6 +168,13 @@ int b2sv_set_state_vector(b2sv_state *s, const uint64_t *indices, const double *
         st(s).set_state_vector(indices, v.data(), n);
     });
 }
+int b2sv_set_state_on_wires(b2sv_state *s, const int64_t *wires, int nw, const double *values) {
+    return guard([&] {
+        B2_ABORT_IF(nw < 1 || nw > 40 || !values, "invalid arguments");
+        auto v = cplx_vec(values, size_t(1) << nw);
+        st(s).set_state_on_wires(wires_vec(wires, nw), v.data());
+    });
+}
 int b2sv_h2d(b2sv_state *s, const void *host, size_t length) {
     return guard([&] { st(s).h2d(host, length); });
 }
@@ -205,7 +212,29 @@ int b2sv_data_length(const b2sv_state *s, uint64_t *len) {
     return guard([&] { *len = st(s).local_length(); });
 }
 int b2sv_device_ptr(const b2sv_state *s, void **ptr) {
-    return guard([&] { *ptr = st(s).data(); });
+    return guard([&] {
+        *ptr = st(s).data();
+        // the caller may write through the pointer: cached measurements are dropped now (and must be
+        // dropped again with b2sv_invalidate after every later write through a retained pointer)
+        const_cast<State &>(st(s)).touch();
+    });
+}
+int b2sv_invalidate(b2sv_state *s) {
+    return guard([&] { st(s).touch(); });
+}
+int b2sv_expval_z_all(const b2sv_state *s, double *out, int cap) {
+    return guard([&] {
+        B2_ABORT_IF(!out, "null output");
+        const State &sv = st(s);
+        if (sv.num_local() >= 12 && sv.num_local() <= 40 && sv.alloc_length() == sv.local_length()) {
+            const std::vector<double> &z = sv.expval_z_all();
+            for (int w = 0; w < cap && w < sv.num_qubits(); w++)
+                out[w] = z[w];
+        } else {
+            for (int w = 0; w < cap && w < sv.num_qubits(); w++)
+                out[w] = sv.expval_named("PauliZ", {static_cast<int64_t>(w)});
+        }
+    });
 }
 int b2sv_stream(const b2sv_state *s, void **stream) {
     return guard([&] { *stream = static_cast<void *>(st(s).stream()); });

@@ -118,6 +118,30 @@ __global__ void k_scatter(amp_t *__restrict__ state, const uint64_t *__restrict_
         state[idx[i]] = v;
     }
 }
+// State preparation on a subset of wires, index table built on the device (the reference's Python
+// layer builds it with itertools.product and ships 2^k indices, lightning_kokkos.py:317-327):
+// state[sum_j bit_j(v) << pos[j]] = val[v], v < 2^k, pos[j] = index bit of the j-th wire (wire 0 of
+// the list = MSB of v). Only the entries of this shard (index >> n_local == rank) are written.
+struct WirePos {
+    int k;
+    int pos[64];
+};
+template <typename amp_t>
+__global__ void k_scatter_wires(amp_t *__restrict__ state, const double2 *__restrict__ val, uint64_t count,
+                                WirePos wp, int n_local, uint64_t rank) {
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t v = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; v < count; v += stride) {
+        uint64_t idx = 0;
+        for (int j = 0; j < wp.k; j++)
+            idx |= ((v >> (wp.k - 1 - j)) & 1ull) << wp.pos[j];
+        if ((n_local >= 64 ? 0 : (idx >> n_local)) == rank) {
+            amp_t a;
+            a.x = val[v].x;
+            a.y = val[v].y;
+            state[idx & ((uint64_t(1) << n_local) - 1)] = a;
+        }
+    }
+}
 // out[k] = state[idx[k]] when the index belongs to this shard (idx >> n_local == rank), else 0
 template <typename amp_t>
 __global__ void k_gather(const amp_t *__restrict__ state, const uint64_t *__restrict__ idx, size_t n,
@@ -306,6 +330,107 @@ __global__ void __launch_bounds__(kReduceThreads)
         const double wr = sg * (phr * b.x - phi * b.y);
         const double wi = sg * (phr * b.y + phi * b.x);
         acc[0] += double(a.x) * wr + double(a.y) * wi;
+    }
+    block_reduce_store<1>(acc, partials);
+}
+
+// All single-qubit <Z> of a state in ONE read pass (the reference runs one reduction kernel per
+// observable, MeasuresKokkos.hpp:167-271 via lightning_kokkos.py:554-559).
+// A block walks chunks of 4096 amplitudes; thread t reads indices base + t + 256 j (j < 16), so
+// bits 0..7 of the index are the thread's own, bits 8..11 follow j and bits >= 12 are uniform per
+// chunk. Per thread: tot = sum |a|^2, four sums for bits 8..11, and for every higher bit the sum over
+// the chunks that have it set. Result per block: [tot, P1(bit 0), ..., P1(bit n-1)] with
+// P1(b) = sum of |a_i|^2 over indices with bit b set;  <Z_b> = tot - 2 P1(b).
+constexpr int kZAllMaxBits = 40;
+constexpr int kZAllVals = 1 + kZAllMaxBits;
+static_assert(kZAllVals == kZAllValsHost, "kernels.cuh and kernels.cu disagree on the all-Z layout");
+template <typename amp_t>
+__global__ void __launch_bounds__(256)
+    k_expval_z_all(const amp_t *__restrict__ s, int n, double *__restrict__ partials) {
+    constexpr int NHI = kZAllMaxBits - 12;
+    double tot = 0.0, mid[4] = {0.0, 0.0, 0.0, 0.0}, hi[NHI];
+#pragma unroll
+    for (int b = 0; b < NHI; b++)
+        hi[b] = 0.0;
+    const uint64_t nchunks = uint64_t(1) << (n - 12);
+    for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const amp_t *p = s + (c << 12) + threadIdx.x;
+        double ct = 0.0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const amp_t a = p[j * 256];
+            const double w = double(a.x) * a.x + double(a.y) * a.y;
+            ct += w;
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (j & (1 << b))
+                    mid[b] += w;
+        }
+        tot += ct;
+#pragma unroll
+        for (int b = 0; b < NHI; b++)
+            if (b < n - 12 && ((c >> b) & 1ull))
+                hi[b] += ct;
+    }
+    double v[kZAllVals];
+    v[0] = tot;
+#pragma unroll
+    for (int b = 0; b < 8; b++)
+        v[1 + b] = ((threadIdx.x >> b) & 1) ? tot : 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        v[9 + b] = mid[b];
+#pragma unroll
+    for (int b = 0; b < NHI; b++)
+        v[13 + b] = hi[b];
+    block_reduce_store<kZAllVals>(v, partials);
+}
+
+// <psi| sum_t c_t P_t |psi> for a sum of Pauli words in one kernel and without a work vector (the
+// reference applies the Hamiltonian term by term into two temporaries and takes an inner product,
+// ObservablesKokkos.hpp:360-373 + MeasuresKokkos.hpp:354-360). Terms are sorted by x mask on the host,
+// so the partner amplitude psi[i ^ x] is re-read only when the mask changes.
+template <typename amp_t>
+__global__ void __launch_bounds__(kReduceThreads)
+    k_pauli_sum_expval(const amp_t *__restrict__ s, uint64_t len, const PauliTerm *__restrict__ terms,
+                       int nterms, double *__restrict__ partials) {
+    constexpr int CH = 128;
+    __shared__ PauliTerm st[CH];
+    double acc[1] = {0.0};
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    const uint64_t i0 = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t iters = (len + stride - 1) / stride;
+    for (uint64_t it = 0; it < iters; it++) {
+        const uint64_t i = i0 + it * stride;
+        amp_t a;
+        a.x = 0;
+        a.y = 0;
+        if (i < len)
+            a = s[i];
+        double sr = 0.0, si = 0.0;
+        for (int t0 = 0; t0 < nterms; t0 += CH) {
+            const int nt = min(CH, nterms - t0);
+            __syncthreads();
+            if (threadIdx.x < nt)
+                st[threadIdx.x] = terms[t0 + threadIdx.x];
+            __syncthreads();
+            if (i < len) {
+                uint64_t cur_x = 0;
+                amp_t b = a;
+                for (int t = 0; t < nt; t++) {
+                    const uint64_t j = i ^ st[t].x;
+                    if (st[t].x != cur_x) {
+                        cur_x = st[t].x;
+                        b = s[j];
+                    }
+                    const double sg = (__popcll(j & st[t].z) & 1) ? -1.0 : 1.0;
+                    const double cr = sg * st[t].cr, ci = sg * st[t].ci;
+                    sr += cr * b.x - ci * b.y;
+                    si += cr * b.y + ci * b.x;
+                }
+            }
+        }
+        acc[0] += double(a.x) * sr + double(a.y) * si; // Re conj(a_i) (H psi)_i
     }
     block_reduce_store<1>(acc, partials);
 }
@@ -964,6 +1089,18 @@ void launch_scatter(int dtype, void *state, const uint64_t *d_idx, const double2
                    (k_scatter<float2><<<grid, 256, 0, st>>>(static_cast<float2 *>(state), d_idx, d_val, n)),
                    (k_scatter<double2><<<grid, 256, 0, st>>>(static_cast<double2 *>(state), d_idx, d_val, n)));
 }
+void launch_scatter_wires(int dtype, void *state, const double2 *d_val, const int *h_pos, int k,
+                          int n_local, uint64_t rank, cudaStream_t st) {
+    WirePos wp{};
+    wp.k = k;
+    for (int j = 0; j < k; j++)
+        wp.pos[j] = h_pos[j];
+    const uint64_t count = uint64_t(1) << k;
+    const int grid = reduce_grid(count);
+    DISPATCH_DTYPE(dtype,
+                   (k_scatter_wires<float2><<<grid, 256, 0, st>>>(static_cast<float2 *>(state), d_val, count, wp, n_local, rank)),
+                   (k_scatter_wires<double2><<<grid, 256, 0, st>>>(static_cast<double2 *>(state), d_val, count, wp, n_local, rank)));
+}
 void launch_gather(int dtype, const void *state, const uint64_t *d_idx, size_t n, int n_local,
                    uint64_t rank, double2 *d_out, cudaStream_t st) {
     if (n == 0)
@@ -1042,6 +1179,22 @@ void launch_pauli_dot(int dtype, const void *bra, const void *ket, uint64_t len,
     DISPATCH_DTYPE(dtype,
                    (k_pauli_dot<float2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(bra), static_cast<const float2 *>(ket), len, x, z, phr, phi, d_partials)),
                    (k_pauli_dot<double2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(bra), static_cast<const double2 *>(ket), len, x, z, phr, phi, d_partials)));
+}
+void launch_expval_z_all(int dtype, const void *state, int n_bits, double *d_partials, cudaStream_t st) {
+    B2_ASSERT(n_bits >= 12 && n_bits <= kZAllMaxBits);
+    const uint64_t nchunks = uint64_t(1) << (n_bits - 12);
+    const int grid = static_cast<int>(std::min<uint64_t>(nchunks, kReduceBlocks));
+    if (grid < kReduceBlocks) // finalize sums kReduceBlocks rows
+        CUDA_CHECK(cudaMemsetAsync(d_partials, 0, sizeof(double) * kReduceBlocks * kZAllValsHost, st));
+    DISPATCH_DTYPE(dtype,
+                   (k_expval_z_all<float2><<<grid, 256, 0, st>>>(static_cast<const float2 *>(state), n_bits, d_partials)),
+                   (k_expval_z_all<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(state), n_bits, d_partials)));
+}
+void launch_pauli_sum_expval(int dtype, const void *state, uint64_t len, const PauliTerm *d_terms,
+                             int nterms, double *d_partials, cudaStream_t st) {
+    DISPATCH_DTYPE(dtype,
+                   (k_pauli_sum_expval<float2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), len, d_terms, nterms, d_partials)),
+                   (k_pauli_sum_expval<double2><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), len, d_terms, nterms, d_partials)));
 }
 void launch_finalize_scaled(const double *d_partials, int nblocks, int nv, int which, double scale,
                             double *d_dst, cudaStream_t st) {

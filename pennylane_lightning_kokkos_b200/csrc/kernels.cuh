@@ -9,7 +9,7 @@ namespace b2sv {
 
 constexpr int kReduceBlocks = 1184; // 148 SMs x 8 resident CTAs of 256 threads
 constexpr int kReduceThreads = 256;
-constexpr int kMaxReduceVals = 8;
+constexpr int kMaxReduceVals = 48; // the all-Z reduction carries 41 values per block
 
 // ---- tile executor (tile_kernel.cu)
 void tile_config(int dtype, int *B, int *R);
@@ -24,6 +24,9 @@ void tile_prof_read(unsigned long long out[16]);
 void launch_set_basis(int dtype, void *state, uint64_t len, uint64_t index, cudaStream_t st);
 void launch_scatter(int dtype, void *state, const uint64_t *d_idx, const double2 *d_val, size_t n,
                     cudaStream_t st);
+// state[sum_j bit_j(v) << h_pos[j]] = d_val[v] for v < 2^k (h_pos[0] <-> MSB of v), this shard's part
+void launch_scatter_wires(int dtype, void *state, const double2 *d_val, const int *h_pos, int k,
+                          int n_local, uint64_t rank, cudaStream_t st);
 // sampled read: d_out[k] = state[d_idx[k]] as complex128 (zero where the index is another rank's)
 void launch_gather(int dtype, const void *state, const uint64_t *d_idx, size_t n, int n_local,
                    uint64_t rank, double2 *d_out, cudaStream_t st);
@@ -77,6 +80,11 @@ void launch_pauli_expval(int dtype, const void *state, uint64_t len, uint64_t x,
                          double phr, double phi, double *d_partials, cudaStream_t st);
 void launch_finalize(const double *d_partials, int nblocks, int nv, double *d_out,
                      cudaStream_t st);
+// every single-qubit <Z> in one read pass (needs 12 <= n_bits <= 40): kReduceBlocks x kZAllValsHost
+// partials; after launch_finalize(nv = kZAllValsHost): [0] = sum |a|^2, [1 + b] = sum over the
+// indices with bit b set
+constexpr int kZAllValsHost = 41;
+void launch_expval_z_all(int dtype, const void *state, int n_bits, double *d_partials, cudaStream_t st);
 // 2 values: Re, Im of <bra| P |ket>, P|j> = ph * (-1)^popc(j & z) |j ^ x>
 void launch_pauli_dot(int dtype, const void *bra, const void *ket, uint64_t len, uint64_t x,
                       uint64_t z, double phr, double phi, double *d_partials, cudaStream_t st);
@@ -89,6 +97,9 @@ struct PauliTerm {
     double cr, ci; // coefficient * i^nY
 };
 // out = sum_t coef_t P_t in   (in != out)
+// 1 value: Re <psi| sum_t coef_t P_t |psi>; terms sorted by x
+void launch_pauli_sum_expval(int dtype, const void *state, uint64_t len, const PauliTerm *d_terms,
+                             int nterms, double *d_partials, cudaStream_t st);
 void launch_pauli_sum_apply(int dtype, const void *in, void *out, uint64_t len,
                             const PauliTerm *d_terms, int nterms, cudaStream_t st);
 

@@ -324,6 +324,15 @@ double expval_obs(const State &sv, const Obs &ob) {
         const PauliWord &w = terms[0].second;
         return terms[0].first * sv.expval_pauli(w.x, w.z, ipow[w.ny & 3]);
     }
+    if (!terms.empty()) { // a sum of Pauli words: one read pass per distinct x mask, no work vector
+        static const cplx ipow[4] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
+        std::vector<PauliTerm> pt(terms.size());
+        for (size_t t = 0; t < terms.size(); t++) {
+            const cplx c = terms[t].first * ipow[terms[t].second.ny & 3];
+            pt[t] = PauliTerm{terms[t].second.x, terms[t].second.z, c.real(), c.imag()};
+        }
+        return sv.expval_pauli_sum(pt);
+    }
     auto tmp = sv.clone();
     ob.apply_in_place(*tmp);
     double re;

@@ -262,11 +262,13 @@ void State::reset() { set_basis_state(0); }
 void State::init_zeros() {
     CUDA_CHECK(cudaSetDevice(device_));
     reset_layout();
+    touch();
     CUDA_CHECK(cudaMemsetAsync(d_state_, 0, alloc_length() * amp_bytes(), stream_));
 }
 void State::set_basis_state(uint64_t index) {
     CUDA_CHECK(cudaSetDevice(device_));
     reset_layout();
+    touch();
     B2_ABORT_IF(n_ < 64 && index >= (uint64_t(1) << n_), "basis-state index out of range");
     const uint64_t owner = index >> n_local_;
     const uint64_t local = (owner == static_cast<uint64_t>(rank_)) ? (index & (local_length() - 1))
@@ -296,16 +298,34 @@ void State::set_state_vector(const uint64_t *indices, const cplx *values, size_t
                                cudaMemcpyHostToDevice, stream_));
     CUDA_CHECK(cudaMemcpyAsync(d_val, val.data(), sizeof(double2) * val.size(),
                                cudaMemcpyHostToDevice, stream_));
+    touch();
     launch_scatter(dtype_, d_state_, d_idx, d_val, idx.size(), stream_);
     launches++;
     CUDA_CHECK(cudaFreeAsync(d_idx, stream_));
     CUDA_CHECK(cudaFreeAsync(d_val, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_)); // host vectors go out of scope
 }
+void State::set_state_on_wires(const std::vector<int64_t> &wires, const cplx *values) {
+    CUDA_CHECK(cudaSetDevice(device_));
+    const std::vector<int> bits = wires_to_bits(wires, n_);
+    const int k = static_cast<int>(bits.size());
+    B2_ABORT_IF(k < 1 || k > 40, "state preparation needs between 1 and 40 wires");
+    init_zeros(); // identity layout: logical bit = physical bit
+    const size_t count = size_t(1) << k;
+    double2 *d_val;
+    CUDA_CHECK(cudaMallocAsync(&d_val, sizeof(double2) * count, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(d_val, values, sizeof(double2) * count, cudaMemcpyHostToDevice, stream_));
+    launch_scatter_wires(dtype_, d_state_, d_val, bits.data(), k, n_local_, static_cast<uint64_t>(rank_),
+                         stream_);
+    launches++;
+    CUDA_CHECK(cudaFreeAsync(d_val, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_)); // the caller's buffer may go away
+}
 void State::h2d(const void *host, size_t length) {
     CUDA_CHECK(cudaSetDevice(device_));
     B2_ABORT_IF(length != local_length(), "HostToDevice: length does not match the state vector");
     reset_layout();
+    touch();
     CUDA_CHECK(cudaMemcpyAsync(d_state_, host, length * amp_bytes(), cudaMemcpyHostToDevice, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
@@ -391,6 +411,7 @@ void State::copy_from(const State &o) {
                                cudaMemcpyDeviceToDevice, stream_));
     order_after(o.stream_, stream_);
     l2p_ = o.l2p_;
+    touch();
     bytes_moved += 2 * state_bytes();
 }
 std::unique_ptr<State> State::clone() const {
@@ -404,7 +425,10 @@ std::unique_ptr<State> State::clone_on_stream() const {
     c->copy_from(*this);
     return c;
 }
-void State::swap_buffer(void *&other) { std::swap(d_state_, other); }
+void State::swap_buffer(void *&other) {
+    std::swap(d_state_, other);
+    touch();
+}
 void *State::acquire_scratch() const {
     CUDA_CHECK(cudaSetDevice(device_));
     if (!scratch_.empty()) {
@@ -595,6 +619,7 @@ int State::pipeline_bits() const {
 // so the pass that needs a given qubit never has to wait for a whole-shard exchange next to it.
 // Tasks outside regions are whole-shard launches on the state's stream.
 void State::run_sharded_pipelined(const std::vector<ShardStep> &steps, int c) {
+    touch();
     const int Q = 1 << c;
     const uint64_t rank_bits = uint64_t(rank_) << n_local_;
     if (!xstream_)
@@ -946,6 +971,7 @@ void State::run_local(const std::vector<Prim> &prims) {
 }
 
 void State::upload_and_run(const std::vector<Pass> &passes) {
+    touch();
     // Pass descriptors travel as kernel parameters (copied by the runtime at launch), so there is
     // no staging buffer, no H2D copy and nothing to keep alive after the launch call returns.
     const uint64_t rank_bits = uint64_t(rank_) << n_local_;
@@ -1048,6 +1074,8 @@ double State::expval_named(const std::string &name, const std::vector<int64_t> &
         return norm2(); // EVF.hpp:13-28
     B2_ABORT_IF(wires.size() != 1, "named observables act on exactly one wire");
     const int tq = wires_to_bits(wires, n_)[0];
+    if (name == "PauliZ" && n_local_ >= 12 && n_local_ <= 40 && n_eff_ == n_local_)
+        return expval_z_all()[wires[0]];
     if (name != "PauliZ")
         ensure_local(bit(tq));
     const int t = phys_bit(tq);
@@ -1075,6 +1103,90 @@ double State::expval_named(const std::string &name, const std::vector<int64_t> &
     launch_expval_1q(dtype_, d_state_, local_length(), t, m, d_partials_, stream_);
     double r;
     finish_reduce(1, &r);
+    return r;
+}
+const std::vector<double> &State::expval_z_all() const {
+    if (zcache_version_ == version_ && !zcache_.empty())
+        return zcache_;
+    CUDA_CHECK(cudaSetDevice(device_));
+    B2_ABORT_IF(n_local_ < 12 || n_local_ > 40 || n_eff_ != n_local_,
+                "internal: the all-Z reduction needs between 12 and 40 local qubits");
+    launch_expval_z_all(dtype_, d_state_, n_local_, d_partials_, stream_);
+    bytes_moved += state_bytes();
+    launch_finalize(d_partials_, kReduceBlocks, kZAllValsHost, d_out_, stream_);
+    reduce_launches += 2;
+    std::vector<double> loc(kZAllValsHost);
+    if (!comm_) {
+        CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(double) * kZAllValsHost, cudaMemcpyDeviceToHost, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        for (int i = 0; i < kZAllValsHost; i++)
+            loc[i] = h_out_[i];
+        zcache_.assign(n_, 0.0);
+        for (int q = 0; q < n_; q++)
+            zcache_[n_ - 1 - q] = loc[0] - 2.0 * loc[1 + q]; // wire w <-> index bit n - 1 - w
+    } else {
+        // per rank: [tot, P1(logical bit 0), ...]; a logical bit that sits on a rank bit contributes
+        // tot or nothing, according to this rank's value of that bit
+        CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, sizeof(double) * kZAllValsHost, cudaMemcpyDeviceToHost, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        std::vector<double> mine(n_ + 1, 0.0);
+        mine[0] = h_out_[0];
+        for (int q = 0; q < n_; q++) {
+            const int p = l2p_[q];
+            mine[1 + q] = p < n_local_ ? h_out_[1 + p] : (((rank_ >> (p - n_local_)) & 1) ? h_out_[0] : 0.0);
+        }
+        double *d_tmp;
+        CUDA_CHECK(cudaMallocAsync(&d_tmp, sizeof(double) * (n_ + 1), stream_));
+        CUDA_CHECK(cudaMemcpyAsync(d_tmp, mine.data(), sizeof(double) * (n_ + 1), cudaMemcpyHostToDevice, stream_));
+        comm_allreduce_sum(comm_.get(), d_tmp, n_ + 1, stream_);
+        CUDA_CHECK(cudaMemcpyAsync(mine.data(), d_tmp, sizeof(double) * (n_ + 1), cudaMemcpyDeviceToHost, stream_));
+        CUDA_CHECK(cudaFreeAsync(d_tmp, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        zcache_.assign(n_, 0.0);
+        for (int q = 0; q < n_; q++)
+            zcache_[n_ - 1 - q] = mine[0] - 2.0 * mine[1 + q];
+    }
+    zcache_version_ = version_;
+    return zcache_;
+}
+double State::expval_pauli_sum(const std::vector<PauliTerm> &terms_in) const {
+    CUDA_CHECK(cudaSetDevice(device_));
+    if (terms_in.empty())
+        return 0.0;
+    uint64_t xall = 0;
+    for (const PauliTerm &t : terms_in)
+        xall |= t.x;
+    ensure_local(xall); // X / Y factors pair amplitudes: those qubits must be shard-local
+    std::vector<PauliTerm> terms;
+    terms.reserve(terms_in.size());
+    const uint64_t rank_bits = uint64_t(rank_) << n_local_;
+    for (const PauliTerm &t : terms_in) {
+        PauliTerm u = t;
+        u.x = phys_mask(t.x);
+        const uint64_t zp = phys_mask(t.z);
+        u.z = zp & (local_length() - 1);
+        if (__builtin_popcountll(rank_bits & zp) & 1) { // Z factors on rank bits: a per-rank sign
+            u.cr = -u.cr;
+            u.ci = -u.ci;
+        }
+        terms.push_back(u);
+    }
+    std::stable_sort(terms.begin(), terms.end(),
+                     [](const PauliTerm &a, const PauliTerm &b) { return a.x < b.x; });
+    PauliTerm *d_terms;
+    CUDA_CHECK(cudaMallocAsync(&d_terms, sizeof(PauliTerm) * terms.size(), stream_));
+    CUDA_CHECK(cudaMemcpyAsync(d_terms, terms.data(), sizeof(PauliTerm) * terms.size(), cudaMemcpyHostToDevice, stream_));
+    launch_pauli_sum_expval(dtype_, d_state_, local_length(), d_terms, static_cast<int>(terms.size()),
+                            d_partials_, stream_);
+    CUDA_CHECK(cudaFreeAsync(d_terms, stream_));
+    {
+        size_t nx = 1;
+        for (size_t i = 1; i < terms.size(); i++)
+            nx += terms[i].x != terms[i - 1].x;
+        bytes_moved += nx * state_bytes();
+    }
+    double r;
+    finish_reduce(1, &r); // synchronises: `terms` may go out of scope
     return r;
 }
 double State::expval_matrix(const std::vector<int64_t> &wires, const std::vector<cplx> &mat) const {
@@ -1192,6 +1304,7 @@ void State::axpy(cplx alpha, const State &x) {
     }
     order_after(stream_, x.stream_);
     launch_axpy(dtype_, alpha.real(), alpha.imag(), x.d_state_, d_state_, local_length(), stream_);
+    touch();
     launches++;
     bytes_moved += 3 * state_bytes();
     order_after(x.stream_, stream_);

@@ -64,6 +64,8 @@ class State {
     void init_zeros();
     void set_basis_state(uint64_t index);
     void set_state_vector(const uint64_t *indices, const cplx *values, size_t n);
+    // all zeros, then the 2^k amplitudes `values` on the given wires (the other wires in |0>)
+    void set_state_on_wires(const std::vector<int64_t> &wires, const cplx *values);
     void h2d(const void *host, size_t length);
     void d2h(void *host, size_t length) const;
     // amplitudes at global flat indices, as complex128 (sampled read; sharded: all-reduced)
@@ -103,6 +105,12 @@ class State {
     double expval_matrix(const std::vector<int64_t> &wires, const std::vector<cplx> &m) const;
     double expval_csr(const CsrDevice &m) const;
     double expval_pauli(uint64_t x, uint64_t z, cplx ph) const;
+    // <Z_w> for every wire w from ONE read pass; cached until the state changes, so a run of
+    // ExpectationValue("PauliZ", [w]) calls (lightning_kokkos.py:554-559) costs one kernel and one sync
+    const std::vector<double> &expval_z_all() const;
+    // Re <psi| sum_t c_t P_t |psi>, Pauli words as (x, z, coefficient * i^nY) in logical bits
+    double expval_pauli_sum(const std::vector<PauliTerm> &terms) const;
+    void touch() { version_++; } // the amplitudes changed: cached measurements are stale
     void axpy(cplx alpha, const State &x);
     // Adjoint-sweep reductions that stay on the device (no host synchronisation):
     //   *d_dst = factor * Im <bra| P |this>   with P|j> = ph (-1)^popc(j&z) |j^x>  (logical bits)
@@ -177,6 +185,9 @@ class State {
         TraceScope(const State &state, int k, cudaStream_t stream = nullptr);
         ~TraceScope();
     };
+    uint64_t version_ = 1;
+    mutable uint64_t zcache_version_ = 0;
+    mutable std::vector<double> zcache_;
     mutable bool tracing_ = false;
     mutable cudaEvent_t trace_t0_ = nullptr;
     mutable std::vector<TraceRec> trace_;

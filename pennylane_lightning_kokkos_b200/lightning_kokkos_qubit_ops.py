@@ -329,6 +329,15 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
                 raise PLException("indices and state must have the same length")
             check(lib.b2sv_set_state_vector(self._h, ip_, vp_, n))
 
+        def setStateOnWires(self, wires, state):
+            """State preparation on a subset of wires, index table built on the device
+            (replaces lightning_kokkos.py:317-327 + setStateVector)."""
+            _, wp, nw = _i64(wires)
+            vals, vp_, nv = _c128(state)
+            if nv != 1 << nw:
+                raise PLException("state must have 2**len(wires) amplitudes")
+            check(lib.b2sv_set_state_on_wires(self._h, wp, nw, vp_))
+
         def DeviceToHost(self, host_sv):
             if not (isinstance(host_sv, np.ndarray) and host_sv.dtype == cdtype
                     and host_sv.flags["C_CONTIGUOUS"]):
@@ -432,6 +441,13 @@ def _make_classes(bits: str, dtype_flag: int, cdtype, rdtype):
                 check(lib.b2sv_expval_csr(self._h, dptr, iptr, pptr, nnz, np1 - 1, C.byref(out)))
                 return out.value
             raise TypeError("ExpectationValue(): incompatible function arguments")
+
+        def expval_z_all(self):
+            """<Z_w> for every wire w from one read pass over the state."""
+            n = self.numQubits()
+            out = np.zeros(n, dtype=np.float64)
+            check(lib.b2sv_expval_z_all(self._h, out.ctypes.data_as(_lib.dp), n))
+            return out
 
         def expval(self, obs) -> float:
             """MeasuresKokkos::expval(Observable) (MK.hpp:354-360; unbound in the reference)."""

@@ -16,9 +16,13 @@ TOL = {np.complex128: 1e-12, np.complex64: 1e-5}
 DTYPES = [np.complex128, np.complex64]
 
 
-@pytest.fixture(scope="module")
-def ops():
-    from pennylane_lightning_kokkos_b200 import lightning_kokkos_qubit_ops as m
+@pytest.fixture(scope="module", params=["ctypes", "pybind11"])
+def ops(request):
+    """The binding surface twice: the ctypes mirror and the compiled pybind11 module (same names)."""
+    if request.param == "ctypes":
+        from pennylane_lightning_kokkos_b200 import lightning_kokkos_qubit_ops as m
+    else:
+        from pennylane_lightning_kokkos_b200 import lightning_kokkos_qubit_ops_pyb as m
     return m
 
 

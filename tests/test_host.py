@@ -41,8 +41,10 @@ def test_header_cites_the_reference_interface():
         assert cite in text
 
 
-def test_module_surface_matches_reference_binding():
-    from pennylane_lightning_kokkos_b200 import lightning_kokkos_qubit_ops as m
+@pytest.mark.parametrize("modname", ["lightning_kokkos_qubit_ops", "lightning_kokkos_qubit_ops_pyb"])
+def test_module_surface_matches_reference_binding(modname):
+    import importlib
+    m = importlib.import_module("pennylane_lightning_kokkos_b200." + modname)
     for bits in ("64", "128"):
         for cls in ("LightningKokkos", "NamedObsKokkos", "HermitianObsKokkos", "TensorProdObsKokkos",
                     "HamiltonianKokkos", "SparseHamiltonianKokkos", "OpsStructKokkos",
