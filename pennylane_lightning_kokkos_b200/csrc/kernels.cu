@@ -506,6 +506,8 @@ struct TransTile {
     int tile_pos[12];  // ascending index bit positions of the tile
     int nb;            // wires of this launch
     int wire_tpos[8];  // position (0..n_tile-1) of each wire's bit inside the tile
+    int u_pos[2];      // two tile positions that are not wires (ascending): the bits that tell a
+                       // thread's four elements apart
 };
 __device__ __forceinline__ void cp_async_16(void *sdst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
@@ -524,13 +526,17 @@ __device__ __forceinline__ void cp_async_amp(float2 *d, const float2 *s) { cp_as
 constexpr int kTransThreads = 512;
 // One persistent CTA per SM, two shared-memory stages: the copies of tile k+1 (cp.async) are in flight
 // while tile k is reduced.
+// Arithmetic: thread <-> element mapping puts the tile positions of all requested wires into the
+// thread-id bits (the two bits that distinguish a thread's four elements are non-wire positions), so
+// s_t(e) is a per-thread constant: per element only  d += c l  (4 FMA) and, per wire,  x_t += c l_{e^t}
+// (4 FMA) are accumulated; Z_t = s_t d and W_t = s_t x_t are formed once, after the loop.
 template <typename amp_t>
 __global__ void __launch_bounds__(kTransThreads, 1)
     k_transition_tile(const amp_t *__restrict__ bra, const amp_t *__restrict__ ket, uint64_t n_tiles,
                       TransTile tt, double *__restrict__ partials) {
     extern __shared__ __align__(16) unsigned char tsm[];
     constexpr int tile = 1 << kTransTileBits;
-    constexpr int per_thread = tile / kTransThreads;
+    constexpr int per_thread = tile / kTransThreads; // 4: two element-index bits per thread
     amp_t *stage = reinterpret_cast<amp_t *>(tsm); // [2 stages][ket tile, bra tile]
     __shared__ uint64_t rowoff[64];
     constexpr int n_rows = tile >> 5;
@@ -541,10 +547,15 @@ __global__ void __launch_bounds__(kTransThreads, 1)
                 off |= uint64_t(1) << tt.tile_pos[j];
         rowoff[threadIdx.x] = off;
     }
-    double acc[kTransitionVals];
+    // element index of this thread's u-th element: thread-id bits deposited around the two u positions
+    const int ua = tt.u_pos[0], ub = tt.u_pos[1]; // ua < ub, non-wire tile positions
+    int e0 = static_cast<int>(threadIdx.x);
+    e0 = ((e0 >> ua) << (ua + 1)) | (e0 & ((1 << ua) - 1));
+    e0 = ((e0 >> ub) << (ub + 1)) | (e0 & ((1 << ub) - 1));
+    double dx = 0.0, dy = 0.0, xr[kTransitionBits], xi[kTransitionBits];
 #pragma unroll
-    for (int j = 0; j < kTransitionVals; j++)
-        acc[j] = 0.0;
+    for (int w = 0; w < kTransitionBits; w++)
+        xr[w] = xi[w] = 0.0;
     __syncthreads();
     auto issue = [&](uint64_t t, int st) {
         uint64_t base = t; // tile id -> index with zeros at the tile's bit positions
@@ -573,31 +584,41 @@ __global__ void __launch_bounds__(kTransThreads, 1)
         }
         __syncthreads();
         const amp_t *sk = stage + size_t(st) * 2 * tile, *sb = sk + tile;
-#pragma unroll 2
+#pragma unroll
         for (int u = 0; u < per_thread; u++) {
-            const int e = u * kTransThreads + threadIdx.x;
+            const int e = e0 | ((u & 1) << ua) | ((u >> 1) << ub);
             const amp_t h = sb[e], l = sk[e];
-            const double cx = double(h.x), cy = -double(h.y);
-            const double dx = cx * l.x - cy * l.y, dy = cx * l.y + cy * l.x;
-            acc[0] += dx;
-            acc[1] += dy;
+            const double cx = double(h.x), cy = -double(h.y); // conj(bra)
+            dx = fma(cx, double(l.x), dx);
+            dx = fma(-cy, double(l.y), dx);
+            dy = fma(cx, double(l.y), dy);
+            dy = fma(cy, double(l.x), dy);
 #pragma unroll
             for (int w = 0; w < kTransitionBits; w++) {
                 if (w < tt.nb) {
-                    const int tp = tt.wire_tpos[w];
-                    const double sg = ((e >> tp) & 1) ? -1.0 : 1.0;
-                    const amp_t p = sk[e ^ (1 << tp)];
-                    const double xx = cx * p.x - cy * p.y, xy = cx * p.y + cy * p.x;
-                    acc[2 + 6 * w + 0] += sg * dx;
-                    acc[2 + 6 * w + 1] += sg * dy;
-                    acc[2 + 6 * w + 2] += xx;
-                    acc[2 + 6 * w + 3] += xy;
-                    acc[2 + 6 * w + 4] += sg * xx;
-                    acc[2 + 6 * w + 5] += sg * xy;
+                    const amp_t p = sk[e ^ (1 << tt.wire_tpos[w])];
+                    xr[w] = fma(cx, double(p.x), xr[w]);
+                    xr[w] = fma(-cy, double(p.y), xr[w]);
+                    xi[w] = fma(cx, double(p.y), xi[w]);
+                    xi[w] = fma(cy, double(p.x), xi[w]);
                 }
             }
         }
         __syncthreads(); // the stage is free for the copies issued in the next iteration
+    }
+    double acc[kTransitionVals];
+    acc[0] = dx;
+    acc[1] = dy;
+#pragma unroll
+    for (int w = 0; w < kTransitionBits; w++) {
+        const double sg = (w < tt.nb && ((e0 >> tt.wire_tpos[w]) & 1)) ? -1.0 : 1.0;
+        const bool on = w < tt.nb;
+        acc[2 + 6 * w + 0] = on ? sg * dx : 0.0;
+        acc[2 + 6 * w + 1] = on ? sg * dy : 0.0;
+        acc[2 + 6 * w + 2] = xr[w];
+        acc[2 + 6 * w + 3] = xi[w];
+        acc[2 + 6 * w + 4] = sg * xr[w];
+        acc[2 + 6 * w + 5] = sg * xi[w];
     }
     block_reduce_store<kTransitionVals>(acc, partials);
 }
@@ -700,6 +721,64 @@ __global__ void __launch_bounds__(kReduceThreads)
     }
     if (EXPVAL)
         block_reduce_store<1>(acc, partials);
+}
+
+// Expectation value of a CSR matrix as a pure stream over the non-zeros:
+//   <psi|A|psi> = sum_j Re( conj(psi[row(j)]) * data[j] * psi[ind[j]] ),
+// no per-row reduction at all. A warp takes chunks of 32 x K consecutive non-zeros (coalesced 16-byte
+// and 4-byte streams, all loads of a chunk in flight together), finds the row of the chunk's first
+// element by one binary search over the row pointers and then advances its row cursor monotonically.
+// The gathers psi[ind], psi[row] hit L2 for states up to ~100 MB. Deterministic: every lane sums in a
+// fixed order, the block and grid reductions are fixed-order too.
+template <typename amp_t, typename ptr_t>
+__global__ void __launch_bounds__(kReduceThreads)
+    k_csr_expval_stream(const amp_t *__restrict__ x, const double2 *__restrict__ data,
+                        const uint32_t *__restrict__ ind, const ptr_t *__restrict__ ptr, uint64_t nrows,
+                        uint64_t nnz, double *__restrict__ partials) {
+    constexpr int K = 8;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    const uint64_t nchunks = (nnz + 32 * K - 1) / (32 * K);
+    double acc[1] = {0.0};
+    for (uint64_t c = warp; c < nchunks; c += nwarps) {
+        const uint64_t j0 = c * (32 * K);
+        double2 d[K];
+        uint32_t col[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const uint64_t j = j0 + lane + 32 * k;
+            if (j < nnz) {
+                d[k] = data[j];
+                col[k] = ind[j];
+            } else {
+                d[k] = make_double2(0.0, 0.0);
+                col[k] = 0;
+            }
+        }
+        // row of element j0: the largest r with ptr[r] <= j0 (uniform over the warp)
+        uint64_t lo = 0, hi = nrows;
+        while (hi - lo > 1) {
+            const uint64_t mid = lo + ((hi - lo) >> 1);
+            if (static_cast<uint64_t>(ptr[mid]) <= j0)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        uint64_t row = lo;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const uint64_t j = j0 + lane + 32 * k;
+            if (j < nnz) {
+                while (static_cast<uint64_t>(ptr[row + 1]) <= j)
+                    row++;
+                const amp_t v = x[col[k]], a = x[row];
+                const double tr = d[k].x * v.x - d[k].y * v.y, ti = d[k].x * v.y + d[k].y * v.x;
+                acc[0] += double(a.x) * tr + double(a.y) * ti;
+            }
+        }
+    }
+    block_reduce_store<1>(acc, partials);
 }
 
 // ---- probabilities ------------------------------------------------------------------------------
@@ -1217,6 +1296,19 @@ void launch_pauli_sum_apply(int dtype, const void *in, void *out, uint64_t len,
                    (k_pauli_sum_apply<float2><<<grid, 256, 0, st>>>(static_cast<const float2 *>(in), static_cast<float2 *>(out), len, d_terms, nterms)),
                    (k_pauli_sum_apply<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(in), static_cast<double2 *>(out), len, d_terms, nterms)));
 }
+void launch_csr_expval_stream(int dtype, const void *state, const double2 *d_data, const uint32_t *d_ind,
+                              const uint64_t *d_ptr64, const uint32_t *d_ptr32, uint64_t nrows, uint64_t nnz,
+                              double *d_partials, cudaStream_t st) {
+    if (d_ptr32) {
+        DISPATCH_DTYPE(dtype,
+                       (k_csr_expval_stream<float2, uint32_t><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), d_data, d_ind, d_ptr32, nrows, nnz, d_partials)),
+                       (k_csr_expval_stream<double2, uint32_t><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), d_data, d_ind, d_ptr32, nrows, nnz, d_partials)));
+    } else {
+        DISPATCH_DTYPE(dtype,
+                       (k_csr_expval_stream<float2, uint64_t><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), d_data, d_ind, d_ptr64, nrows, nnz, d_partials)),
+                       (k_csr_expval_stream<double2, uint64_t><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), d_data, d_ind, d_ptr64, nrows, nnz, d_partials)));
+    }
+}
 void launch_csr_expval(int dtype, const void *state, const double2 *d_data, const uint32_t *d_ind,
                        const uint64_t *d_ptr, uint64_t nrows, int L, double *d_partials,
                        cudaStream_t st) {
@@ -1303,10 +1395,20 @@ void launch_transition_tile(int dtype, const void *bra, const void *ket, int n_b
         if ((mask >> b) & 1)
             tt.tile_pos[tt.n_tile++] = b;
     B2_ASSERT(tt.n_tile == 11 && tt.tile_pos[10] < n_bits);
+    uint32_t wire_positions = 0;
     for (int j = 0; j < nb; j++)
         for (int k = 0; k < tt.n_tile; k++)
-            if (tt.tile_pos[k] == h_bits[j])
+            if (tt.tile_pos[k] == h_bits[j]) {
                 tt.wire_tpos[j] = k;
+                wire_positions |= 1u << k;
+            }
+    { // the two highest non-wire tile positions (at most 6 of the 11 positions are wires)
+        int found = 0;
+        for (int k = tt.n_tile - 1; k >= 0 && found < 2; k--)
+            if (!((wire_positions >> k) & 1u))
+                tt.u_pos[1 - found++] = k;
+        B2_ASSERT(found == 2);
+    }
     const uint64_t n_tiles = uint64_t(1) << (n_bits - tt.n_tile);
     const int sms = sm_count_current_device();
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(sms)));

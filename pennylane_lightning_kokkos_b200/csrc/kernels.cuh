@@ -108,6 +108,11 @@ void launch_pauli_sum_apply(int dtype, const void *in, void *out, uint64_t len,
 void launch_csr_expval(int dtype, const void *state, const double2 *d_data, const uint32_t *d_ind,
                        const uint64_t *d_ptr, uint64_t nrows, int lanes_per_row,
                        double *d_partials, cudaStream_t st);
+// expectation value as a stream over the non-zeros (no per-row reduction); d_ptr32 (32-bit row
+// pointers, for nnz < 2^32) is used when not null, else d_ptr64
+void launch_csr_expval_stream(int dtype, const void *state, const double2 *d_data, const uint32_t *d_ind,
+                              const uint64_t *d_ptr64, const uint32_t *d_ptr32, uint64_t nrows, uint64_t nnz,
+                              double *d_partials, cudaStream_t st);
 void launch_csr_spmv(int dtype, const void *x, void *y, const double2 *d_data,
                      const uint32_t *d_ind, const uint64_t *d_ptr, uint64_t nrows,
                      int lanes_per_row, cudaStream_t st);

@@ -413,7 +413,11 @@ template <int DT, class np_c, class np_r> void bind_precision(py::module_ &m, co
                  return py::array_t<np_r>(jac);
              })
         .def("vjp", [](Adj &, const S &sv, const std::vector<ObsP> &obs, const Ops &ops, const std::vector<uint64_t> &tp,
-                       const std::vector<double> &dy) {
+                       const py::array &dy_in) {
+                 if (dy_in.dtype().kind() == 'c') // lightning_kokkos.py:709-712
+                     throw py::value_error("The vjp method only works with a real-valued dy when the tape is returning an expectation value");
+                 const auto dy_arr = py::array_t<double, py::array::c_style | py::array::forcecast>::ensure(dy_in);
+                 const std::vector<double> dy(dy_arr.data(), dy_arr.data() + dy_arr.size());
                  if (dy.size() != obs.size())
                      throw py::value_error("Number of observables in the tape must be the same as the length of dy in the vjp method");
                  std::vector<b2sv_obs *> hs;

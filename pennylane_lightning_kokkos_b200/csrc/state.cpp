@@ -101,6 +101,7 @@ CsrDevice::~CsrDevice() {
     cudaFree(data);
     cudaFree(ind);
     cudaFree(ptr);
+    cudaFree(ptr32);
 }
 
 std::shared_ptr<CsrDevice> csr_upload(int device, const cplx *data, const uint64_t *indices,
@@ -123,6 +124,15 @@ std::shared_ptr<CsrDevice> csr_upload(int device, const cplx *data, const uint64
     CUDA_CHECK(cudaMemcpy(m->data, data, sizeof(double2) * nnz, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(m->ind, ind32.data(), sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(m->ptr, indptr, sizeof(uint64_t) * (nrows + 1), cudaMemcpyHostToDevice));
+    if (nnz < (uint64_t(1) << 32)) {
+        std::vector<uint32_t> p32(nrows + 1);
+        for (size_t i = 0; i <= nrows; i++) {
+            B2_ABORT_IF(indptr[i] > nnz || (i > 0 && indptr[i] < indptr[i - 1]), "CSR indptr is not monotone");
+            p32[i] = static_cast<uint32_t>(indptr[i]);
+        }
+        CUDA_CHECK(cudaMalloc(&m->ptr32, sizeof(uint32_t) * (nrows + 1)));
+        CUDA_CHECK(cudaMemcpy(m->ptr32, p32.data(), sizeof(uint32_t) * (nrows + 1), cudaMemcpyHostToDevice));
+    }
     const double avg = nrows ? double(nnz) / double(nrows) : 1.0;
     int L = 1;
     while (L < 32 && L < avg)
@@ -1234,7 +1244,12 @@ double State::expval_csr(const CsrDevice &m) const {
     CUDA_CHECK(cudaSetDevice(device_));
     B2_ABORT_IF(world_ > 1, "CSR expectation values are not supported on sharded states");
     B2_ABORT_IF(m.nrows != local_length(), "CSR matrix dimension does not match the state vector");
-    launch_csr_expval(dtype_, d_state_, m.data, m.ind, m.ptr, m.nrows, m.lanes, d_partials_, stream_);
+    if (m.nnz > 0 && (getenv("B2SV_CSR_ROWS") == nullptr))
+        launch_csr_expval_stream(dtype_, d_state_, m.data, m.ind, m.ptr, m.ptr32, m.nrows, m.nnz, d_partials_,
+                                 stream_);
+    else
+        launch_csr_expval(dtype_, d_state_, m.data, m.ind, m.ptr, m.nrows, m.lanes, d_partials_, stream_);
+    bytes_moved += m.nnz * 20 + state_bytes();
     double r;
     finish_reduce(1, &r);
     return r;

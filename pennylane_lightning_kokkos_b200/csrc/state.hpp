@@ -28,6 +28,7 @@ struct CsrDevice {
     double2 *data = nullptr;
     uint32_t *ind = nullptr;
     uint64_t *ptr = nullptr;
+    uint32_t *ptr32 = nullptr; // 32-bit copy of the row pointers when nnz < 2^32
     uint64_t nrows = 0, nnz = 0;
     int lanes = 1;
     ~CsrDevice();
