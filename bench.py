@@ -58,7 +58,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-TOUCH = {"RX": 1.0, "RY": 1.0, "RZ": 1.0, "CNOT": 0.5}
+TOUCH = {"RX": 1.0, "RY": 1.0, "RZ": 1.0, "CNOT": 0.5, "CRX": 0.5, "CRY": 0.5, "CRZ": 0.5, "CRot": 0.5,
+         "IsingXX": 1.0, "IsingYY": 1.0, "IsingZZ": 1.0, "MultiRZ": 1.0, "SingleExcitation": 0.5,
+         "DoubleExcitation": 0.125, "Toffoli": 0.25, "ControlledPhaseShift": 0.25}
 METRIC = ("30q c128 gate-layer GB/s (reference-equivalent bytes: what one gate per HBM sweep moves "
           "for the same gates; roofline.achieved is the HBM traffic rate vs peak)")
 NVLINK_PEER_GBS = 770.0  # measured peer-copy GB/s per direction, B200_PROFILING.md
@@ -74,6 +76,30 @@ def layer_circuit(n, layers, seed=42):
                 ops.append((g, [w], False, [float(rng.uniform(0, 2 * np.pi))]))
         for w in range(n):
             ops.append(("CNOT", [w, (w + 1) % n], False, []))
+    return ops
+
+
+def controlled_circuit(n, layers, seed=42):
+    """--workload controlled: the controlled / parametric two- to four-qubit families of north_star on
+    neighbouring wires (CRX, CRot, IsingXX, SingleExcitation, DoubleExcitation, MultiRZ, Toffoli)."""
+    rng = np.random.default_rng(seed)
+    u = lambda: float(rng.uniform(0, 2 * np.pi))
+    ops = []
+    for _ in range(layers):
+        for w in range(0, n - 1, 2):
+            ops.append(("CRX", [w, w + 1], False, [u()]))
+        for w in range(1, n - 1, 2):
+            ops.append(("CRot", [w + 1, w], False, [u(), u(), u()]))
+        for w in range(0, n - 1, 2):
+            ops.append(("IsingXX", [w, w + 1], False, [u()]))
+        for w in range(1, n - 1, 2):
+            ops.append(("SingleExcitation", [w, w + 1], False, [u()]))
+        for w in range(0, n - 3, 4):
+            ops.append(("DoubleExcitation", [w, w + 1, w + 2, w + 3], False, [u()]))
+        for w in range(0, n - 2, 3):
+            ops.append(("MultiRZ", [w, w + 1, w + 2], False, [u()]))
+        for w in range(0, n - 2, 3):
+            ops.append(("Toffoli", [w + 2, w, w + 1], False, []))
     return ops
 
 
@@ -328,6 +354,71 @@ def sharded_parity(ops, b2dist, dist, torch, local_rank, world):
             "against": "oracle/np_oracle.py (full state gathered from all ranks + <Z> on a global and a local wire)"}
 
 
+def sharded_adjoint_sample(ops, b2dist, local_rank, world, dist, q_per_gpu=24, layers=7, terms=100):
+    """BASELINE config 3's ansatz on a state sharded over `world` GPUs (24 qubits per GPU): seconds
+    per adjoint Jacobian, max over ranks, plus a parity check of the same code path at 12 + g qubits
+    against the NumPy oracle."""
+    import time as _t
+
+    from cases import random_pauli_hamiltonian
+    from oracle import np_oracle as npo
+
+    bdir = os.path.join(ROOT, "benchmarks")
+    if bdir not in sys.path:
+        sys.path.insert(0, bdir)
+    import configs as cfgs
+    g = world.bit_length() - 1
+
+    def build(n, layers, terms):
+        circ = cfgs.hea_circuit(n, layers)
+        ham = random_pauli_hamiltonian(n, terms, seed=42)
+        tobs = []
+        for _, word in ham:
+            fac = [ops.NamedObsKokkos_C128(l, [w]) for l, w in word]
+            tobs.append(fac[0] if len(fac) == 1 else ops.TensorProdObsKokkos_C128(fac))
+        H = ops.HamiltonianKokkos_C128(np.array([c for c, _ in ham]), tobs)
+        names, wires, invs, params = cfgs.split(circ)
+        sv = b2dist.create_sharded_state(ops, n, np.complex128, local_rank)
+        sv.apply(names, wires, invs, params)
+        adj = ops.AdjointJacobianKokkos_C128()
+        oplist = adj.create_ops_list(names, [np.array(p) for p in params], wires, invs,
+                                     [np.zeros(0, dtype=complex) for _ in names])
+        tp = list(range(sum(1 for p in params if len(p))))
+        return circ, ham, sv, adj, oplist, H, tp
+
+    # parity at a size the oracle finishes in seconds
+    n_s = 13 + g
+    circ, ham, sv, adj, oplist, H, tp = build(n_s, 2, 12)
+    jac = adj.adjoint_jacobian(sv, [H], oplist, tp)
+    psi0 = np.zeros(1 << n_s, dtype=complex)
+    psi0[0] = 1
+    final = npo.apply_ops(psi0, n_s, circ)
+    hob = ("hamiltonian", [c for c, _ in ham],
+           [("tensor", [("named", l, [w]) for l, w in word]) for _, word in ham])
+    want = npo.adjoint_jacobian(final, n_s, [hob], circ, tp)
+    err = float(np.max(np.abs(jac - want)) / max(np.max(np.abs(want)), 1e-300))
+    del sv
+    dist.barrier()
+    n = q_per_gpu + g
+    circ, ham, sv, adj, oplist, H, tp = build(n, layers, terms)
+    adj.adjoint_jacobian(sv, [H], oplist, tp)
+    sv.sync()
+    dist.barrier()
+    t0 = _t.perf_counter()
+    jac = adj.adjoint_jacobian(sv, [H], oplist, tp)
+    dt = _t.perf_counter() - t0
+    import torch
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del sv
+    dist.barrier()
+    return {"s_per_jacobian": float(t.item()), "jac_norm": float(np.linalg.norm(jac)),
+            "workload": f"{n}q HEA {layers} layers, {len(tp)} params, adjoint Jacobian of a {terms}-term Pauli "
+                        f"Hamiltonian, c128, state sharded over {world} GPUs ({q_per_gpu} qubits per GPU)",
+            "parity": {"max_rel_err": err, "n": n_s, "world": world, "tolerance": 1e-12, "ok": bool(err < 1e-12),
+                       "against": "oracle/np_oracle.py adjoint_jacobian (2 layers, 12-term Hamiltonian)"}}
+
+
 def adjoint_sample(ops_module):
     """The second half of BASELINE.json's metric ("adjoint-Jacobian s/circuit"): BASELINE config 3
     (24 qubits, 504 parameters, 100-term Pauli Hamiltonian) through the binding's adjoint_jacobian on
@@ -370,7 +461,12 @@ def run_b200(args):
     g = world.bit_length() - 1
     assert (1 << g) == world, "number of GPUs must be a power of two"
     n = args.qubits + g  # weak scaling: 2^qubits amplitudes per GPU
-    circ = layer_circuit(n, args.layers, seed=42)
+    c64 = args.dtype == "c64"
+    np_dtype = np.complex64 if c64 else np.complex128
+    amp_bytes = 8 if c64 else 16
+    SV = ops.LightningKokkos_C64 if c64 else ops.LightningKokkos_C128
+    OPS = ops.OpsStructKokkos_C64 if c64 else ops.OpsStructKokkos_C128
+    circ = (controlled_circuit if args.workload == "controlled" else layer_circuit)(n, args.layers, seed=42)
     names, wires = [c[0] for c in circ], [c[1] for c in circ]
     invs, params = [c[2] for c in circ], [c[3] for c in circ]
 
@@ -382,13 +478,12 @@ def run_b200(args):
                 parity = sharded_parity(ops, b2dist, dist, torch, local_rank, world)
             except Exception as e:
                 parity = {"ok": False, "error": str(e)[:300], "world": world}
-        sv = b2dist.create_sharded_state(ops, n, np.complex128, local_rank)
+        sv = b2dist.create_sharded_state(ops, n, np_dtype, local_rank)
     else:
-        sv = ops.LightningKokkos_C128(n)
-    had = ops.OpsStructKokkos_C128(["Hadamard"] * n, [[] for _ in range(n)],
-                                   [[w] for w in range(n)], [False] * n)
+        sv = SV(n)
+    had = OPS(["Hadamard"] * n, [[] for _ in range(n)], [[w] for w in range(n)], [False] * n)
     sv.apply_ops(had)
-    oplist = ops.OpsStructKokkos_C128(names, params, wires, invs)
+    oplist = OPS(names, params, wires, invs)
     stream = torch.cuda.ExternalStream(sv.stream_ptr(), device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -468,19 +563,31 @@ def run_b200(args):
     blob_bytes = sv.last_upload_bytes() if hasattr(sv, "last_upload_bytes") else 0
     norm = sv.ExpectationValue("Identity", [0], [], np.zeros(0))
 
-    nbytes = ref_equiv_bytes(circ, n)  # whole job (all ranks)
+    nbytes = ref_equiv_bytes(circ, n, amp_bytes)  # whole job (all ranks)
     value = nbytes / (ms_dev / args.steps * 1e-3) / 1e9
     e2e_value = nbytes / (ms_e2e / args.steps * 1e-3) / 1e9
     peaks, which = measured_peaks()
-    sweep_bytes = 2.0 * 16 * (1 << args.qubits)  # per GPU, per launch of the tile kernel
+    sweep_bytes = 2.0 * amp_bytes * (1 << args.qubits)  # per GPU, per launch of the tile kernel
     avg_pass_ms = float(np.mean(pass_ms)) if pass_ms else None
     achieved = sweep_bytes / (avg_pass_ms * 1e-3) / 1e9 if avg_pass_ms else None
+    # ---- N > 1: the adjoint half of the metric on a sharded state (24 qubits per GPU, collective)
+    adj_sharded = None
+    if world > 1 and not args.no_adjoint and args.workload == "layers" and not c64:
+        try:
+            adj_sharded = sharded_adjoint_sample(ops, b2dist, local_rank, world, dist)
+        except Exception as e:
+            adj_sharded = {"s_per_jacobian": None, "error": str(e)[:300]}
     line = None
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        default_workload = args.workload == "layers" and not c64
+        if world == 1 and not args.no_cpu_baseline and default_workload:
             cpu, parity = cpu_baseline_and_parity(sv, n)
         cfg = static_config(world, args.qubits, args.layers)
+        if not default_workload:
+            cfg["workload"] = (f"{n}-qubit {args.dtype} --workload {args.workload}, {args.layers} layers = "
+                               f"{len(circ)} gates per step (not the BASELINE headline config)")
+            cfg["gates_per_step"] = len(circ)
         roof = {
             "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"] if achieved else None,
@@ -500,7 +607,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "c64 (f32)" if c64 else "c128 (f64)", "data": "synthetic",
             "config": cfg,
             "hbm_gbs": achieved, "hbm_frac": roof["frac"], "hbm_gbs_step": hbm_step,
             "schedule": {"sweeps_per_step": sweeps_per_step,
@@ -535,8 +642,10 @@ def run_b200(args):
                                      "frac_of_sum": (hbm_term + nvl_term) / (ms_dev / args.steps)}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if world == 1 and not args.no_adjoint:
+        if world == 1 and not args.no_adjoint and default_workload:
             line["adjoint_jacobian"] = adjoint_sample(ops)
+        if adj_sharded is not None:
+            line["adjoint_jacobian"] = adj_sharded
         print(json.dumps(line))
     del sv
     if world > 1:
@@ -554,6 +663,9 @@ def main():
     ap.add_argument("--qubits", type=int, default=30, help="qubits per GPU (weak scaling)")
     ap.add_argument("--ref-qubits", type=int, default=30, help="state size of the reference arm's sample")
     ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--workload", default="layers", choices=["layers", "controlled"],
+                    help="layers = BASELINE config 2 (default); controlled = CRX/CRot/Ising/excitation/MultiRZ layers")
+    ap.add_argument("--dtype", default="c128", choices=["c128", "c64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-adjoint", action="store_true", help="skip the config-3 adjoint Jacobian sample")

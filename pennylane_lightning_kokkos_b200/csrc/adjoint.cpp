@@ -157,7 +157,7 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
     std::vector<double> jac_host(n_obs * tp_size, 0.0);
     // B2SV_ADJOINT_RUNS=0 turns the run path off (A/B measurements); sharded states use the per-op path
     const char *runs_env = getenv("B2SV_ADJOINT_RUNS");
-    const bool runs_enabled = !sv.sharded() && (runs_env == nullptr || atoi(runs_env) != 0);
+    const bool runs_enabled = runs_env == nullptr || atoi(runs_env) != 0;
     double *d_tr_scratch = nullptr, *d_tr_out = nullptr;
     auto one_qubit_matrix = [&](const GateOp &op, int *bit, cplx u[4]) {
         if (op.wires.size() != 1 || !op.matrix.empty())
@@ -242,10 +242,23 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
                 CUDA_CHECK(cudaMallocAsync(&d_tr_out, sizeof(double) * kTransitionVals, st));
             }
             std::vector<double> vals(kTransitionVals);
-            for (size_t o = 0; o < n_obs; o++) {
-                for (size_t c0 = 0; c0 < wires_needed.size(); c0 += kTransitionBits) {
-                    const int nb = static_cast<int>(std::min<size_t>(kTransitionBits, wires_needed.size() - c0));
-                    lambda->transition_1q_to(*H[o], wires_needed.data() + c0, nb, d_tr_scratch, d_tr_out);
+            for (size_t c0 = 0; c0 < wires_needed.size(); c0 += kTransitionBits) {
+                const int nb = static_cast<int>(std::min<size_t>(kTransitionBits, wires_needed.size() - c0));
+                // sharded states: the chunk's qubits come into the shard on lambda and on every H_lambda
+                // (identical layouts, hence identical exchanges), then each rank sums over its shard
+                int phys[kTransitionBits];
+                if (sv.sharded()) {
+                    uint64_t mask = 0;
+                    for (int t = 0; t < nb; t++)
+                        mask |= bit(wires_needed[c0 + t]);
+                    lambda->ensure_local(mask);
+                    for (auto &h : H)
+                        h->ensure_local(mask);
+                }
+                for (int t = 0; t < nb; t++)
+                    phys[t] = lambda->phys_bit(wires_needed[c0 + t]);
+                for (size_t o = 0; o < n_obs; o++) {
+                    lambda->transition_1q_to(*H[o], phys, nb, d_tr_scratch, d_tr_out);
                     CUDA_CHECK(cudaMemcpyAsync(vals.data(), d_tr_out, sizeof(double) * kTransitionVals,
                                                cudaMemcpyDeviceToHost, st));
                     CUDA_CHECK(cudaStreamSynchronize(st));

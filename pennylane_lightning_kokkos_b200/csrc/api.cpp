@@ -21,6 +21,7 @@ struct b2sv_obs {
 };
 struct b2sv_ops {
     OpsData d;
+    mutable std::shared_ptr<PlanCache> plan; // schedule (+ CUDA graph) of the last state geometry it ran on
 };
 struct b2sv_csr {
     std::shared_ptr<CsrDevice> m;
@@ -272,7 +273,10 @@ int b2sv_apply_matrix(b2sv_state *s, const int64_t *wires, int nw, int inverse,
 int b2sv_apply_ops(b2sv_state *s, const b2sv_ops *ops, int adjoint) {
     return guard([&] {
         B2_ABORT_IF(!ops, "null ops handle");
-        st(s).apply_ops(ops->d.ops, adjoint != 0);
+        if (adjoint)
+            st(s).apply_ops(ops->d.ops, true);
+        else
+            st(s).apply_ops_cached(ops->d.ops, ops->plan);
     });
 }
 int b2sv_apply_generator(b2sv_state *s, const char *name, const int64_t *wires, int nw, int adj,

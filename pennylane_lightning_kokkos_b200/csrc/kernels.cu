@@ -725,56 +725,75 @@ __global__ void __launch_bounds__(kReduceThreads)
 
 // Expectation value of a CSR matrix as a pure stream over the non-zeros:
 //   <psi|A|psi> = sum_j Re( conj(psi[row(j)]) * data[j] * psi[ind[j]] ),
-// no per-row reduction at all. A warp takes chunks of 32 x K consecutive non-zeros (coalesced 16-byte
-// and 4-byte streams, all loads of a chunk in flight together), finds the row of the chunk's first
-// element by one binary search over the row pointers and then advances its row cursor monotonically.
-// The gathers psi[ind], psi[row] hit L2 for states up to ~100 MB. Deterministic: every lane sums in a
-// fixed order, the block and grid reductions are fixed-order too.
+// no per-row reduction at all. Every warp owns one contiguous range of the non-zeros: it finds the row
+// of its first element by ONE binary search over the row pointers and from then on only advances its
+// row cursor (row pointers come from L1); the range is walked in chunks of 32 x K elements whose
+// 16-byte and 4-byte loads are all issued before the previous chunk is consumed (register double
+// buffering). The gathers psi[ind], psi[row] hit L2 for states up to ~100 MB. Deterministic: every
+// lane sums in a fixed order, the block and grid reductions are fixed-order too.
 template <typename amp_t, typename ptr_t>
 __global__ void __launch_bounds__(kReduceThreads)
     k_csr_expval_stream(const amp_t *__restrict__ x, const double2 *__restrict__ data,
                         const uint32_t *__restrict__ ind, const ptr_t *__restrict__ ptr, uint64_t nrows,
                         uint64_t nnz, double *__restrict__ partials) {
-    constexpr int K = 8;
+    constexpr int K = 4;
+    constexpr uint64_t CH = 32 * K;
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
-    const uint64_t nchunks = (nnz + 32 * K - 1) / (32 * K);
+    // ranges are whole chunks, so every chunk belongs to exactly one warp
+    const uint64_t nchunks = (nnz + CH - 1) / CH;
+    const uint64_t per = (nchunks + nwarps - 1) / nwarps;
+    const uint64_t c_beg = warp * per, c_end = min(nchunks, c_beg + per);
     double acc[1] = {0.0};
-    for (uint64_t c = warp; c < nchunks; c += nwarps) {
-        const uint64_t j0 = c * (32 * K);
-        double2 d[K];
-        uint32_t col[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const uint64_t j = j0 + lane + 32 * k;
-            if (j < nnz) {
-                d[k] = data[j];
-                col[k] = ind[j];
-            } else {
-                d[k] = make_double2(0.0, 0.0);
-                col[k] = 0;
-            }
-        }
-        // row of element j0: the largest r with ptr[r] <= j0 (uniform over the warp)
-        uint64_t lo = 0, hi = nrows;
+    if (c_beg < c_end) {
+        uint64_t lo = 0, hi = nrows; // the largest r with ptr[r] <= first element of the range
+        const uint64_t jfirst = c_beg * CH;
         while (hi - lo > 1) {
             const uint64_t mid = lo + ((hi - lo) >> 1);
-            if (static_cast<uint64_t>(ptr[mid]) <= j0)
+            if (static_cast<uint64_t>(__ldg(ptr + mid)) <= jfirst)
                 lo = mid;
             else
                 hi = mid;
         }
         uint64_t row = lo;
+        uint64_t next_start = static_cast<uint64_t>(__ldg(ptr + row + 1)); // first element of row + 1
+        double2 d[K], dn[K];
+        uint32_t col[K], coln[K];
+        auto load = [&](uint64_t c, double2(&dd)[K], uint32_t(&cc)[K]) {
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            const uint64_t j = j0 + lane + 32 * k;
-            if (j < nnz) {
-                while (static_cast<uint64_t>(ptr[row + 1]) <= j)
-                    row++;
-                const amp_t v = x[col[k]], a = x[row];
-                const double tr = d[k].x * v.x - d[k].y * v.y, ti = d[k].x * v.y + d[k].y * v.x;
-                acc[0] += double(a.x) * tr + double(a.y) * ti;
+            for (int k = 0; k < K; k++) {
+                const uint64_t j = c * CH + lane + 32 * k;
+                if (j < nnz) {
+                    dd[k] = data[j];
+                    cc[k] = ind[j];
+                } else {
+                    dd[k] = make_double2(0.0, 0.0);
+                    cc[k] = 0;
+                }
+            }
+        };
+        load(c_beg, d, col);
+        for (uint64_t c = c_beg; c < c_end; c++) {
+            if (c + 1 < c_end)
+                load(c + 1, dn, coln);
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const uint64_t j = c * CH + lane + 32 * k;
+                if (j < nnz) {
+                    while (next_start <= j) { // empty rows are skipped the same way
+                        row++;
+                        next_start = static_cast<uint64_t>(__ldg(ptr + row + 1));
+                    }
+                    const amp_t v = x[col[k]], a = x[row];
+                    const double tr = d[k].x * v.x - d[k].y * v.y, ti = d[k].x * v.y + d[k].y * v.x;
+                    acc[0] += double(a.x) * tr + double(a.y) * ti;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                d[k] = dn[k];
+                col[k] = coln[k];
             }
         }
     }

@@ -914,6 +914,78 @@ void State::apply_ops(const std::vector<GateOp> &ops, bool adjoint) {
     flush();
 }
 
+void State::apply_ops_cached(const std::vector<GateOp> &ops, std::shared_ptr<PlanCache> &cache) {
+    const char *off = getenv("B2SV_PLAN_CACHE");
+    if (comm_ || !fuse_ || ops.empty() || (off && atoi(off) == 0)) {
+        apply_ops(ops, false);
+        return;
+    }
+    CUDA_CHECK(cudaSetDevice(device_));
+    const SchedConfig cfg = sched_config();
+    std::ostringstream ks;
+    ks << n_ << ':' << dtype_ << ':' << cfg.B << ':' << cfg.R << ':' << cfg.low << ':' << cfg.max_heavy << ':'
+       << cfg.factor << ':' << cfg.fuse_store << ':' << n_eff_;
+    const std::string key = ks.str();
+    if (!cache || cache->key != key) {
+        std::vector<Prim> prims;
+        for (const auto &op : ops)
+            lower(op, false, prims);
+        auto pc = std::make_shared<PlanCache>();
+        pc->key = key;
+        if (!prims.empty())
+            pc->passes = build_schedule(prims, cfg);
+        pc->graphable = true;
+        for (const Pass &ps : pc->passes)
+            pc->graphable = pc->graphable && !ps.is_matk;
+        cache = std::move(pc);
+    }
+    if (cache->passes.empty())
+        return;
+    // small states are launch-bound: replay the passes as one CUDA graph
+    int graph_max_bits = 24;
+    if (const char *e = getenv("B2SV_GRAPH_MAX_BITS"))
+        graph_max_bits = atoi(e);
+    if (!cache->graphable || tracing_ || n_eff_ > graph_max_bits) {
+        upload_and_run(cache->passes);
+        return;
+    }
+    if (!cache->graph || cache->graph_state != d_state_ || cache->graph_stream != stream_) {
+        if (cache->graph) {
+            cudaGraphExecDestroy(cache->graph);
+            cache->graph = nullptr;
+        }
+        const uint64_t s0 = sweeps, l0 = launches, b0 = bytes_moved;
+        cudaGraph_t g = nullptr;
+        CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        try {
+            upload_and_run(cache->passes);
+        } catch (...) {
+            cudaStreamEndCapture(stream_, &g);
+            if (g)
+                cudaGraphDestroy(g);
+            throw;
+        }
+        CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
+        sweeps = s0, launches = l0, bytes_moved = b0; // capturing launched nothing
+        cudaError_t e = cudaGraphInstantiate(&cache->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { // no graph: plain launches
+            cudaGetLastError();
+            cache->graph = nullptr;
+            cache->graphable = false;
+            upload_and_run(cache->passes);
+            return;
+        }
+        cache->graph_state = d_state_;
+        cache->graph_stream = stream_;
+    }
+    touch();
+    CUDA_CHECK(cudaGraphLaunch(cache->graph, stream_));
+    sweeps += cache->passes.size();
+    launches += 1;
+    bytes_moved += 2 * state_bytes() * cache->passes.size();
+}
+
 void State::apply_ops_to_all(const std::vector<State *> &states, const std::vector<GateOp> &ops) {
     if (states.empty() || ops.empty())
         return;
@@ -1281,13 +1353,19 @@ void State::transition_1q_to(const State &bra, const int *bits, int nb, double *
     CUDA_CHECK(cudaSetDevice(device_));
     B2_ABORT_IF(bra.n_ != n_ || bra.dtype_ != dtype_ || bra.device_ != device_,
                 "state vectors are not compatible");
-    B2_ABORT_IF(world_ > 1, "internal: batched transition sums are not available on sharded states");
+    // sharded states: `bits` are PHYSICAL, shard-local positions in a layout both states share (the
+    // caller made the wires local); every rank sums over its shard and the sums are all-reduced
+    B2_ABORT_IF(world_ > 1 && !same_layout(bra), "internal: transition sums need identical layouts");
+    for (int j = 0; j < nb; j++)
+        B2_ABORT_IF(bits[j] < 0 || bits[j] >= n_local_, "internal: transition sums need shard-local bits");
     order_after(stream_, bra.stream_);
     if (n_eff_ >= 11 && n_eff_ == n_local_)
         launch_transition_tile(dtype_, bra.d_state_, d_state_, n_local_, bits, nb, d_scratch, stream_);
     else
         launch_transition_1q(dtype_, bra.d_state_, d_state_, local_length(), bits, nb, d_scratch, stream_);
     launch_finalize(d_scratch, kReduceBlocks, kTransitionVals, d_dst, stream_);
+    if (comm_)
+        comm_allreduce_sum(comm_.get(), d_dst, kTransitionVals, stream_);
     order_after(bra.stream_, stream_);
     reduce_launches += 2;
     bytes_moved += 2 * state_bytes();

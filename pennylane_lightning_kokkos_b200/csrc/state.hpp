@@ -36,6 +36,23 @@ struct CsrDevice {
 std::shared_ptr<CsrDevice> csr_upload(int device, const cplx *data, const uint64_t *indices,
                                       const uint64_t *indptr, size_t nnz, size_t nrows);
 
+// What a State keeps about an op list it has applied before (owned by the op-list handle): the tile
+// passes of the fused schedule and, for small states, a CUDA graph of their launches. Repeated
+// circuits (optimisation loops re-applying one handle) skip lowering, scheduling and per-kernel
+// launch overhead.
+struct PlanCache {
+    std::string key;           // state geometry + scheduler settings the plan was built for
+    std::vector<Pass> passes;
+    bool graphable = false;    // no generic-matrix pass (those synchronise the stream)
+    cudaGraphExec_t graph = nullptr;
+    void *graph_state = nullptr; // device buffer and stream the graph was captured for
+    cudaStream_t graph_stream = nullptr;
+    ~PlanCache() {
+        if (graph)
+            cudaGraphExecDestroy(graph);
+    }
+};
+
 class State {
   public:
     State(int num_qubits, int dtype, int device, int rank = 0, int world = 1,
@@ -80,6 +97,8 @@ class State {
     // ---- gates
     void apply_gate(const GateOp &op);
     void apply_ops(const std::vector<GateOp> &ops, bool adjoint);
+    // the same, forward direction, remembering the schedule (and a CUDA graph) in `cache`
+    void apply_ops_cached(const std::vector<GateOp> &ops, std::shared_ptr<PlanCache> &cache);
     // the same op list applied to several states of identical shape (adjoint sweep: lambda and every
     // H_lambda): lowered and scheduled once, the passes launched on each state
     static void apply_ops_to_all(const std::vector<State *> &states, const std::vector<GateOp> &ops);

@@ -289,3 +289,45 @@ def test_adjoint_param_count_check_is_lazy(ops):
     assert jac.shape == (1, 2)
     with pytest.raises(ops.PLException):
         adj.adjoint_jacobian(sv, ob, oplist, [0, 1, 2])  # now the loop reaches the Rot
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.complex128, 1e-12), (np.complex64, 2e-5)])
+def test_op_list_handle_replay_matches_reference(ops, ref, dtype, tol):
+    """An op-list handle applied again re-uses its schedule and, on small states, a CUDA graph of the
+    pass launches; every replay must give what the reference gives for the same gates."""
+    n = 14
+    sfx = "C128" if dtype == np.complex128 else "C64"
+    circ = layered_circuit(n, 3, seed=21) + [("CRX", [0, n - 1], False, [0.4]), ("Toffoli", [3, 1, 7], False, [])]
+    names, wires, invs, params = split(circ)
+    handle = getattr(ops, "OpsStructKokkos_" + sfx)(names, params, wires, invs)
+    sv = getattr(ops, "LightningKokkos_" + sfx)(n)
+    rsv = ref.RefStateVector(n, dtype)
+    got = np.zeros(1 << n, dtype=dtype)
+    for rep in range(3):  # build + capture, replay, replay
+        sv.apply_ops(handle)
+        rsv.apply_ops(circ)
+        sv.DeviceToHost(got)
+        assert rel_err(got, rsv.d2h()) < tol * (rep + 1)
+    # a second state of another size invalidates the cached plan; a second state of the same size
+    # needs its own graph (different buffer)
+    sv2 = getattr(ops, "LightningKokkos_" + sfx)(n)
+    sv2.apply_ops(handle)
+    rsv2 = ref.RefStateVector(n, dtype)
+    rsv2.apply_ops(circ)
+    sv2.DeviceToHost(got)
+    assert rel_err(got, rsv2.d2h()) < tol
+    small = getattr(ops, "OpsStructKokkos_" + sfx)(["Hadamard", "CNOT"], [[], []], [[0], [0, 1]], [False, False])
+    for nn in (2, 5, 2):
+        s3 = getattr(ops, "LightningKokkos_" + sfx)(nn)
+        s3.apply_ops(small)
+        out = np.zeros(1 << nn, dtype=dtype)
+        s3.DeviceToHost(out)
+        want = np.zeros(1 << nn, dtype=complex)
+        want[0] = want[3 << (nn - 2)] = 2 ** -0.5
+        assert np.max(np.abs(out - want)) < tol
+    # the <Z> cache must follow graph replays too
+    z0 = sv.expval_z_all().copy()
+    sv.apply_ops(handle)
+    rsv.apply_ops(circ)
+    z1 = np.array([rsv.expval_named("PauliZ", [w]) for w in range(n)])
+    assert np.max(np.abs(sv.expval_z_all() - z1)) < 10 * tol and np.max(np.abs(z0 - z1)) > 1e-3
