@@ -66,6 +66,19 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
         H.push_back(lambda->clone_on_stream());
         obs[o]->apply_in_place(*H[o]);
     }
+    if (sv.sharded()) {
+        // applying an observable may leave H_lambda in another qubit layout than lambda (a Hamiltonian
+        // built term by term starts from a fresh buffer); the sweep needs them identical, and they
+        // stay identical from here on because every state sees the same ops
+        bool same = true;
+        for (auto &h : H)
+            same = same && lambda->same_layout(*h);
+        if (!same) {
+            lambda->normalize_layout();
+            for (auto &h : H)
+                h->normalize_layout();
+        }
+    }
     std::unique_ptr<State> mu; // only for generators that are not Pauli words
     cudaStream_t st = lambda->stream();
     double *d_jac = nullptr;

@@ -637,7 +637,7 @@ void State::run_sharded_pipelined(const std::vector<ShardStep> &steps, int c) {
     // SMs the exchange kernel occupies while tile passes run beside it. The passes are the longer
     // stream at every world size measured (profiles/r2_trace*.json), and their speed follows the
     // number of SMs they keep, so the exchange gets just enough SMs to stay hidden behind them.
-    int x_sms = 12;
+    int x_sms = 16;
     if (const char *e = getenv("B2SV_EXCHANGE_SMS"))
         x_sms = std::max(4, std::min(64, atoi(e)));
     const int x_sms_extra = 4; // exchanges of two or more bits move more data per pass beside them
