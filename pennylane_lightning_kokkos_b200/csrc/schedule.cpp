@@ -513,6 +513,13 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                 free_bits--;
             }
         }
+        // The pass is built for the swizzled tile layout first; when no round keeps one of the lowest SW
+        // tile bits in registers (so the lanes of a shared-memory wavefront can always enumerate the
+        // bank groups through those bits) it is rebuilt for the PLAIN layout, which the load warps can
+        // fill with bulk async copies of whole HBM runs (cp.async.bulk) instead of one 16-byte cp.async
+        // per amplitude.
+        auto make_pass = [&](bool plain) -> Pass {
+        auto PH = [&](uint32_t v) { return plain ? v : phys_slot(v, B, cfg.SW); };
         Pass ps;
         ps.hdr.low_bits = low;
         {
@@ -581,7 +588,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                 DevCx &c = ps.hdr.cx[n_cx++];
                 c.gcm = p.cmask;
                 c.gcv = p.cval;
-                c.vec = static_cast<uint16_t>(phys_slot(Mcol[jt], B, cfg.SW));
+                c.vec = static_cast<uint16_t>(PH(Mcol[jt]));
                 c.round = static_cast<uint16_t>(round_idx);
             }
             ps.n_absorbed++;
@@ -704,11 +711,11 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                 for (int s = 0; s < R; s++) {
                     rbits[s] = static_cast<uint8_t>(slot_bits[s]);
                     ps.hdr.round_poff[n_rounds][s] =
-                        static_cast<uint16_t>(phys_slot(Mcol[slot_bits[s]], B, cfg.SW));
+                        static_cast<uint16_t>(PH(Mcol[slot_bits[s]]));
                 }
                 for (int j = 0; j < B; j++)
                     if (!(reg_mask & (1u << j)))
-                        free_cols.push_back(((1u << j) << 16) | phys_slot(Mcol[j], B, cfg.SW));
+                        free_cols.push_back(((1u << j) << 16) | PH(Mcol[j]));
                 B2_ASSERT(free_cols.size() <= static_cast<size_t>(kMaxFreeBits));
                 // Bank-conflict-free gathers: the lanes that share one shared-memory wavefront
                 // (8 x 16 B or 16 x 8 B) differ in the lowest SW thread-id bits, so give those
@@ -760,7 +767,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                 for (size_t k = 0; k < lanes.size(); k++) {
                     const int j = lanes[k];
                     ps.hdr.round_col[last][k] =
-                        ((1u << j) << 16) | phys_slot(McolLast[j], B, cfg.SW);
+                        ((1u << j) << 16) | PH(McolLast[j]);
                     ps.hdr.store_free[k] = spread(Lcol[j]);
                 }
                 for (int k = 0; k < R; k++) {
@@ -809,11 +816,36 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
             }
         }
         for (int j = 0; j < B; j++)
-            ps.hdr.final_col[j] = static_cast<uint16_t>(phys_slot(Mcol[j], B, cfg.SW));
+            ps.hdr.final_col[j] = static_cast<uint16_t>(PH(Mcol[j]));
         ps.hdr.n_cx = n_cx;
         ps.hdr.round_begin[n_rounds] = static_cast<uint16_t>(ps.ops.size());
         ps.hdr.n_rounds = n_rounds;
         ps.hdr.n_ops = static_cast<int32_t>(ps.ops.size());
+        ps.hdr.plain_layout = plain ? 1 : 0;
+        {
+            int run_bits = 0;
+            while (run_bits < B && ps.hdr.tile_bits[run_bits] == run_bits)
+                run_bits++;
+            ps.hdr.bulk_run_bits = static_cast<uint8_t>(std::max(run_bits, low));
+        }
+        return ps;
+        };
+        Pass ps = make_pass(false);
+        if (cfg.bulk && low >= cfg.SW) {
+            // A bulk copy costs the SM's copy engine ~46 cycles whatever its size (B300_MICROARCH.md,
+            // "TMA service/SM"), so 512-byte runs cap a tile at ~11 B/cycle -- measured 10 % slower than
+            // the per-amplitude cp.async loader (profiles/r2_tile_bulk_ab.md). Bulk loads are used where
+            // the tile's low bits form runs of at least cfg.bulk_min_run_bits amplitudes (>= 4 KiB).
+            int run_bits = 0;
+            while (run_bits < B && ps.hdr.tile_bits[run_bits] == run_bits)
+                run_bits++;
+            bool eligible = ps.hdr.n_rounds >= 1 && run_bits >= cfg.bulk_min_run_bits;
+            for (int rd = 0; rd < ps.hdr.n_rounds && eligible; rd++)
+                for (int k = 0; k < R; k++)
+                    eligible = eligible && ps.hdr.round_regbits[rd][k] >= cfg.SW;
+            if (eligible)
+                ps = make_pass(true);
+        }
         passes.push_back(std::move(ps));
     }
     return passes;

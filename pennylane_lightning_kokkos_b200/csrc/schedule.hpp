@@ -87,7 +87,11 @@ struct alignas(16) DevPassHeader {
     // how the tile leaves the SM: 0 = store phase (worker threads copy shared -> HBM through the
     // final address map); 1 = fused store, the last round writes its registers straight to HBM
     uint8_t fused_store;
-    uint8_t pad2_[13];
+    // 1: the tile lives in shared memory in plain order (slot = tile-local index) and is filled by bulk
+    // async copies; 0: XOR-swizzled slots, filled amplitude by amplitude (cp.async)
+    uint8_t plain_layout;
+    uint8_t bulk_run_bits; // plain layout: the tile bits 0 .. bulk_run_bits-1 are the index bits of the same number
+    uint8_t pad2_[11];
     // global index offsets (already pushed through the permutations absorbed after the last round):
     // of thread-id bit k of the last round, of register slot s, and of conditional toggle c
     uint64_t store_free[kMaxFreeBits];
@@ -144,6 +148,9 @@ struct SchedConfig {
     // grow the tile by marginal gain over a look-ahead window instead of first come, first served;
     // off by default: no fewer passes on the circuits tried, and it costs host time per pass
     bool lookahead = false;
+    // allow plain-layout passes (bulk async tile loads) where the rounds permit it
+    bool bulk = false;
+    int bulk_min_run_bits = 8; // contiguous amplitudes per bulk copy: 2^8 x 16 B = 4 KiB (complex128)
 };
 
 // contiguous low index bits kept in every tile (2^low amplitudes per HBM run); B2SV_TILE_LOW overrides

@@ -924,7 +924,7 @@ void State::apply_ops_cached(const std::vector<GateOp> &ops, std::shared_ptr<Pla
     const SchedConfig cfg = sched_config();
     std::ostringstream ks;
     ks << n_ << ':' << dtype_ << ':' << cfg.B << ':' << cfg.R << ':' << cfg.low << ':' << cfg.max_heavy << ':'
-       << cfg.factor << ':' << cfg.fuse_store << ':' << n_eff_;
+       << cfg.factor << ':' << cfg.fuse_store << ':' << n_eff_ << ':' << cfg.bulk << ':' << cfg.bulk_min_run_bits;
     const std::string key = ks.str();
     if (!cache || cache->key != key) {
         std::vector<Prim> prims;
@@ -1045,6 +1045,12 @@ SchedConfig State::sched_config() const {
     cfg.n_local = n_local_;
     cfg.n_alloc = n_eff_;
     cfg.fuse = fuse_;
+    // bulk async tile loads (plain-layout passes); B2SV_BULK=0 keeps every pass on the swizzled layout
+    cfg.bulk = true;
+    if (const char *e = getenv("B2SV_BULK"))
+        cfg.bulk = atoi(e) != 0;
+    if (const char *e = getenv("B2SV_BULK_MIN_RUN")) // experiments: 5 = every eligible pass (512-byte copies)
+        cfg.bulk_min_run_bits = std::max(cfg.low, atoi(e));
     return cfg;
 }
 

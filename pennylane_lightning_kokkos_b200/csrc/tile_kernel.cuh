@@ -70,6 +70,26 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t *mbar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(mbar))
                  : "memory");
 }
+// Bulk async copy (TMA engine, non-tensor form): `bytes` contiguous bytes global -> shared, completion
+// counted in bytes on the mbarrier. Addresses and size are multiples of 16.
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+}
+// one arrival that also announces `bytes` of bulk-copy traffic to wait for
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *mbar, uint32_t bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(
+                     smem_u32(mbar)),
+                 "r"(bytes)
+                 : "memory");
+}
+// generic-proxy accesses of this thread (tile gathers / scatters) before async-proxy writes that follow
+// the hand-off (the next bulk copy into the same buffer)
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t *mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count)
                  : "memory");
@@ -470,8 +490,10 @@ struct TileInfo {
 // unfactored dense rounds of 2..5 gates (one-gate dense rounds are in every variant). A pass is
 // launched on the leanest variant that covers its rounds: code the pass never runs would still cost
 // it registers (ptxas allocates for the union of all paths of the round loop).
+// BULK: the pass uses the plain tile layout and the load warps fill it with bulk async copies
+// (cp.async.bulk); a template parameter so that neither path costs the other registers.
 template <typename real, int B, int R, int GT, int NG, int NB, bool FACT, bool INTERP, bool DENSEK,
-          bool PROF>
+          bool PROF, bool BULK>
 __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
     tile_exec_kernel(typename AmpT<real>::type *__restrict__ state,
                      const __grid_constant__ PassParams pp, uint64_t rank_bits,
@@ -514,7 +536,9 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
         for (int i = threadIdx.x; i < n_ops * static_cast<int>(sizeof(DevOp) / 16); i += NTHREADS)
             odst[i] = osrc[i];
         if (threadIdx.x < kTileBuffers) {
-            mbar_init(&full[threadIdx.x], kLoadThreads + 1);
+            // plain-layout passes: one arrival (with the byte count of the bulk copies); swizzled
+            // passes: every load thread's cp.async group + the publisher of the tile's facts
+            mbar_init(&full[threadIdx.x], BULK ? 1 : kLoadThreads + 1);
             // direct-store passes: every worker warp releases the buffer after its last gather
             mbar_init(&empty[threadIdx.x], (pp.hdr.fused_store == 1 && !gsync) ? GT / 32 : 1);
         }
@@ -531,6 +555,7 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
     }
     const int n_rounds = pp.hdr.n_rounds;
     const uint32_t lowmask = (1u << low) - 1u;
+    constexpr bool plain = BULK;
     __syncthreads();
 
     // tiles of this CTA: k = 0 .. n_mine-1  <->  global tile blockIdx.x + k * gridDim.x
@@ -586,9 +611,23 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
                 }
                 if (ptid == 0) {
                     tinfo[bi].tb = tb;
-                    mbar_arrive(&full[bi]); // release: the stores above are visible to whoever acquires
+                    if (plain)
+                        mbar_arrive_expect_tx(&full[bi], static_cast<uint32_t>(TILE * sizeof(amp_t)));
+                    else
+                        mbar_arrive(&full[bi]); // release: the stores above are visible to whoever acquires
                 }
             }
+            if constexpr (plain) {
+                // plain layout: a tile is 2^(B-low) runs of 2^low amplitudes, each contiguous in HBM and
+                // in shared memory -- one bulk async copy per run, no per-amplitude address arithmetic
+                amp_t *buf = tiles + bi * TILE;
+                const int run = pp.hdr.bulk_run_bits; // leading tile bits that are index bits 0..run-1
+                const uint32_t run_bytes = static_cast<uint32_t>(sizeof(amp_t)) << run;
+                for (int r = ptid; r < (TILE >> run); r += kLoadThreads)
+                    bulk_load(buf + (r << run), state + (tb | rowoff[r << (run - low)]), run_bytes, &full[bi]);
+                if constexpr (PROF)
+                    p_issue += clock64() - p_t1;
+            } else {
             // element i = e * 128 + ptid: the thread part of both addresses is loop-invariant, the
             // e part is a compile-time slot offset and a uniform (constant-bank) index offset
             amp_t *buf = tiles + bi * TILE;
@@ -600,6 +639,7 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
             cp_async_arrive(&full[bi]);
             if constexpr (PROF)
                 p_issue += clock64() - p_t1;
+            }
         }
         if constexpr (PROF) {
             if (ptid == 0) {
@@ -672,12 +712,16 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
             // as soon as every thread of the group has gathered from it
             const int fused = rd == n_rounds - 1 ? pp.hdr.fused_store : 0;
             if (fused == 1 && gsync) {
+                if constexpr (plain)
+                    fence_proxy_async();
                 group_sync(1 + grp, GT);
                 if (tid == 0)
                     mbar_arrive(&empty[bi]);
             } else if (fused == 1) {
                 // no group barrier: the buffer is handed back once all warps of the group arrived,
                 // and a warp whose stores are out moves on to its next tile on its own
+                if constexpr (plain)
+                    fence_proxy_async();
                 __syncwarp();
                 if ((tid & 31) == 0)
                     mbar_arrive(&empty[bi]);
@@ -800,6 +844,8 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
                 state[tb | rowoff[i >> low] | (i & lowmask)] = tile[x];
             }
         }
+        if constexpr (plain)
+            fence_proxy_async();
         group_sync(1 + grp, GT); // every thread of the group is done with this buffer (and xoff)
         if (tid == 0)
             mbar_arrive(&empty[bi]);
@@ -834,11 +880,11 @@ bool tile_prof() {
     return v;
 }
 template <typename real, int B, int R, int GT, int NG, int NB, bool FACT, bool INTERP, bool DENSEK,
-          bool PROF>
+          bool PROF, bool BULK>
 void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
                     cudaStream_t stream, int max_ctas) {
     using amp_t = typename AmpT<real>::type;
-    auto kern = tile_exec_kernel<real, B, R, GT, NG, NB, FACT, INTERP, DENSEK, PROF>;
+    auto kern = tile_exec_kernel<real, B, R, GT, NG, NB, FACT, INTERP, DENSEK, PROF, BULK>;
     constexpr size_t smem = tile_smem_bytes<real, B, NB>();
     static uint64_t configured = 0; // one bit per device: the attribute is per device
     if (first_use_on_device(configured))
@@ -857,8 +903,8 @@ void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_
 }
 
 // Picks the leanest kernel variant that covers the rounds of the pass.
-template <typename real, int B, int R>
-void launch_tile_pass_t(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
+template <typename real, int B, int R, bool BULK>
+void launch_tile_pass_v(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
                         cudaStream_t stream, int max_ctas) {
     bool fact = false, interp = false, densek = false;
     for (int rd = 0; rd < pp.hdr.n_rounds; rd++) {
@@ -868,15 +914,15 @@ void launch_tile_pass_t(void *state, const PassParams &pp, int n_eff, uint64_t r
         densek |= kind >= 2 && kind < 8;
     }
     if (tile_prof())
-        launch_variant<real, B, R, 256, 2, 3, true, true, true, true>(state, pp, n_eff, rank_bits, stream, max_ctas);
+        launch_variant<real, B, R, 256, 2, 3, true, true, true, true, false>(state, pp, n_eff, rank_bits, stream, max_ctas);
     else if (fact && !interp && !densek) // layered circuits: factored rounds (+ single gates)
-        launch_variant<real, B, R, 256, 2, 3, true, false, false, false>(state, pp, n_eff, rank_bits, stream, max_ctas);
+        launch_variant<real, B, R, 256, 2, 3, true, false, false, false, BULK>(state, pp, n_eff, rank_bits, stream, max_ctas);
     else if (!fact && !interp)           // unfactored dense rounds, single gates, permutation-only passes
-        launch_variant<real, B, R, 256, 2, 3, false, false, true, false>(state, pp, n_eff, rank_bits, stream, max_ctas);
+        launch_variant<real, B, R, 256, 2, 3, false, false, true, false, BULK>(state, pp, n_eff, rank_bits, stream, max_ctas);
     else if (!fact)                      // controlled / diagonal ops through the interpreter
-        launch_variant<real, B, R, 256, 2, 3, false, true, true, false>(state, pp, n_eff, rank_bits, stream, max_ctas);
+        launch_variant<real, B, R, 256, 2, 3, false, true, true, false, BULK>(state, pp, n_eff, rank_bits, stream, max_ctas);
     else
-        launch_variant<real, B, R, 256, 2, 3, true, true, true, false>(state, pp, n_eff, rank_bits, stream, max_ctas);
+        launch_variant<real, B, R, 256, 2, 3, true, true, true, false, BULK>(state, pp, n_eff, rank_bits, stream, max_ctas);
 }
 } // namespace
 

@@ -126,7 +126,7 @@ template <typename real> struct Emu {
                 tb |= static_cast<uint64_t>(t & h.seg_mask[j]) << h.seg_shift[j];
             const uint64_t tbr = tb | rank_bits;
             for (uint32_t i = 0; i < static_cast<uint32_t>(TILE); i++)
-                tile[phys(i)] = state[tb | rowoff[i >> h.low_bits] | (i & lowmask)];
+                tile[h.plain_layout ? i : phys(i)] = state[tb | rowoff[i >> h.low_bits] | (i & lowmask)];
             std::vector<uint32_t> xoff(h.n_rounds + 1, 0);
             for (int r = 0; r <= h.n_rounds; r++)
                 for (int c = 0; c < h.n_cx; c++)
@@ -210,6 +210,8 @@ int run(int n, int B, int R, int low, int max_heavy, int factor, int store_mode,
     cfg.factor = factor != 0;
     cfg.max_heavy = max_heavy;
     cfg.lookahead = getenv("B2EMU_NO_LOOKAHEAD") == nullptr;
+    cfg.bulk = getenv("B2EMU_BULK") != nullptr;
+    cfg.bulk_min_run_bits = low; // the tests want as many plain-layout passes as possible
     cfg.fuse_store = store_mode != 0;
     cfg.n_local = n;
     cfg.n_alloc = std::max(n, B);
@@ -224,7 +226,7 @@ int run(int n, int B, int R, int low, int max_heavy, int factor, int store_mode,
         emu.run_pass(ps, 0);
         n_pass++;
         n_fused += ps.hdr.fused_store == 1;
-        n_staged += ps.hdr.fused_store == 2;
+        n_staged += ps.hdr.plain_layout == 1; // (slot 5 of the stats: passes in the plain tile layout)
         for (int rd = 0; rd < ps.hdr.n_rounds; rd++) {
             n_rounds++;
             n_fact += ps.hdr.round_kind[rd] >= 8;
@@ -255,7 +257,7 @@ extern "C" {
 const char *b2emu_last_error() { return g_err.c_str(); }
 
 // names / wires / params as in b2sv_ops_create; state: 2^n interleaved (re, im) doubles, in place.
-// stats (6 values): passes, rounds, dense rounds, factored rounds, fused stores, (unused).
+// stats (6 values): passes, rounds, dense rounds, factored rounds, fused stores, plain-layout passes.
 // store_mode: 0 = always the store phase, 1 = fused stores where the schedule allows.
 int b2emu_run(int n, int f32, int B, int R, int low, int max_heavy, int factor, int store_mode,
               int n_ops,

@@ -54,5 +54,5 @@ def run(circ, n, psi, f32=False, B=None, R=None, low=5, max_heavy=8, factor=True
                          stats.ctypes.data_as(C.c_void_p))
     if rc != 0:
         raise RuntimeError(lib().b2emu_last_error().decode())
-    keys = ("passes", "rounds", "dense", "factored", "fused_stores", "unused")
+    keys = ("passes", "rounds", "dense", "factored", "fused_stores", "plain_passes")
     return st, dict(zip(keys, (int(x) for x in stats)))

@@ -126,3 +126,22 @@ def test_reference_param_gate_literals_through_the_scheduler(f32):
         n = int(np.log2(ini.size))
         got, _ = emu.run([(c["gate"], c["wires"], c["inverse"], c["params"])], n, ini, f32=f32)
         assert np.max(np.abs(got - want)) < 2e-6, c["gate"]  # the literals carry ~7 digits
+
+
+def test_plain_layout_passes_for_bulk_loads(monkeypatch):
+    """With bulk tile loads allowed, passes whose rounds keep the lowest index bits out of the register
+    set are laid out in plain order (filled by cp.async.bulk on the GPU); results are unchanged."""
+    import emu
+    monkeypatch.setenv("B2EMU_BULK", "1")
+    n = 16
+    for f32 in (False, True):
+        circ = layered_circuit(n, 3, seed=17)
+        psi0 = np.zeros(1 << n, dtype=complex)
+        psi0[0] = 1
+        got, st = emu.run(circ, n, psi0, f32=f32)
+        want = npo.apply_ops(psi0, n, circ)
+        assert np.max(np.abs(got - want)) < (2e-5 if f32 else 1e-12)
+        assert st["plain_passes"] >= 1 and st["plain_passes"] < st["passes"]
+    circ = random_circuit(n, 200, seed=23)
+    got, st = emu.run(circ, n, psi0)
+    assert np.max(np.abs(got - npo.apply_ops(psi0, n, circ))) < 1e-12
