@@ -577,6 +577,13 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
         // ---- load warps
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n");
         const int ptid = threadIdx.x - NG * GT;
+        if constexpr (BULK) {
+            // Bulk copies are issued by the first load warp alone. The other load warps must not stay
+            // around as idle observers of the `empty` barriers: a warp that takes no part in the
+            // hand-offs can fall two phases behind, and a parity wait cannot tell phase q from q + 2.
+            if (ptid >= 32)
+                return;
+        }
         // load warps: HBM -> shared (swizzled slots), running ahead of the workers
         long long p_wait = 0, p_t0 = 0, p_t1 = 0, p_issue = 0;
         // conditional address toggle `ptid` of the pass, kept in registers by the first load warp
@@ -623,7 +630,7 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
                 amp_t *buf = tiles + bi * TILE;
                 const int run = pp.hdr.bulk_run_bits; // leading tile bits that are index bits 0..run-1
                 const uint32_t run_bytes = static_cast<uint32_t>(sizeof(amp_t)) << run;
-                for (int r = ptid; r < (TILE >> run); r += kLoadThreads)
+                for (int r = ptid; r < (TILE >> run); r += 32)
                     bulk_load(buf + (r << run), state + (tb | rowoff[r << (run - low)]), run_bytes, &full[bi]);
                 if constexpr (PROF)
                     p_issue += clock64() - p_t1;
@@ -912,6 +919,20 @@ void launch_tile_pass_v(void *state, const PassParams &pp, int n_eff, uint64_t r
         fact |= kind >= 8;
         interp |= kind == 0;
         densek |= kind >= 2 && kind < 8;
+    }
+    static const bool debug = env_int("B2SV_DEBUG_PASSES", 0) != 0;
+    if (debug) { // one line per launch: variant flags, layout, round kinds (then synchronise to localise faults)
+        fprintf(stderr, "b2sv pass: fact=%d interp=%d densek=%d bulk=%d run_bits=%d fused=%d n_cx=%d n_ops=%d kinds=", fact,
+                interp, densek, int(BULK), int(pp.hdr.bulk_run_bits), int(pp.hdr.fused_store), pp.hdr.n_cx, pp.hdr.n_ops);
+        for (int rd = 0; rd < pp.hdr.n_rounds; rd++)
+            fprintf(stderr, "%d,", int(pp.hdr.round_kind[rd]));
+        fprintf(stderr, " tile_bits=");
+        for (int j = 0; j < B; j++)
+            fprintf(stderr, "%d,", int(pp.hdr.tile_bits[j]));
+        fprintf(stderr, "\n");
+        cudaError_t e0 = cudaStreamSynchronize(stream);
+        if (e0 != cudaSuccess)
+            fprintf(stderr, "b2sv pass: error BEFORE this launch: %s\n", cudaGetErrorString(e0));
     }
     if (tile_prof())
         launch_variant<real, B, R, 256, 2, 3, true, true, true, true, false>(state, pp, n_eff, rank_bits, stream, max_ctas);
