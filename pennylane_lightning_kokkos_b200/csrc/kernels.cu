@@ -679,6 +679,47 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// The same for a sharded state: an X or Y factor on a qubit that sits on a rank bit pairs this shard
+// with the shard of rank ^ x_global, so term t gathers from peers.p[st[t].src] -- the partner's shard,
+// read in place through its IPC mapping (NVLink loads), no exchange and no staging copy.
+template <typename amp_t>
+__global__ void __launch_bounds__(256)
+    k_pauli_sum_apply_sharded(PeerPtrs peers, amp_t *__restrict__ out, uint64_t len,
+                              const PauliTerm *__restrict__ terms, int nterms) {
+    constexpr int CH = 128;
+    __shared__ PauliTerm st[CH];
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    const uint64_t i0 = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t iters = (len + stride - 1) / stride;
+    for (uint64_t it = 0; it < iters; it++) {
+        const uint64_t i = i0 + it * stride;
+        double sr = 0.0, si = 0.0;
+        for (int t0 = 0; t0 < nterms; t0 += CH) {
+            const int nt = min(CH, nterms - t0);
+            __syncthreads();
+            if (threadIdx.x < nt)
+                st[threadIdx.x] = terms[t0 + threadIdx.x];
+            __syncthreads();
+            if (i < len) {
+                for (int t = 0; t < nt; t++) {
+                    const uint64_t j = i ^ st[t].x;
+                    const amp_t b = static_cast<const amp_t *>(peers.p[st[t].src])[j];
+                    const double sg = (__popcll(j & st[t].z) & 1) ? -1.0 : 1.0;
+                    const double cr = sg * st[t].cr, ci = sg * st[t].ci;
+                    sr += cr * b.x - ci * b.y;
+                    si += cr * b.y + ci * b.x;
+                }
+            }
+        }
+        if (i < len) {
+            amp_t o;
+            o.x = sr;
+            o.y = si;
+            out[i] = o;
+        }
+    }
+}
+
 // ---- CSR ----------------------------------------------------------------------------------------
 template <typename amp_t, bool EXPVAL>
 __global__ void __launch_bounds__(kReduceThreads)
@@ -1314,6 +1355,14 @@ void launch_pauli_sum_apply(int dtype, const void *in, void *out, uint64_t len,
     DISPATCH_DTYPE(dtype,
                    (k_pauli_sum_apply<float2><<<grid, 256, 0, st>>>(static_cast<const float2 *>(in), static_cast<float2 *>(out), len, d_terms, nterms)),
                    (k_pauli_sum_apply<double2><<<grid, 256, 0, st>>>(static_cast<const double2 *>(in), static_cast<double2 *>(out), len, d_terms, nterms)));
+}
+void launch_pauli_sum_apply_sharded(int dtype, const PeerPtrs &peers, void *out, uint64_t len,
+                                    const PauliTerm *d_terms, int nterms, cudaStream_t st) {
+    const uint64_t b = (len + 255) / 256;
+    const int grid = static_cast<int>(b < 148 * 8 ? b : 148 * 8);
+    DISPATCH_DTYPE(dtype,
+                   (k_pauli_sum_apply_sharded<float2><<<grid, 256, 0, st>>>(peers, static_cast<float2 *>(out), len, d_terms, nterms)),
+                   (k_pauli_sum_apply_sharded<double2><<<grid, 256, 0, st>>>(peers, static_cast<double2 *>(out), len, d_terms, nterms)));
 }
 void launch_csr_expval_stream(int dtype, const void *state, const double2 *d_data, const uint32_t *d_ind,
                               const uint64_t *d_ptr64, const uint32_t *d_ptr32, uint64_t nrows, uint64_t nnz,

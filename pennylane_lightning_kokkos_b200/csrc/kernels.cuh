@@ -95,7 +95,16 @@ void launch_finalize_scaled(const double *d_partials, int nblocks, int nv, int w
 struct PauliTerm {
     uint64_t x, z;
     double cr, ci; // coefficient * i^nY
+    uint32_t src;  // sharded application: which rank's shard holds the partner amplitudes of this term
+    uint32_t pad_;
 };
+struct PeerPtrs {
+    const void *p[64];
+};
+// sharded form of launch_pauli_sum_apply: term t reads its partner amplitudes from shard peers.p[src]
+// (this rank's own buffer or a peer's IPC-mapped shard over NVLink); x, z are shard-local masks
+void launch_pauli_sum_apply_sharded(int dtype, const PeerPtrs &peers, void *out, uint64_t len,
+                                    const PauliTerm *d_terms, int nterms, cudaStream_t st);
 // out = sum_t coef_t P_t in   (in != out)
 // 1 value: Re <psi| sum_t coef_t P_t |psi>; terms sorted by x
 void launch_pauli_sum_expval(int dtype, const void *state, uint64_t len, const PauliTerm *d_terms,

@@ -245,7 +245,7 @@ void pauli_sum_into(const State &sv, const void *in, void *out,
     static const cplx ipow[4] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
     for (size_t t = 0; t < terms.size(); t++) {
         const cplx c = terms[t].first * ipow[terms[t].second.ny & 3];
-        h[t] = PauliTerm{terms[t].second.x, terms[t].second.z, c.real(), c.imag()};
+        h[t] = PauliTerm{terms[t].second.x, terms[t].second.z, c.real(), c.imag(), 0, 0};
     }
     PauliTerm *d_terms;
     CUDA_CHECK(cudaSetDevice(sv.device()));
@@ -266,6 +266,19 @@ void pauli_sum_into(const State &sv, const void *in, void *out,
 
 void HamiltonianObs::apply_in_place(State &sv) const {
     std::vector<std::pair<double, PauliWord>> terms;
+    if (sv.world() > 1 && pauli_terms(sv.num_qubits(), 1.0, terms)) {
+        // sharded: one kernel, partner amplitudes of terms that flip a global qubit come straight from
+        // the peer's shard over NVLink
+        static const cplx ipow[4] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
+        std::vector<PauliTerm> pt(terms.size());
+        for (size_t t = 0; t < terms.size(); t++) {
+            const cplx c = terms[t].first * ipow[terms[t].second.ny & 3];
+            pt[t] = PauliTerm{terms[t].second.x, terms[t].second.z, c.real(), c.imag(), 0, 0};
+        }
+        if (sv.pauli_sum_apply_sharded(pt))
+            return;
+        terms.clear();
+    }
     if (sv.world() == 1 && pauli_terms(sv.num_qubits(), 1.0, terms)) {
         void *out = sv.acquire_scratch();
         if (sv.alloc_length() != sv.local_length())
@@ -324,12 +337,12 @@ double expval_obs(const State &sv, const Obs &ob) {
         const PauliWord &w = terms[0].second;
         return terms[0].first * sv.expval_pauli(w.x, w.z, ipow[w.ny & 3]);
     }
-    if (!terms.empty()) { // a sum of Pauli words: one read pass per distinct x mask, no work vector
+    if (!terms.empty() && sv.world() == 1) { // a sum of Pauli words: one read pass per distinct x mask, no work vector
         static const cplx ipow[4] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
         std::vector<PauliTerm> pt(terms.size());
         for (size_t t = 0; t < terms.size(); t++) {
             const cplx c = terms[t].first * ipow[terms[t].second.ny & 3];
-            pt[t] = PauliTerm{terms[t].second.x, terms[t].second.z, c.real(), c.imag()};
+            pt[t] = PauliTerm{terms[t].second.x, terms[t].second.z, c.real(), c.imag(), 0, 0};
         }
         return sv.expval_pauli_sum(pt);
     }

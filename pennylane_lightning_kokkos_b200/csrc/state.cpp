@@ -1045,8 +1045,11 @@ SchedConfig State::sched_config() const {
     cfg.n_local = n_local_;
     cfg.n_alloc = n_eff_;
     cfg.fuse = fuse_;
-    // bulk async tile loads (plain-layout passes); B2SV_BULK=0 keeps every pass on the swizzled layout
-    cfg.bulk = true;
+    // Bulk async tile loads (plain-layout passes, cp.async.bulk) are opt-in, B2SV_BULK=1: on one GPU
+    // they are neutral for runs >= 4 KiB and 10 % slower for 512-byte runs (profiles/r2_tile_bulk_ab.md),
+    // and a 4-GPU run with sliced passes beside exchanges failed after ~20 steps with them (cause not
+    // found) -- the default keeps every pass on the swizzled cp.async loader.
+    cfg.bulk = false;
     if (const char *e = getenv("B2SV_BULK"))
         cfg.bulk = atoi(e) != 0;
     if (const char *e = getenv("B2SV_BULK_MIN_RUN")) // experiments: 5 = every eligible pass (512-byte copies)
@@ -1276,6 +1279,50 @@ double State::expval_pauli_sum(const std::vector<PauliTerm> &terms_in) const {
     double r;
     finish_reduce(1, &r); // synchronises: `terms` may go out of scope
     return r;
+}
+bool State::pauli_sum_apply_sharded(const std::vector<PauliTerm> &terms_in) {
+    if (!comm_ || !comm_uses_peer(comm_.get()) || world_ > 64 || n_eff_ != n_local_)
+        return false;
+    for (int r = 0; r < world_; r++)
+        if (!peers_[r])
+            return false;
+    CUDA_CHECK(cudaSetDevice(device_));
+    std::vector<PauliTerm> terms;
+    terms.reserve(terms_in.size());
+    const uint64_t local_mask = local_length() - 1;
+    for (const PauliTerm &t : terms_in) {
+        PauliTerm u = t;
+        const uint64_t xp = phys_mask(t.x), zp = phys_mask(t.z);
+        const int src = rank_ ^ static_cast<int>(xp >> n_local_); // the shard that holds index i ^ x
+        u.x = xp & local_mask;
+        u.z = zp & local_mask;
+        u.src = static_cast<uint32_t>(src);
+        // Z factors on rank bits see the SOURCE index: its rank bits are those of `src`
+        if (__builtin_popcountll((uint64_t(src) << n_local_) & zp) & 1) {
+            u.cr = -u.cr;
+            u.ci = -u.ci;
+        }
+        terms.push_back(u);
+    }
+    PeerPtrs pp{};
+    for (int r = 0; r < world_; r++)
+        pp.p[r] = peers_[r];
+    void *out = acquire_scratch();
+    PauliTerm *d_terms;
+    CUDA_CHECK(cudaMallocAsync(&d_terms, sizeof(PauliTerm) * terms.size(), stream_));
+    CUDA_CHECK(cudaMemcpyAsync(d_terms, terms.data(), sizeof(PauliTerm) * terms.size(), cudaMemcpyHostToDevice, stream_));
+    comm_barrier(comm_.get(), stream_, 0); // every rank's shard holds the state the terms are applied to
+    launch_pauli_sum_apply_sharded(dtype_, pp, out, local_length(), d_terms, static_cast<int>(terms.size()), stream_);
+    comm_barrier(comm_.get(), stream_, 0); // nobody still reads this shard: it may be overwritten now
+    // the shard itself is what the peers have mapped, so the result is copied back (no buffer swap)
+    CUDA_CHECK(cudaMemcpyAsync(d_state_, out, local_length() * amp_bytes(), cudaMemcpyDeviceToDevice, stream_));
+    CUDA_CHECK(cudaFreeAsync(d_terms, stream_));
+    touch();
+    launches += 2;
+    bytes_moved += (terms.size() + 3) * state_bytes();
+    CUDA_CHECK(cudaStreamSynchronize(stream_)); // `terms` goes out of scope
+    release_scratch(out);
+    return true;
 }
 double State::expval_matrix(const std::vector<int64_t> &wires, const std::vector<cplx> &mat) const {
     CUDA_CHECK(cudaSetDevice(device_));

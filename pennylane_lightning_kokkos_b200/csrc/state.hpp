@@ -130,6 +130,10 @@ class State {
     const std::vector<double> &expval_z_all() const;
     // Re <psi| sum_t c_t P_t |psi>, Pauli words as (x, z, coefficient * i^nY) in logical bits
     double expval_pauli_sum(const std::vector<PauliTerm> &terms) const;
+    // sharded states: this <- sum_t c_t P_t this, the partner amplitudes of terms with X / Y factors on
+    // rank bits read from the peers' shards in place (terms in logical bits); false if the peers'
+    // shards are not mapped (NCCL-only path), nothing done then
+    bool pauli_sum_apply_sharded(const std::vector<PauliTerm> &terms);
     void touch() { version_++; } // the amplitudes changed: cached measurements are stale
     void axpy(cplx alpha, const State &x);
     // Adjoint-sweep reductions that stay on the device (no host synchronisation):

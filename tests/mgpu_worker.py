@@ -75,6 +75,24 @@ def main():
                 print(f"  {mode} {case} {np.dtype(dtype).name} n={n_eff} world={world}: amp err {err:.2e} "
                       f"expval err {e2:.2e} swaps {stats['swaps']} path {stats['path']}", flush=True)
             assert err < tol and e2 < tol, (case, dtype, err, e2)
+            # a Pauli-sum Hamiltonian: applied by one kernel that reads the partner amplitudes of terms with
+            # X / Y factors on global qubits from the peers' shards (expval = <psi|H psi>, var uses it twice)
+            if dtype == np.complex128:
+                from cases import random_pauli_hamiltonian
+                sfx = "C128"
+                ham = random_pauli_hamiltonian(n_eff, 16, seed=11)
+                ham[0] = (0.7, [("PauliX", 0), ("PauliY", n_eff - 1)])  # global X, local Y
+                ham[1] = (-0.4, [("PauliZ", 0), ("PauliX", g)])        # global Z, first local X
+                tobs = []
+                for _, word in ham:
+                    fac = [getattr(ops, "NamedObsKokkos_" + sfx)(l, [w]) for l, w in word]
+                    tobs.append(fac[0] if len(fac) == 1 else getattr(ops, "TensorProdObsKokkos_" + sfx)(fac))
+                Hobs = getattr(ops, "HamiltonianKokkos_" + sfx)(np.array([c for c, _ in ham]), tobs)
+                hnp = ("hamiltonian", [c for c, _ in ham],
+                       [("tensor", [("named", l, [w]) for l, w in word]) for _, word in ham])
+                eh, eh_want = sv.expval(Hobs), npo.expval(want, n_eff, hnp)
+                vh, vh_want = sv.var(Hobs), npo.var(want, n_eff, hnp)
+                assert abs(eh - eh_want) < 1e-12 and abs(vh - vh_want) < 1e-11, (eh, eh_want, vh, vh_want)
             # marginal probabilities over global + local wires (all-reduced histograms) and sampling
             # (one shared random stream; each shot resolved by the rank that owns its interval)
             for pw in ([0, g, n_eff - 1], [1, 2], list(range(min(n_eff, 10)))):

@@ -331,3 +331,20 @@ def test_op_list_handle_replay_matches_reference(ops, ref, dtype, tol):
     rsv.apply_ops(circ)
     z1 = np.array([rsv.expval_named("PauliZ", [w]) for w in range(n)])
     assert np.max(np.abs(sv.expval_z_all() - z1)) < 10 * tol and np.max(np.abs(z0 - z1)) > 1e-3
+
+
+def test_bulk_tile_loads_opt_in(ops, ref, monkeypatch):
+    """B2SV_BULK=1: passes whose tile starts with >= 8 contiguous index bits use the plain layout and
+    bulk async copies (cp.async.bulk); same results as the reference, also when a CTA's three tile
+    buffers are re-used many times (24 qubits: ~28 tiles per CTA)."""
+    monkeypatch.setenv("B2SV_BULK", "1")
+    for n, layers in ((15, 3), (24, 1)):
+        circ = layered_circuit(n, layers, seed=31) + [("CRY", [n - 1, 2], False, [0.6]),
+                                                      ("MultiRZ", [0, n - 2, 3], False, [0.3])]
+        sv = ops.LightningKokkos_C128(n)
+        sv.apply(*split(circ))
+        rsv = ref.RefStateVector(n, np.complex128)
+        rsv.apply_ops(circ)
+        idx = np.random.default_rng(2).integers(0, 1 << n, size=4096, dtype=np.uint64)
+        assert rel_err(sv.amplitudes(idx), rsv.amplitudes(idx.astype(np.int64))) < TOL
+        assert abs(sv.ExpectationValue("Identity", [0], [], np.zeros(0)) - 1.0) < TOL
