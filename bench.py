@@ -387,7 +387,7 @@ def sharded_adjoint_sample(ops, b2dist, local_rank, world, dist, q_per_gpu=24, l
         return circ, ham, sv, adj, oplist, H, tp
 
     # parity at a size the oracle finishes in seconds
-    n_s = 13 + g
+    n_s = 13 + 2 * g  # a shard must hold at least tile_bits + log2(world) qubits
     circ, ham, sv, adj, oplist, H, tp = build(n_s, 2, 12)
     jac = adj.adjoint_jacobian(sv, [H], oplist, tp)
     psi0 = np.zeros(1 << n_s, dtype=complex)
