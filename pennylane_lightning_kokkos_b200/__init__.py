@@ -4,7 +4,8 @@
 Layout:
   csrc/                          CUDA kernels (sm_100a) + C++ host + the C ABI -> libb2sv.so
   _lib.py                        ctypes loader (fails loudly if the library is missing)
-  lightning_kokkos_qubit_ops.py  mirror of the reference's pybind11 module (same class/method names)
+  lightning_kokkos_qubit_ops.py  ctypes mirror of the reference's pybind11 module (same class/method names)
+  lightning_kokkos_qubit_ops_pyb compiled pybind11 module with the same surface (csrc/pybind/bindings.cpp)
   lightning_kokkos.py            PennyLane-free mirror of the reference's device class
   dist.py                        torch.distributed plumbing for sharded states
 """
