@@ -818,6 +818,9 @@ __global__ void __launch_bounds__(kReduceThreads)
         for (uint64_t c = c_beg; c < c_end; c++) {
             if (c + 1 < c_end)
                 load(c + 1, dn, coln);
+            // rows of this lane's K elements first (row pointers come from L1), then all 2K gathers in
+            // flight together, then the arithmetic: one L2 round trip per chunk instead of one per element
+            uint32_t rowk[K];
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const uint64_t j = c * CH + lane + 32 * k;
@@ -826,10 +829,20 @@ __global__ void __launch_bounds__(kReduceThreads)
                         row++;
                         next_start = static_cast<uint64_t>(__ldg(ptr + row + 1));
                     }
-                    const amp_t v = x[col[k]], a = x[row];
-                    const double tr = d[k].x * v.x - d[k].y * v.y, ti = d[k].x * v.y + d[k].y * v.x;
-                    acc[0] += double(a.x) * tr + double(a.y) * ti;
                 }
+                rowk[k] = static_cast<uint32_t>(row);
+            }
+            amp_t v[K], a[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                v[k] = x[col[k]];
+                a[k] = x[rowk[k]];
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                // elements past the end carry d = 0
+                const double tr = d[k].x * v[k].x - d[k].y * v[k].y, ti = d[k].x * v[k].y + d[k].y * v[k].x;
+                acc[0] += double(a[k].x) * tr + double(a[k].y) * ti;
             }
 #pragma unroll
             for (int k = 0; k < K; k++) {
