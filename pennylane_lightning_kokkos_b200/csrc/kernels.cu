@@ -772,24 +772,35 @@ __global__ void __launch_bounds__(kReduceThreads)
 // 16-byte and 4-byte loads are all issued before the previous chunk is consumed (register double
 // buffering). The gathers psi[ind], psi[row] hit L2 for states up to ~100 MB. Deterministic: every
 // lane sums in a fixed order, the block and grid reductions are fixed-order too.
-template <typename amp_t, typename ptr_t>
+// Sharded states (SHARDED): this rank streams the non-zeros of ITS rows (j_begin .. nnz of the call,
+// rows row_begin ..), psi[row] is local and psi[col] comes from whichever shard holds it -- read in
+// place through the peers' IPC mappings (csr.n_local = index bits per shard).
+struct CsrShard {
+    PeerPtrs peers;
+    int n_local;
+    uint64_t j_begin, row_begin;
+};
+template <typename amp_t, typename ptr_t, bool SHARDED>
 __global__ void __launch_bounds__(kReduceThreads)
     k_csr_expval_stream(const amp_t *__restrict__ x, const double2 *__restrict__ data,
                         const uint32_t *__restrict__ ind, const ptr_t *__restrict__ ptr, uint64_t nrows,
-                        uint64_t nnz, double *__restrict__ partials) {
+                        uint64_t nnz, CsrShard sh, double *__restrict__ partials) {
     constexpr int K = 4;
     constexpr uint64_t CH = 32 * K;
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
     // ranges are whole chunks, so every chunk belongs to exactly one warp
-    const uint64_t nchunks = (nnz + CH - 1) / CH;
+    const uint64_t jb = SHARDED ? sh.j_begin : 0; // the call covers non-zeros jb .. nnz, rows row0 .. nrows
+    const uint64_t row0 = SHARDED ? sh.row_begin : 0;
+    const uint64_t nchunks = (nnz - jb + CH - 1) / CH;
     const uint64_t per = (nchunks + nwarps - 1) / nwarps;
     const uint64_t c_beg = warp * per, c_end = min(nchunks, c_beg + per);
+    const uint64_t local_mask = SHARDED ? ((uint64_t(1) << sh.n_local) - 1) : ~uint64_t(0);
     double acc[1] = {0.0};
     if (c_beg < c_end) {
-        uint64_t lo = 0, hi = nrows; // the largest r with ptr[r] <= first element of the range
-        const uint64_t jfirst = c_beg * CH;
+        uint64_t lo = row0, hi = nrows; // the largest r with ptr[r] <= first element of the range
+        const uint64_t jfirst = jb + c_beg * CH;
         while (hi - lo > 1) {
             const uint64_t mid = lo + ((hi - lo) >> 1);
             if (static_cast<uint64_t>(__ldg(ptr + mid)) <= jfirst)
@@ -804,7 +815,7 @@ __global__ void __launch_bounds__(kReduceThreads)
         auto load = [&](uint64_t c, double2(&dd)[K], uint32_t(&cc)[K]) {
 #pragma unroll
             for (int k = 0; k < K; k++) {
-                const uint64_t j = c * CH + lane + 32 * k;
+                const uint64_t j = jb + c * CH + lane + 32 * k;
                 if (j < nnz) {
                     dd[k] = data[j];
                     cc[k] = ind[j];
@@ -823,7 +834,7 @@ __global__ void __launch_bounds__(kReduceThreads)
             uint32_t rowk[K];
 #pragma unroll
             for (int k = 0; k < K; k++) {
-                const uint64_t j = c * CH + lane + 32 * k;
+                const uint64_t j = jb + c * CH + lane + 32 * k;
                 if (j < nnz) {
                     while (next_start <= j) { // empty rows are skipped the same way
                         row++;
@@ -835,8 +846,11 @@ __global__ void __launch_bounds__(kReduceThreads)
             amp_t v[K], a[K];
 #pragma unroll
             for (int k = 0; k < K; k++) {
-                v[k] = x[col[k]];
-                a[k] = x[rowk[k]];
+                if constexpr (SHARDED)
+                    v[k] = static_cast<const amp_t *>(sh.peers.p[col[k] >> sh.n_local])[col[k] & local_mask];
+                else
+                    v[k] = x[col[k]];
+                a[k] = x[rowk[k] & local_mask];
             }
 #pragma unroll
             for (int k = 0; k < K; k++) {
@@ -1380,15 +1394,30 @@ void launch_pauli_sum_apply_sharded(int dtype, const PeerPtrs &peers, void *out,
 void launch_csr_expval_stream(int dtype, const void *state, const double2 *d_data, const uint32_t *d_ind,
                               const uint64_t *d_ptr64, const uint32_t *d_ptr32, uint64_t nrows, uint64_t nnz,
                               double *d_partials, cudaStream_t st) {
+    const CsrShard none{};
     if (d_ptr32) {
         DISPATCH_DTYPE(dtype,
-                       (k_csr_expval_stream<float2, uint32_t><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), d_data, d_ind, d_ptr32, nrows, nnz, d_partials)),
-                       (k_csr_expval_stream<double2, uint32_t><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), d_data, d_ind, d_ptr32, nrows, nnz, d_partials)));
+                       (k_csr_expval_stream<float2, uint32_t, false><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), d_data, d_ind, d_ptr32, nrows, nnz, none, d_partials)),
+                       (k_csr_expval_stream<double2, uint32_t, false><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), d_data, d_ind, d_ptr32, nrows, nnz, none, d_partials)));
     } else {
         DISPATCH_DTYPE(dtype,
-                       (k_csr_expval_stream<float2, uint64_t><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), d_data, d_ind, d_ptr64, nrows, nnz, d_partials)),
-                       (k_csr_expval_stream<double2, uint64_t><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), d_data, d_ind, d_ptr64, nrows, nnz, d_partials)));
+                       (k_csr_expval_stream<float2, uint64_t, false><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), d_data, d_ind, d_ptr64, nrows, nnz, none, d_partials)),
+                       (k_csr_expval_stream<double2, uint64_t, false><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), d_data, d_ind, d_ptr64, nrows, nnz, none, d_partials)));
     }
+}
+// rows row_begin .. row_end of the matrix belong to this shard; non-zeros j_begin .. j_end
+void launch_csr_expval_sharded(int dtype, const void *state, const PeerPtrs &peers, int n_local,
+                               const double2 *d_data, const uint32_t *d_ind, const uint64_t *d_ptr64,
+                               uint64_t row_begin, uint64_t row_end, uint64_t j_begin, uint64_t j_end,
+                               double *d_partials, cudaStream_t st) {
+    CsrShard sh{};
+    sh.peers = peers;
+    sh.n_local = n_local;
+    sh.j_begin = j_begin;
+    sh.row_begin = row_begin;
+    DISPATCH_DTYPE(dtype,
+                   (k_csr_expval_stream<float2, uint64_t, true><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const float2 *>(state), d_data, d_ind, d_ptr64, row_end, j_end, sh, d_partials)),
+                   (k_csr_expval_stream<double2, uint64_t, true><<<kReduceBlocks, kReduceThreads, 0, st>>>(static_cast<const double2 *>(state), d_data, d_ind, d_ptr64, row_end, j_end, sh, d_partials)));
 }
 void launch_csr_expval(int dtype, const void *state, const double2 *d_data, const uint32_t *d_ind,
                        const uint64_t *d_ptr, uint64_t nrows, int L, double *d_partials,

@@ -122,6 +122,12 @@ void launch_csr_expval(int dtype, const void *state, const double2 *d_data, cons
 void launch_csr_expval_stream(int dtype, const void *state, const double2 *d_data, const uint32_t *d_ind,
                               const uint64_t *d_ptr64, const uint32_t *d_ptr32, uint64_t nrows, uint64_t nnz,
                               double *d_partials, cudaStream_t st);
+// sharded state: rank-local rows [row_begin, row_end), their non-zeros [j_begin, j_end); psi[col] is
+// read from the shard that holds it (peers.p[col >> n_local], IPC-mapped)
+void launch_csr_expval_sharded(int dtype, const void *state, const PeerPtrs &peers, int n_local,
+                               const double2 *d_data, const uint32_t *d_ind, const uint64_t *d_ptr64,
+                               uint64_t row_begin, uint64_t row_end, uint64_t j_begin, uint64_t j_end,
+                               double *d_partials, cudaStream_t st);
 void launch_csr_spmv(int dtype, const void *x, void *y, const double2 *d_data,
                      const uint32_t *d_ind, const uint64_t *d_ptr, uint64_t nrows,
                      int lanes_per_row, cudaStream_t st);

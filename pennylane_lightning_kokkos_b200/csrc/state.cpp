@@ -1367,7 +1367,36 @@ double State::expval_matrix(const std::vector<int64_t> &wires, const std::vector
 }
 double State::expval_csr(const CsrDevice &m) const {
     CUDA_CHECK(cudaSetDevice(device_));
-    B2_ABORT_IF(world_ > 1, "CSR expectation values are not supported on sharded states");
+    if (world_ > 1) {
+        // Sharded: the matrix is resident on every rank (device-resident CSR of the whole operator), rank r
+        // streams the non-zeros of ITS rows, psi[col] is read in place from the shard that holds it
+        // (NVLink through the IPC mappings), the partial sums are all-reduced.
+        B2_ABORT_IF(!comm_uses_peer(comm_.get()) || world_ > 64 || n_eff_ != n_local_,
+                    "CSR expectation values on sharded states need the peer-mapped shards");
+        B2_ABORT_IF(m.nrows != (uint64_t(1) << n_), "CSR matrix dimension does not match the state vector");
+        normalize_layout(); // rows and columns are plain indices: rank = top bits
+        const uint64_t r0 = uint64_t(rank_) << n_local_, r1 = r0 + local_length();
+        uint64_t jr[2];
+        CUDA_CHECK(cudaMemcpyAsync(&jr[0], m.ptr + r0, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream_));
+        CUDA_CHECK(cudaMemcpyAsync(&jr[1], m.ptr + r1, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        PeerPtrs pp{};
+        for (int r = 0; r < world_; r++) {
+            B2_ABORT_IF(!peers_[r], "CSR expectation values on sharded states need the peer-mapped shards");
+            pp.p[r] = peers_[r];
+        }
+        comm_barrier(comm_.get(), stream_, 0); // every shard holds its final amplitudes
+        if (jr[1] > jr[0])
+            launch_csr_expval_sharded(dtype_, d_state_, pp, n_local_, m.data, m.ind, m.ptr, r0, r1, jr[0], jr[1],
+                                      d_partials_, stream_);
+        else
+            CUDA_CHECK(cudaMemsetAsync(d_partials_, 0, sizeof(double) * kReduceBlocks, stream_));
+        comm_barrier(comm_.get(), stream_, 0); // nobody still reads this shard
+        bytes_moved += (jr[1] - jr[0]) * 20 + state_bytes();
+        double r;
+        finish_reduce(1, &r); // all-reduces
+        return r;
+    }
     B2_ABORT_IF(m.nrows != local_length(), "CSR matrix dimension does not match the state vector");
     if (m.nnz > 0 && (getenv("B2SV_CSR_ROWS") == nullptr))
         launch_csr_expval_stream(dtype_, d_state_, m.data, m.ind, m.ptr, m.ptr32, m.nrows, m.nnz, d_partials_,

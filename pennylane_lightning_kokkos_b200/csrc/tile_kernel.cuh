@@ -101,11 +101,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
 }
 // Polling must not steal issue slots from the arithmetic warps of the same SM sub-partition: the
 // try_wait carries a suspend-time hint and a missed poll backs off with nanosleep.
+// A lost hand-off must surface as a CUDA error, never as a hung GPU: the wait gives up after
+// kMbarTimeoutNs of wall time (%globaltimer, looked at every 4096 missed polls), not after a number of
+// polls whose duration depends on the sleep granularity.
+constexpr unsigned long long kMbarTimeoutNs = 10ull * 1000 * 1000 * 1000;
 template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
     const uint32_t a = smem_u32(mbar);
     uint32_t ok;
     uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while (true) {
         asm volatile("{\n .reg .pred p;\n"
                      " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
@@ -116,8 +121,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
         if (ok)
             break;
         __nanosleep(SLEEP_NS);
-        if (++spins == (1u << 24))
-            __trap(); // a lost hand-off must surface as a CUDA error, never as a hung GPU
+        if ((++spins & 0xfffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0)
+                t0 = now;
+            else if (now - t0 > kMbarTimeoutNs)
+                __trap();
+        }
     }
 }
 // one lane polls, the rest of the warp parks at the warp barrier (no 32-wide spinning)

@@ -93,6 +93,30 @@ def main():
                 eh, eh_want = sv.expval(Hobs), npo.expval(want, n_eff, hnp)
                 vh, vh_want = sv.var(Hobs), npo.var(want, n_eff, hnp)
                 assert abs(eh - eh_want) < 1e-12 and abs(vh - vh_want) < 1e-11, (eh, eh_want, vh, vh_want)
+                if mode == "plain":
+                    # the same operator as CSR: every rank streams its rows, columns on other ranks are
+                    # read from the peers' shards
+                    import scipy.sparse as sp
+                    dim = 1 << n_eff
+                    idx = np.arange(dim, dtype=np.int64)
+                    mat = sp.csr_matrix((dim, dim), dtype=np.complex128)
+                    for c, word in ham:
+                        x = z = ny = 0
+                        for l, w in word:
+                            b = 1 << (n_eff - 1 - w)
+                            x |= b if l in ("PauliX", "PauliY") else 0
+                            z |= b if l in ("PauliZ", "PauliY") else 0
+                            ny += l == "PauliY"
+                        par = np.zeros(dim, dtype=np.int64)
+                        zz = z
+                        while zz:
+                            par ^= (idx >> ((zz & -zz).bit_length() - 1)) & 1
+                            zz &= zz - 1
+                        mat = mat + sp.csr_matrix((c * (1j ** ny) * (1 - 2 * par), (idx ^ x, idx)), shape=(dim, dim))
+                    mat = mat.tocsr()
+                    mat.sort_indices()
+                    ec = sv.ExpectationValue(mat.data, mat.indices.astype(np.uint64), mat.indptr.astype(np.uint64))
+                    assert abs(ec - eh_want) < 1e-12, (ec, eh_want)
             # marginal probabilities over global + local wires (all-reduced histograms) and sampling
             # (one shared random stream; each shot resolved by the rank that owns its interval)
             for pw in ([0, g, n_eff - 1], [1, 2], list(range(min(n_eff, 10)))):
