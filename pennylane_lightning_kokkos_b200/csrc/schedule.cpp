@@ -345,7 +345,10 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
 constexpr int kAutoBudgetMinBits = 25; // from 2^25 amplitudes on, trying several budgets pays
 }
 
-std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedConfig &cfg) {
+std::vector<Pass> build_schedule(const std::vector<Prim> &prims_in, const SchedConfig &cfg_in) {
+    SchedConfig cfg = cfg_in;
+    if (const char *e = getenv("B2SV_LOOKAHEAD")) // experiments: tile bits by marginal gain
+        cfg.lookahead = atoi(e) != 0;
     if (cfg.max_heavy > 0)
         return build_schedule_fixed(prims_in, cfg);
     if (std::max(cfg.n_alloc, cfg.n_local) < kAutoBudgetMinBits) {
