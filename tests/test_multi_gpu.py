@@ -79,3 +79,39 @@ def test_sharded_state_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MGPU_OK" in out.stdout
+
+
+@pytest.mark.gpu
+def test_two_devices_in_one_process():
+    """Function attributes (dynamic shared memory opt-in) and the SM count are per device: a process
+    that holds states on two GPUs must be able to run the tile executor and the transition-sum kernel
+    on both."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cases import layered_circuit
+    from oracle import np_oracle as npo
+    from pennylane_lightning_kokkos_b200 import lightning_kokkos_qubit_ops as ops
+
+    n = 14
+    circ = layered_circuit(n, 2, seed=5)
+    names, wires = [c[0] for c in circ], [c[1] for c in circ]
+    invs, params = [c[2] for c in circ], [c[3] for c in circ]
+    psi0 = np.zeros(1 << n, dtype=complex)
+    psi0[0] = 1
+    want = npo.apply_ops(psi0, n, circ)
+    tp = list(range(sum(1 for p in params if p)))
+    jac_want = npo.adjoint_jacobian(want, n, [("named", "PauliZ", [0])], circ, tp)
+    for dev in (0, 1, 0):
+        sv = ops.LightningKokkos_C128(n, ops.InitializationSettings().set_device_id(dev))
+        sv.apply(names, wires, invs, params)
+        got = np.zeros(1 << n, dtype=np.complex128)
+        sv.DeviceToHost(got)
+        assert np.max(np.abs(got - want)) < 1e-12
+        adj = ops.AdjointJacobianKokkos_C128()
+        ol = adj.create_ops_list(names, [np.array(p) for p in params], wires, invs,
+                                 [np.zeros(0, dtype=complex) for _ in names])
+        jac = adj.adjoint_jacobian(sv, [ops.NamedObsKokkos_C128("PauliZ", [0])], ol, tp)
+        assert np.max(np.abs(jac - jac_want)) < 1e-12
