@@ -168,7 +168,8 @@ void adjoint_jacobian(const State &sv, const std::vector<ObsPtr> &obs, const Ops
     };
     std::vector<RunOp> run; // in processing order = descending op index
     std::vector<double> jac_host(n_obs * tp_size, 0.0);
-    // B2SV_ADJOINT_RUNS=0 turns the run path off (A/B measurements); sharded states use the per-op path
+    // B2SV_ADJOINT_RUNS=0 turns the run path off (A/B measurements). Sharded states take the run path too:
+    // the wires of a chunk are brought into the shard and the transition sums are all-reduced.
     const char *runs_env = getenv("B2SV_ADJOINT_RUNS");
     const bool runs_enabled = runs_env == nullptr || atoi(runs_env) != 0;
     double *d_tr_scratch = nullptr, *d_tr_out = nullptr;

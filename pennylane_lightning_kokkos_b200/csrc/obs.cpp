@@ -207,7 +207,7 @@ class SparseHamiltonianObs final : public Obs {
     void apply_in_place(State &sv) const override { // OBS.hpp:484-494
         B2_ABORT_IF(static_cast<int>(wires_.size()) != sv.num_qubits(),
                     "SparseH wire count does not match state-vector size");
-        B2_ABORT_IF(sv.world() > 1, "SparseHamiltonian is not supported on sharded states");
+        B2_ABORT_IF(sv.world() > 1, "SparseHamiltonian::applyInPlace is not supported on sharded states (expval is)");
         const CsrDevice &m = device_csr(sv.device());
         B2_ABORT_IF(m.nrows != sv.local_length(), "CSR matrix dimension does not match the state vector");
         void *y = sv.acquire_scratch();

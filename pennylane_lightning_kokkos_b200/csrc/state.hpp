@@ -145,7 +145,8 @@ class State {
     void dot_im_to(const State &bra, double factor, double *d_dst) const;
     // Single-qubit transition sums <bra| . |this> for nb <= kTransitionBits index bits in one read
     // pass (kernels.cu k_transition_1q); d_scratch: kReduceBlocks x kTransitionVals doubles, result
-    // (kTransitionVals doubles) lands in d_dst. Not for sharded states.
+    // (kTransitionVals doubles) lands in d_dst. Sharded states: `bits` are physical, shard-local positions in
+    // a layout both states share; the sums are all-reduced over the ranks.
     void transition_1q_to(const State &bra, const int *bits, int nb, double *d_scratch,
                           double *d_dst) const;
     bool sharded() const { return world_ > 1; }
