@@ -502,12 +502,13 @@ def test_adjoint_vs_reference(ops, ref, dtype, n, layers):
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_reference_param_gate_literals(ops, dtype):
     """In/out state vectors written out in the reference's own tests
-    (src/tests/Test_StateVectorKokkos_Param.cpp, extracted into tests/golden/ref_param_literals.json)."""
+    (src/tests/Test_StateVectorKokkos_Param.cpp and _NonParam.cpp, extracted into
+    tests/golden/ref_param_literals.json: 61 gate applications over 15 gate kinds)."""
     import json
     import os
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_param_literals.json")) as f:
         cases = json.load(f)["cases"]
-    assert len(cases) >= 7
+    assert len(cases) >= 61
     for c in cases:
         ini = np.array([complex(a, b) for a, b in c["ini"]], dtype=dtype)
         want = np.array([complex(a, b) for a, b in c["expected"]])
