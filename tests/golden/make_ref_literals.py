@@ -5,7 +5,8 @@
 and the sparse-table style of the Ising/MultiRZ tests (`expected_results[i][j] = cp_t{..}` tables
 indexed by `index (+ angles.size())`, applied to |0..0>)
 plus the symbolic tables of the fixed-gate tests (Test_StateVectorKokkos_NonParam.cpp: SWAP, CZ, Toffoli,
-CSWAP on H(0) X(1)|000>, rows written with z = ZERO and i = INVSQRT2, which this script evaluates)
+CSWAP on H(0) X(1)|000>, rows written with z = ZERO and i = INVSQRT2; PauliY, PauliZ, S, T on |+++>, rows of
+symbols defined from Util:: constants -- this script evaluates the symbols)
 into tests/golden/ref_param_literals.json. Runs only where /root/reference exists (the build
 container); the JSON it writes is committed and travels to the GPU box.
 
@@ -123,6 +124,42 @@ def nonparam_cases(text):
     return out
 
 
+UTIL = {"HALF": 0.5, "INVSQRT2": 2.0 ** -0.5, "IMAG": 1j, "NEGONE": -1.0, "ONE": 1.0, "ZERO": 0.0}
+SYMDEF = re.compile(r"(?:const\s+)?auto\s+([a-z])\s*=\s*([^;]*Util::[^;]*);")
+PREP3H = re.compile(r'\{\{"Hadamard"\},\s*\{"Hadamard"\},\s*\{"Hadamard"\}\},\s*\{\{0\},\s*\{1\},\s*\{2\}\}')
+
+
+def plus_state_cases(text):
+    """PauliY / PauliZ / S / T on |+++>: rows of one-letter symbols defined from Util:: constants
+    (`auto p = Util::HALF<..>() * Util::INVSQRT2<..>() * ...`), row `index` = gate on wire `index`."""
+    out = []
+    starts = [m.start() for m in re.finditer(r"TEMPLATE_TEST_CASE\(", text)] + [len(text)]
+    for s0, s1 in zip(starts, starts[1:]):
+        body = text[s0:s1]
+        tab = re.search(r"std::vector<std::vector<cp_t>>\s+expected_results\s*=\s*\{", body)
+        app = re.search(r"kokkos_sv\.apply([A-Z][A-Za-z]*)\(\s*\{index\}\s*,\s*(true|false)\s*\)", body)
+        if not PREP3H.search(body) or not tab or not app:
+            continue
+        env = {}
+        for name, expr in SYMDEF.findall(body[:tab.start()]):
+            expr = re.sub(r"Util::([A-Z0-9]+)<[^>]*>\(\)", lambda m: repr(UTIL[m.group(1)]), expr)
+            env[name] = complex(eval(" ".join(expr.split()), {"__builtins__": {}}, dict(env)))
+        init, _ = block(body, tab.end() - 1)
+        rows = re.findall(r"\{([a-z,\s]+)\}", init)
+        if len(rows) != 3:
+            continue
+        amp = 0.5 * 2.0 ** -0.5
+        for w, row in enumerate(rows):
+            sym = [t.strip() for t in row.split(",") if t.strip()]
+            if len(sym) != 8:
+                break
+            out.append({"gate": app.group(1), "wires": [w], "inverse": app.group(2) == "true", "params": [],
+                        "ini": [[amp, 0.0]] * 8, "expected": [[env[t].real, env[t].imag] for t in sym],
+                        "ref_file": "Test_StateVectorKokkos_NonParam.cpp",
+                        "ref_line": text.count("\n", 0, s0 + app.start()) + 1})
+    return out
+
+
 def main():
     text = open(SRC).read()
     cases = []
@@ -146,6 +183,7 @@ def main():
                       "ini": ini, "expected": exp, "ref_line": line})
     cases += table_cases(text)
     cases += nonparam_cases(open(SRC_NP).read())
+    cases += plus_state_cases(open(SRC_NP).read())
     with open(OUT, "w") as f:
         json.dump({"source": "reference src/tests/Test_StateVectorKokkos_Param.cpp, Test_StateVectorKokkos_NonParam.cpp", "cases": cases}, f, indent=0)
     print(f"{len(cases)} cases ->", OUT)

@@ -503,12 +503,12 @@ def test_adjoint_vs_reference(ops, ref, dtype, n, layers):
 def test_reference_param_gate_literals(ops, dtype):
     """In/out state vectors written out in the reference's own tests
     (src/tests/Test_StateVectorKokkos_Param.cpp and _NonParam.cpp, extracted into
-    tests/golden/ref_param_literals.json: 61 gate applications over 15 gate kinds)."""
+    tests/golden/ref_param_literals.json: 73 gate applications over 19 gate kinds)."""
     import json
     import os
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_param_literals.json")) as f:
         cases = json.load(f)["cases"]
-    assert len(cases) >= 61
+    assert len(cases) >= 73
     for c in cases:
         ini = np.array([complex(a, b) for a, b in c["ini"]], dtype=dtype)
         want = np.array([complex(a, b) for a, b in c["expected"]])
@@ -518,6 +518,75 @@ def test_reference_param_gate_literals(ops, dtype):
         getattr(sv, c["gate"])(c["wires"], c["inverse"], c["params"])
         # the literals carry ~7 digits (the reference compares them with Catch2 Approx, 1.2e-5 relative)
         assert np.max(np.abs(to_host(sv, n, dtype) - want)) < 2e-6, c["gate"]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 2])
+def test_one_and_two_qubit_states(ops, ref, dtype, n):
+    """States far below one tile (the reference's own tests mostly use 1-3 qubits): every gate that
+    fits, a random circuit, named / matrix expvals, var, probs, sampling and the adjoint Jacobian."""
+    S = suffix(dtype)
+    prec = 1 if dtype == np.complex128 else 0
+    tol = TOL[dtype]
+    st = random_state(n, 90 + n, dtype)
+    sv = sv_class(ops, dtype)(n)
+    r = ref.RefStateVector(n, dtype)
+    for case in gate_cases(n, seed=3, per_gate=2):
+        sv.HostToDevice(st)
+        r.h2d(st)
+        apply_gpu(sv, case)
+        r.apply(*case)
+        assert rel_err(to_host(sv, n, dtype), r.d2h()) < tol, case
+    circ = random_circuit(n, 30, seed=5)
+    sv.HostToDevice(st)
+    r.h2d(st)
+    sv.apply([c[0] for c in circ], [c[1] for c in circ], [c[2] for c in circ], [c[3] for c in circ])
+    r.apply_ops(circ)
+    assert rel_err(to_host(sv, n, dtype), r.d2h()) < 10 * tol
+    N = getattr(ops, f"NamedObsKokkos_{S}")
+    for name in ("Identity", "PauliX", "PauliY", "PauliZ", "Hadamard"):
+        for w in range(n):
+            assert abs(sv.ExpectationValue(name, [w], [], np.zeros(0)) - r.expval_named(name, [w])) < 10 * tol
+            assert abs(sv.var(N(name, [w])) - r.var_obs(ref.RefObs.named(name, [w], prec))) < 10 * tol
+    rng = np.random.default_rng(6)
+    for wires in ([0], [n - 1], list(range(n)), list(range(n))[::-1]):
+        k = len(wires)
+        a = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+        h = a + a.conj().T
+        want = r.expval_matrix(h, wires)
+        assert abs(sv.ExpectationValue(wires, h.ravel()) - want) < 10 * tol * max(1, abs(want)), wires
+    ptol = 1e-12 if dtype == np.complex128 else 5e-6
+    np.testing.assert_allclose(sv.probs([]), r.probs(), atol=ptol)
+    for wires in ([0], [n - 1], list(range(n))[::-1]):
+        np.testing.assert_allclose(sv.probs(wires), r.probs(wires), atol=ptol, err_msg=str(wires))
+    shots = 20000
+    smp = sv.GenerateSamples(n, shots)
+    assert smp.shape == (shots, n)
+    idx = (smp * (1 << np.arange(n - 1, -1, -1, dtype=np.uint64))).sum(axis=1)
+    hist = np.bincount(idx.astype(np.int64), minlength=1 << n) / shots
+    assert np.max(np.abs(hist - r.probs())) < 0.02
+    # adjoint: RX RY (CNOT) RZ per wire, <Z_0>, <X_{n-1}> and their tensor / sum
+    circ = [("RX", [0], False, [0.4]), ("RY", [n - 1], True, [-0.9])]
+    if n == 2:
+        circ += [("CNOT", [0, 1], False, []), ("IsingXY", [1, 0], False, [0.3])]
+    circ += [("RZ", [0], False, [1.1]), ("PhaseShift", [n - 1], False, [0.2])]
+    names, wires = [c[0] for c in circ], [c[1] for c in circ]
+    invs, params = [c[2] for c in circ], [c[3] for c in circ]
+    sv2 = sv_class(ops, dtype)(n)
+    sv2.apply(names, wires, invs, params)
+    r2 = ref.RefStateVector(n, dtype)
+    r2.apply_ops(circ)
+    g_all = [N("PauliZ", [0]), N("PauliX", [n - 1]),
+             getattr(ops, f"HamiltonianKokkos_{S}")([0.5, -0.25], [N("PauliZ", [0]), N("PauliY", [n - 1])])]
+    r_all = [ref.RefObs.named("PauliZ", [0], prec), ref.RefObs.named("PauliX", [n - 1], prec),
+             ref.RefObs.hamiltonian([0.5, -0.25], [ref.RefObs.named("PauliZ", [0], prec),
+                                                   ref.RefObs.named("PauliY", [n - 1], prec)], prec)]
+    adj = getattr(ops, f"AdjointJacobianKokkos_{S}")()
+    ol = adj.create_ops_list(names, [np.array(x) for x in params], wires, invs, [np.zeros(0)] * len(names))
+    tp = list(range(sum(1 for c in circ if c[3])))
+    jac = adj.adjoint_jacobian(sv2, g_all, ol, tp)
+    want = r2.adjoint_jacobian(r_all, circ, tp)
+    assert rel_err(jac, want) < (1e-12 if dtype == np.complex128 else 2e-5)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

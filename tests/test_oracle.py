@@ -205,12 +205,12 @@ def test_reference_param_gate_literals_pin_both_oracles():
     """The literal in/out state vectors of the reference's own parametric-gate tests
     (src/tests/Test_StateVectorKokkos_Param.cpp: IsingXY :24-62, RX :92-150, IsingXX/YY/ZZ :508-855,
     MultiRZ :856-953, SingleExcitation[Minus/Plus] :960-1110, DoubleExcitation[Minus/Plus] :1127-1320)
-    and fixed-gate tests (Test_StateVectorKokkos_NonParam.cpp: SWAP :428-625, CZ :626-822, Toffoli
-    :823-931, CSWAP :1011-1113), extracted by tests/golden/make_ref_literals.py,
+    and fixed-gate tests (Test_StateVectorKokkos_NonParam.cpp: PauliY/PauliZ/S/T :119-378, SWAP :428-625,
+    CZ :626-822, Toffoli :823-931, CSWAP :1011-1113), extracted by tests/golden/make_ref_literals.py,
     pin the compiled reference over the Kokkos stand-in AND the NumPy restatement."""
     cases = _ref_param_literals()
-    assert len(cases) >= 61
-    assert {"IsingXX", "IsingYY", "IsingZZ", "MultiRZ", "RX", "SWAP", "CZ", "Toffoli", "CSWAP"} <= {c["gate"] for c in cases}
+    assert len(cases) >= 73
+    assert {"IsingXX", "IsingYY", "IsingZZ", "MultiRZ", "RX", "SWAP", "CZ", "Toffoli", "CSWAP", "PauliY", "PauliZ", "S", "T"} <= {c["gate"] for c in cases}
     for c in cases:
         ini = np.array([complex(a, b) for a, b in c["ini"]])
         want = np.array([complex(a, b) for a, b in c["expected"]])
