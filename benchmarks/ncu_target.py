@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small driver for ncu captures: BASELINE config-2 layers on an n-qubit c128 state (default 28),
-one warm-up step then one profiled step.  usage: python benchmarks/ncu_target.py [qubits] [layers]"""
+one warm-up step then one profiled step.  usage: python benchmarks/ncu_target.py [qubits] [layers] [c128|c64]"""
 import os
 import sys
 
@@ -11,11 +11,12 @@ from pennylane_lightning_kokkos_b200 import lightning_kokkos_qubit_ops as ops  #
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 28
 layers = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+S = "C64" if len(sys.argv) > 3 and sys.argv[3] == "c64" else "C128"
 circ = layer_circuit(n, layers, seed=42)
-sv = ops.LightningKokkos_C128(n)
-had = ops.OpsStructKokkos_C128(["Hadamard"] * n, [[] for _ in range(n)], [[w] for w in range(n)], [False] * n)
+sv = getattr(ops, f"LightningKokkos_{S}")(n)
+had = getattr(ops, f"OpsStructKokkos_{S}")(["Hadamard"] * n, [[] for _ in range(n)], [[w] for w in range(n)], [False] * n)
 sv.apply_ops(had)
-ol = ops.OpsStructKokkos_C128([c[0] for c in circ], [c[3] for c in circ], [c[1] for c in circ], [c[2] for c in circ])
+ol = getattr(ops, f"OpsStructKokkos_{S}")([c[0] for c in circ], [c[3] for c in circ], [c[1] for c in circ], [c[2] for c in circ])
 for _ in range(2):
     sv.apply_ops(ol)
     sv.sync()

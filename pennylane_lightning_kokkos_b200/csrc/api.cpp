@@ -366,6 +366,7 @@ int b2sv_plan_ops(const b2sv_ops *ops, int num_qubits, int dtype, uint64_t *pass
         SchedConfig cfg;
         tile_config(dtype, &cfg.B, &cfg.R);
         cfg.SW = dtype == 1 ? 3 : 4;
+        cfg.SH = dtype == 1 ? 0 : 1;
         cfg.f32 = dtype != 1;
         cfg.n_local = num_qubits;
         cfg.n_alloc = std::max(num_qubits, cfg.B);
@@ -431,6 +432,7 @@ int b2sv_plan_sharded(const b2sv_ops *ops, int num_qubits, int world, int dtype,
         SchedConfig cfg;
         tile_config(dtype, &cfg.B, &cfg.R);
         cfg.SW = dtype == 1 ? 3 : 4;
+        cfg.SH = dtype == 1 ? 0 : 1;
         cfg.f32 = dtype != 1;
         cfg.n_local = pc.n_local;
         cfg.n_alloc = std::max(pc.n_local, cfg.B);

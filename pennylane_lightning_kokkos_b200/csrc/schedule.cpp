@@ -329,7 +329,7 @@ void fill_tile_id_segments(DevPassHeader &hdr, uint64_t excluded_mask, int top) 
 
 int default_tile_low() {
     const char *e = getenv("B2SV_TILE_LOW"); // read on every call: experiments sweep it
-    return e ? std::max(2, std::min(6, atoi(e))) : kDefaultTileLow;
+    return e ? std::max(3, std::min(6, atoi(e))) : kDefaultTileLow; // 3 = the tile kernel's kMinLow
 }
 
 double schedule_cost(const std::vector<Pass> &passes) {
@@ -522,7 +522,7 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
         // fill with bulk async copies of whole HBM runs (cp.async.bulk) instead of one 16-byte cp.async
         // per amplitude.
         auto make_pass = [&](bool plain) -> Pass {
-        auto PH = [&](uint32_t v) { return plain ? v : phys_slot(v, B, cfg.SW); };
+        auto PH = [&](uint32_t v) { return plain ? v : phys_slot(v, B, cfg.SW, cfg.SH); };
         Pass ps;
         ps.hdr.low_bits = low;
         {
@@ -532,12 +532,13 @@ std::vector<Pass> build_schedule_fixed(const std::vector<Prim> &prims_in, const 
                     ps.hdr.tile_bits[j++] = static_cast<uint8_t>(b);
             B2_ASSERT(j == B);
         }
-        for (int e = 0; e < 64 && (e << 7) < (1 << B); e++) {
+        // a load thread's e-th copy is the 16-byte unit e * 128 + (thread): tile-local index (e * 128) << SH
+        for (int e = 0; e < 64 && (e << (7 + cfg.SH)) < (1 << B); e++) {
             uint64_t off = 0;
-            for (int j = 7; j < B; j++)
-                if (((e << 7) >> j) & 1)
+            for (int j = 7 + cfg.SH; j < B; j++)
+                if (((e << (7 + cfg.SH)) >> j) & 1)
                     off |= bit(ps.hdr.tile_bits[j]);
-            ps.hdr.load_off[e] = off;
+            ps.hdr.load_off[e] = off * (cfg.f32 ? 8u : 16u); // bytes: the load warps add it to a byte pointer
         }
         fill_tile_id_segments(ps.hdr, tile_mask, std::max(cfg.n_alloc, cfg.n_local));
         // ---- rounds, with permutation primitives folded into the address map at round boundaries

@@ -97,8 +97,8 @@ struct alignas(16) DevPassHeader {
     uint64_t store_free[kMaxFreeBits];
     uint64_t store_reg[8];
     uint64_t store_cx[kMaxCx];
-    // load warps: global index offset of tile-local index e * 128 (the part of a load thread's
-    // element index that does not depend on the thread), e < 2^B / 128
+    // load warps: global BYTE offset of tile-local index e * 128 (the part of a load thread's
+    // element address that does not depend on the thread), e < 2^B / 128
     uint64_t load_off[64];
     uint16_t round_begin[kMaxRounds + 1]; // op index ranges per round
     uint16_t pad_[3];
@@ -134,6 +134,7 @@ struct SchedConfig {
     int B = 12;        // tile bits
     int R = 4;         // register bits
     int SW = 3;        // log2(amplitudes per 128 B): the shared-memory swizzle width
+    int SH = 0;        // log2(amplitudes per 16 B): index bits below SH are not swizzled (1 for complex64)
     int low = 5;       // contiguous low bits forced into every tile
     int n_local = 0;   // bits >= n_local cannot be targets (rank bits when sharded)
     int n_alloc = 0;   // index bits of the allocation (>= B; small states are zero-padded)
@@ -156,13 +157,16 @@ struct SchedConfig {
 // contiguous low index bits kept in every tile (2^low amplitudes per HBM run); B2SV_TILE_LOW overrides
 int default_tile_low();
 
-// Shared-memory swizzle (same function as tile_kernel.cu phys<B,SW>): XOR-folds every higher
-// SW-bit group of the index into its low SW bits. GF(2)-linear.
-inline uint32_t phys_slot(uint32_t i, int B, int SW) {
+// Shared-memory swizzle (same function as tile_kernel.cuh phys<B,SW,SH>): XOR-folds every higher
+// (SW - SH)-bit group of the index into bits SH .. SW-1. GF(2)-linear. SW = log2(amplitudes per 128 B),
+// SH = log2(amplitudes per 16 B): complex64 keeps bit 0 in place, so the two amplitudes of a 16-byte
+// unit stay together and the load warps copy 16 bytes at a time (L1-bypassing cp.async.cg).
+inline uint32_t phys_slot(uint32_t i, int B, int SW, int SH = 0) {
+    const int FW = SW - SH;
     uint32_t f = 0;
-    for (int s = SW; s < B; s += SW)
+    for (int s = SH + FW; s < B; s += FW)
         f ^= (i >> s);
-    return i ^ (f & ((1u << SW) - 1u));
+    return i ^ ((f & ((1u << FW) - 1u)) << SH);
 }
 
 // Pre-pass: merge runs of uncontrolled single-bit primitives on the same bit into one 2x2.

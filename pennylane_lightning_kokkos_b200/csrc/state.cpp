@@ -1037,6 +1037,7 @@ SchedConfig State::sched_config() const {
     if (const char *e = getenv("B2SV_MAX_HEAVY"))
         cfg.max_heavy = std::max(1, atoi(e));
     cfg.SW = dtype_ == 1 ? 3 : 4;
+    cfg.SH = dtype_ == 1 ? 0 : 1;
     cfg.f32 = dtype_ != 1;
     if (const char *e = getenv("B2SV_FACTOR"))
         cfg.factor = atoi(e) != 0;

@@ -24,10 +24,11 @@
 //     the launcher (launch_tile_pass_t) picks the leanest one that covers the pass.
 // HBM traffic is exactly one read + one write of the state per pass, whatever the number of gates.
 //
-// Shared-memory layout: amplitude i of the tile lives at slot phys(i) = i ^ fold(i) where fold XORs
-// the higher SW-bit groups of i into its low SW bits (SW = log2(128 B / sizeof(amp))). phys is
-// GF(2)-linear, so phys(base | off) = phys(base) ^ phys(off), and any 8 (c128) / 16 (c64) consecutive
-// lanes hit distinct 16 B / 8 B bank groups for every choice of register bits.
+// Shared-memory layout: amplitude i of the tile lives at slot phys(i) = i ^ (fold(i) << SH) where fold
+// XORs the higher 3-bit groups of i into bits SH .. SH+2 (SH = 0 for complex128, 1 for complex64: the
+// two complex64 of a 16-byte unit stay together, so both types are loaded with 16-byte cp.async.cg).
+// phys is GF(2)-linear, so phys(base | off) = phys(base) ^ phys(off), and any 8 consecutive lanes hit
+// distinct 16 B bank groups for every choice of register bits.
 #pragma once
 #include "schedule.hpp"
 
@@ -45,25 +46,22 @@ template <> struct AmpT<float> {
     using type = float2;
 };
 
-template <int B, int SW> __device__ __forceinline__ uint32_t phys(uint32_t i) {
+template <int B, int SW, int SH = 0> __host__ __device__ __forceinline__ constexpr uint32_t phys(uint32_t i) {
+    constexpr int FW = SW - SH;
     uint32_t f = 0;
-#pragma unroll
-    for (int s = SW; s < B; s += SW)
+    for (int s = SH + FW; s < B; s += FW)
         f ^= (i >> s);
-    return i ^ (f & ((1u << SW) - 1u));
+    return i ^ ((f & ((1u << FW) - 1u)) << SH);
 }
 
 // ---- async-copy / mbarrier / named-barrier primitives ----------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void cp_async_amp(double2 *dst, const double2 *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_amp(float2 *dst, const float2 *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(dst)), "l"(src)
-                 : "memory");
+// 16 bytes global -> shared (L1-bypassing), destination given as a shared-window address
+template <int BYTES> __device__ __forceinline__ void cp_async_to(uint32_t dst, const void *src) {
+    static_assert(BYTES == 16, "the tile loader copies 16-byte units");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
 }
 // the mbarrier receives one arrival from this thread once all its cp.async issued so far have landed
 __device__ __forceinline__ void cp_async_arrive(uint64_t *mbar) {
@@ -398,8 +396,9 @@ __device__ __forceinline__ void dense_factored(amp_t (&a)[NS], const DevDense &d
         a[s].y = p.x * v.y + p.y * v.x;
     }
 }
+// pb / poff: byte offsets from the start of the tile buffers (buffer offset included in pb)
 template <int R, int NS, typename amp_t>
-__device__ __forceinline__ void scatter_round(amp_t *tile, const amp_t (&a)[NS], uint32_t pb,
+__device__ __forceinline__ void scatter_round(unsigned char *tiles_raw, const amp_t (&a)[NS], uint32_t pb,
                                               const uint32_t (&poff)[R]) {
 #pragma unroll
     for (int s = 0; s < NS; s++) {
@@ -408,27 +407,20 @@ __device__ __forceinline__ void scatter_round(amp_t *tile, const amp_t (&a)[NS],
         for (int c = 0; c < R; c++)
             if (s & (1 << c))
                 x ^= poff[c];
-        tile[x] = a[s];
+        *reinterpret_cast<amp_t *>(tiles_raw + x) = a[s];
     }
 }
 
-// last round of a pass: registers -> HBM directly. Addresses are XOR-combinations of global index
-// offsets read from the (uniform) pass descriptor; computed here, after the arithmetic, so nothing
-// extra stays live across the round.
-template <int R, int NS, int NF, typename amp_t>
+// last round of a pass: registers -> HBM directly. `sbase` = global index of this thread's register
+// slot 0: the tile's part (base index ^ the conditional toggles that fire for it, published by the load
+// warps) ^ the thread's part (tabulated once per pass); the slots are XOR-combinations of the uniform
+// store_reg offsets away.
+template <int R, int NS, typename amp_t>
 __device__ __forceinline__ void store_round(amp_t *__restrict__ state, const amp_t (&a)[NS],
-                                            const DevPassHeader &ph, uint64_t tb, uint64_t tbr,
-                                            int tid) {
-    uint64_t addr0 = tb;
-#pragma unroll
-    for (int c = 0; c < NF; c++)
-        addr0 ^= (uint64_t(0) - ((static_cast<uint64_t>(tid) >> c) & 1u)) & ph.store_free[c];
-    for (int c = 0; c < ph.n_cx; c++)
-        if ((tbr & ph.cx[c].gcm) == ph.cx[c].gcv)
-            addr0 ^= ph.store_cx[c];
+                                            const DevPassHeader &ph, uint64_t sbase) {
 #pragma unroll
     for (int s = 0; s < NS; s++) {
-        uint64_t x = addr0;
+        uint64_t x = sbase;
 #pragma unroll
         for (int c = 0; c < R; c++)
             if (s & (1 << c))
@@ -437,31 +429,30 @@ __device__ __forceinline__ void store_round(amp_t *__restrict__ state, const amp
     }
 }
 // mode: 0 = scatter back in place, 1 = registers -> HBM
-template <int R, int NS, int NF, typename amp_t>
-__device__ __forceinline__ void finish_round(int mode, amp_t *__restrict__ state, amp_t *tile,
+template <int R, int NS, typename amp_t>
+__device__ __forceinline__ void finish_round(int mode, amp_t *__restrict__ state, unsigned char *tiles_raw,
                                              const amp_t (&a)[NS], uint32_t pb,
                                              const uint32_t (&poff)[R], const DevPassHeader &ph,
-                                             uint64_t tb, uint64_t tbr, int tid) {
+                                             uint64_t sbase) {
     if (mode == 1)
-        store_round<R, NS, NF>(state, a, ph, tb, tbr, tid);
+        store_round<R, NS>(state, a, ph, sbase);
     else
-        scatter_round<R, NS>(tile, a, pb, poff);
+        scatter_round<R, NS>(tiles_raw, a, pb, poff);
 }
 
 // Factored round whose constants sit at a compile-time offset of the kernel parameter (round RD):
 // ptxas reads them through the uniform datapath (LDCU -> DFMA R, R, UR, R), no vector registers.
-template <int RD, int R, int NS, int NF, typename amp_t, typename real>
+template <int RD, int R, int NS, typename amp_t, typename real>
 __device__ __forceinline__ bool factored_round_fixed(int kind, amp_t (&a)[NS], const PassParams &pp,
                                                      int mode, amp_t *__restrict__ state,
-                                                     amp_t *tile, uint32_t pb,
-                                                     const uint32_t (&poff)[R], uint64_t tb,
-                                                     uint64_t tbr, int tid) {
+                                                     unsigned char *tiles_raw, uint32_t pb,
+                                                     const uint32_t (&poff)[R], uint64_t sbase) {
     switch (kind) {
 #define B2_FIX(G)                                                                               \
     case 8 + G:                                                                                 \
         if constexpr (G <= R) {                                                                 \
             dense_factored<G, R, NS, amp_t, real>(a, pp.dense[RD]);                             \
-            finish_round<R, NS, NF>(mode, state, tile, a, pb, poff, pp.hdr, tb, tbr, tid);      \
+            finish_round<R, NS>(mode, state, tiles_raw, a, pb, poff, pp.hdr, sbase);            \
             return true;                                                                        \
         }                                                                                       \
         break;
@@ -482,6 +473,7 @@ __device__ __forceinline__ bool factored_round_fixed(int kind, amp_t (&a)[NS], c
 // them in 16 vector registers per thread.
 // helper warps: one warpgroup that does nothing but stream tiles into shared memory (cp.async)
 constexpr int kLoadThreads = 128;
+constexpr int kMinLow = 3; // smallest B2SV_TILE_LOW the row-offset table is sized for
 
 // Optional phase timers (B2SV_TILE_PROF=1): cycles summed over the lead thread of every worker group
 // / load warpgroup of every CTA. [0] workers waiting for a tile, [1] workers busy on tiles,
@@ -493,9 +485,11 @@ static __device__ unsigned long long g_tile_prof[16];
 // per-buffer facts about the tile it holds, written by the load warps ahead of the workers
 struct TileInfo {
     uint64_t tb;                    // index of the tile's first amplitude (tile bits cleared)
+    uint64_t store_base;            // tb ^ the conditional toggles of the fused store that fire for this tile
     uint32_t xoff[kMaxRounds + 1];  // CTA-uniform address toggles visible from round r on
     uint32_t pad_;
 };
+constexpr int kAccRounds = 4; // rounds whose per-thread gather bases are tabulated in shared memory
 
 // FACT / INTERP / DENSEK: the kernel contains the factored-round bodies / the per-op interpreter / the
 // unfactored dense rounds of 2..5 gates (one-gate dense rounds are in every variant). A pass is
@@ -519,7 +513,8 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
     const bool gsync =
         INTERP ? true : ((flags & 2u) ? false : ((flags & 1u) != 0 || pp.hdr.n_rounds <= 1));
     using amp_t = typename AmpT<real>::type;
-    constexpr int SW = (sizeof(amp_t) == 16) ? 3 : 4;
+    constexpr int SW = (sizeof(amp_t) == 16) ? 3 : 4; // log2(amplitudes per 128 B)
+    constexpr int SH = (sizeof(amp_t) == 16) ? 0 : 1; // log2(amplitudes per 16 B): not swizzled
     constexpr int NS = 1 << R;
     constexpr int TILE = 1 << B;
     constexpr int NF = B - R; // non-register tile bits = thread-id bits within a group
@@ -532,6 +527,10 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
     amp_t *tiles = reinterpret_cast<amp_t *>(smem_raw); // kTileBuffers buffers of TILE amplitudes
     DevOp *sops = reinterpret_cast<DevOp *>(smem_raw + kTileBuffers * sizeof(amp_t) * TILE);
     uint64_t *rowoff = reinterpret_cast<uint64_t *>(sops + kMaxOpsPerPass);
+    // per-thread constants of the pass (the same for both worker groups): the thread part of the fused
+    // store's global index, and (base << 16 | storage slot) of the thread's register group per round
+    uint64_t *sfree = rowoff + (size_t(1) << (B - kMinLow));
+    uint32_t *acc_tab = reinterpret_cast<uint32_t *>(sfree + GT);
     __shared__ DevPassHeader hdr;
     __shared__ TileInfo tinfo[kTileBuffers];
     __shared__ __align__(8) uint64_t full[kTileBuffers], empty[kTileBuffers];
@@ -563,6 +562,20 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
             if ((r >> (j - low)) & 1)
                 off |= uint64_t(1) << hdr.tile_bits[j];
         rowoff[r] = off;
+    }
+    for (int t = threadIdx.x; t < GT; t += NTHREADS) {
+        uint64_t sf = 0;
+#pragma unroll
+        for (int c = 0; c < NF; c++)
+            sf ^= (uint64_t(0) - ((static_cast<uint64_t>(t) >> c) & 1u)) & hdr.store_free[c];
+        sfree[t] = sf;
+        for (int rd = 0; rd < kAccRounds; rd++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int c = 0; c < NF; c++)
+                acc ^= (0u - ((static_cast<uint32_t>(t) >> c) & 1u)) & hdr.round_col[rd][c];
+            acc_tab[rd * GT + t] = acc;
+        }
     }
     const int n_rounds = pp.hdr.n_rounds;
     const uint32_t lowmask = (1u << low) - 1u;
@@ -627,8 +640,13 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
                     if (ptid == 0)
                         tinfo[bi].xoff[r] = x;
                 }
+                // fused store: the conditional toggles of the global index that fire for this tile
+                const uint64_t sx = (fire && ptid < hdr.n_cx) ? hdr.store_cx[ptid] : uint64_t(0);
+                const uint32_t sx_lo = __reduce_xor_sync(0xffffffffu, static_cast<uint32_t>(sx));
+                const uint32_t sx_hi = __reduce_xor_sync(0xffffffffu, static_cast<uint32_t>(sx >> 32));
                 if (ptid == 0) {
                     tinfo[bi].tb = tb;
+                    tinfo[bi].store_base = tb ^ (static_cast<uint64_t>(sx_hi) << 32 | sx_lo);
                     if (plain)
                         mbar_arrive_expect_tx(&full[bi], static_cast<uint32_t>(TILE * sizeof(amp_t)));
                     else
@@ -648,12 +666,25 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
             } else {
             // element i = e * 128 + ptid: the thread part of both addresses is loop-invariant, the
             // e part is a compile-time slot offset and a uniform (constant-bank) index offset
-            amp_t *buf = tiles + bi * TILE;
-            const uint32_t slot = phys<B, SW>(ptid);
-            const amp_t *src = state + (tb | rowoff[ptid >> low] | (ptid & lowmask));
+            // The tile is copied in 16-byte units (one complex128, two complex64 that the swizzle keeps
+            // together): unit q = e * 128 + ptid holds tile-local index q << SH and lands in unit slot
+            // phys<B - SH, SW - SH>(q) = (phys(ptid) ^ f_e) + e * 128 with f_e the swizzle fold of e * 128
+            // (a compile-time constant below 8). The copies are issued grouped by f_e, so that each is one
+            // LDGSTS at an immediate offset of a per-group base address.
+            constexpr int BU = B - SH, FW = SW - SH; // log2(units per tile), swizzled unit bits
+            constexpr uint32_t UPT = (1u << BU) / kLoadThreads;
+            const uint32_t dbase = smem_u32(smem_raw) + static_cast<uint32_t>(bi) * ((1u << BU) * 16u);
+            const uint32_t slotB = phys<BU, FW>(static_cast<uint32_t>(ptid)) * 16u;
+            const uint32_t li = static_cast<uint32_t>(ptid) << SH; // tile-local index of the thread's part
+            const char *src = reinterpret_cast<const char *>(state + (tb | rowoff[li >> low] | (li & lowmask)));
 #pragma unroll
-            for (int e = 0; e < TILE / kLoadThreads; e++)
-                cp_async_amp(buf + (slot ^ phys<B, SW>(e * kLoadThreads)), src + pp.hdr.load_off[e]);
+            for (int f = 0; f < (1 << FW); f++) {
+                const uint32_t d = dbase + (slotB ^ (static_cast<uint32_t>(f) * 16u));
+#pragma unroll
+                for (uint32_t e = 0; e < UPT; e++)
+                    if ((phys<BU, FW>(e * kLoadThreads) & ((1u << FW) - 1u)) == static_cast<uint32_t>(f))
+                        cp_async_to<16>(d + e * kLoadThreads * 16u, src + pp.hdr.load_off[e]);
+            }
             cp_async_arrive(&full[bi]);
             if constexpr (PROF)
                 p_issue += clock64() - p_t1;
@@ -700,15 +731,22 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
         for (int rd = 0; rd < n_rounds; rd++) {
             // this thread's register group: logical base index (high half), storage slot (low half)
             uint32_t acc = 0;
+            if (rd < kAccRounds) {
+                acc = acc_tab[rd * GT + tid];
+            } else {
 #pragma unroll
-            for (int c = 0; c < NF; c++)
-                acc ^= (0u - ((static_cast<uint32_t>(tid) >> c) & 1u)) & hdr.round_col[rd][c];
+                for (int c = 0; c < NF; c++)
+                    acc ^= (0u - ((static_cast<uint32_t>(tid) >> c) & 1u)) & hdr.round_col[rd][c];
+            }
             const uint32_t base = acc >> 16;
-            const uint32_t pb = (acc & 0xffffu) ^ xoff[rd];
+            // Byte offsets from the start of the tile buffers: the buffer's own offset is a multiple of the
+            // tile size, so it joins the XOR and every gather / scatter address is one LOP3 away from pb.
+            constexpr uint32_t AB = static_cast<uint32_t>(sizeof(amp_t));
+            const uint32_t pb = (((acc & 0xffffu) ^ xoff[rd]) * AB) ^ (static_cast<uint32_t>(bi) * (TILE * AB));
             uint32_t poff[R];
 #pragma unroll
             for (int s = 0; s < R; s++)
-                poff[s] = hdr.round_poff[rd][s];
+                poff[s] = static_cast<uint32_t>(hdr.round_poff[rd][s]) * AB;
             const int o_begin = pp.hdr.round_begin[rd], o_end = pp.hdr.round_begin[rd + 1];
             if constexpr (PROF)
                 w_r0 = clock64();
@@ -720,7 +758,7 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
                 for (int c = 0; c < R; c++)
                     if (s & (1 << c))
                         x ^= poff[c];
-                a[s] = tile[x];
+                a[s] = *reinterpret_cast<const amp_t *>(smem_raw + x);
             }
             // a zero the compiler cannot see through: the 2^R scatter addresses are recomputed
             // after the arithmetic instead of being kept alive -- and spilled -- across the round
@@ -729,6 +767,9 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
             // fused store: the last round's registers go straight to HBM; the tile buffer is free
             // as soon as every thread of the group has gathered from it
             const int fused = rd == n_rounds - 1 ? pp.hdr.fused_store : 0;
+            uint64_t sbase = 0; // global index of register slot 0 in the fused store (read before the release)
+            if (fused == 1)
+                sbase = tinfo[bi].store_base ^ sfree[tid];
             if (fused == 1 && gsync) {
                 if constexpr (plain)
                     fence_proxy_async();
@@ -749,7 +790,7 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
 #pragma unroll 1
                     for (int oi = o_begin; oi < o_end; oi++)
                         run_op<R, NS, amp_t, real>(a, sops[oi], tbr, base);
-                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
+                    finish_round<R, NS>(fused, state, smem_raw, a, pb ^ opaque_zero, poff, pp.hdr, sbase);
                 } else {
                     __trap(); // the launcher picked a variant without the interpreter
                 }
@@ -764,8 +805,8 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
                 switch (rd) {
 #define B2_RD(RD)                                                                               \
     case RD:                                                                                    \
-        done = factored_round_fixed<RD, R, NS, NF, amp_t, real>(                                \
-            kind, a, pp, fused, state, tile, pb ^ opaque_zero, poff, tb, tbr, tid);             \
+        done = factored_round_fixed<RD, R, NS, amp_t, real>(                                    \
+            kind, a, pp, fused, state, smem_raw, pb ^ opaque_zero, poff, sbase);                \
         break;
                     B2_RD(0)
                     B2_RD(1)
@@ -781,8 +822,8 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
     case 8 + G:                                                                                 \
         if constexpr (FACT && G <= R) {                                                         \
             dense_factored<G, R, NS, amp_t, real>(a, pp.dense[rd]);                             \
-            finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb,  \
-                                    tbr, tid);                                                  \
+            finish_round<R, NS>(fused, state, smem_raw, a, pb ^ opaque_zero, poff, pp.hdr,      \
+                                sbase);                                                         \
         }                                                                                       \
         break;
                         B2_FACT(2)
@@ -800,26 +841,26 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
                 switch (kind) {
                 case 1:
                     dense_round<1, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                    finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
+                    finish_round<R, NS>(fused, state, smem_raw, a, pb ^ opaque_zero, poff, pp.hdr, sbase);
                     break;
                 default:
                     if constexpr (DENSEK) {
                         switch (kind) {
                         case 2:
                             dense_round<2, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                            finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
+                            finish_round<R, NS>(fused, state, smem_raw, a, pb ^ opaque_zero, poff, pp.hdr, sbase);
                             break;
                         case 3:
                             dense_round<3, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                            finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
+                            finish_round<R, NS>(fused, state, smem_raw, a, pb ^ opaque_zero, poff, pp.hdr, sbase);
                             break;
                         case 4:
                             dense_round<4, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                            finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
+                            finish_round<R, NS>(fused, state, smem_raw, a, pb ^ opaque_zero, poff, pp.hdr, sbase);
                             break;
                         default:
                             dense_round<5, R, NS, amp_t, real>(a, pp.ops + o_begin);
-                            finish_round<R, NS, NF>(fused, state, tile, a, pb ^ opaque_zero, poff, pp.hdr, tb, tbr, tid);
+                            finish_round<R, NS>(fused, state, smem_raw, a, pb ^ opaque_zero, poff, pp.hdr, sbase);
                             break;
                         }
                     } else {
@@ -883,10 +924,10 @@ __global__ void __launch_bounds__(NG * GT + kLoadThreads, 1)
 
 // ---- host side ----------------------------------------------------------------------------------
 namespace {
-constexpr int kMinLow = 2; // smallest B2SV_TILE_LOW the row-offset table is sized for
-template <typename real, int B, int NB> constexpr size_t tile_smem_bytes() {
+template <typename real, int B, int NB, int GT> constexpr size_t tile_smem_bytes() {
     return NB * sizeof(typename AmpT<real>::type) * (size_t(1) << B) +
-           sizeof(DevOp) * kMaxOpsPerPass + sizeof(uint64_t) * (size_t(1) << (B - kMinLow));
+           sizeof(DevOp) * kMaxOpsPerPass + sizeof(uint64_t) * (size_t(1) << (B - kMinLow)) +
+           sizeof(uint64_t) * GT + sizeof(uint32_t) * kAccRounds * GT;
 }
 int sm_count() { return sm_count_current_device(); }
 int env_int(const char *name, int dflt) {
@@ -903,7 +944,8 @@ void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_
                     cudaStream_t stream, int max_ctas) {
     using amp_t = typename AmpT<real>::type;
     auto kern = tile_exec_kernel<real, B, R, GT, NG, NB, FACT, INTERP, DENSEK, PROF, BULK>;
-    constexpr size_t smem = tile_smem_bytes<real, B, NB>();
+    constexpr size_t smem = tile_smem_bytes<real, B, NB, GT>();
+    static_assert(smem + 6 * 1024 <= 227 * 1024, "dynamic + static shared memory of the tile kernel");
     static uint64_t configured = 0; // one bit per device: the attribute is per device
     if (first_use_on_device(configured))
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -924,6 +966,7 @@ void launch_variant(void *state, const PassParams &pp, int n_eff, uint64_t rank_
 template <typename real, int B, int R, bool BULK>
 void launch_tile_pass_v(void *state, const PassParams &pp, int n_eff, uint64_t rank_bits,
                         cudaStream_t stream, int max_ctas) {
+    B2_ABORT_IF(pp.hdr.low_bits < kMinLow, "tile executor: fewer contiguous low bits than the row table is sized for");
     bool fact = false, interp = false, densek = false;
     for (int rd = 0; rd < pp.hdr.n_rounds; rd++) {
         const int kind = pp.hdr.round_kind[rd];

@@ -22,10 +22,10 @@ template <typename real> struct Amp {
 
 template <typename real> struct Emu {
     using amp = Amp<real>;
-    int B, R, SW, low, n_eff;
+    int B, R, SW, SH, low, n_eff;
     std::vector<amp> &state;
 
-    uint32_t phys(uint32_t i) const { return phys_slot(i, B, SW); }
+    uint32_t phys(uint32_t i) const { return phys_slot(i, B, SW, SH); }
 
     void run_op(amp *a, const DevOp &op, uint64_t tbr, uint32_t base) const {
         const int NS = 1 << R;
@@ -206,6 +206,7 @@ int run(int n, int B, int R, int low, int max_heavy, int factor, int store_mode,
     cfg.R = R;
     cfg.low = low;
     cfg.SW = sizeof(real) == 8 ? 3 : 4;
+    cfg.SH = sizeof(real) == 8 ? 0 : 1;
     cfg.f32 = sizeof(real) == 4;
     cfg.factor = factor != 0;
     cfg.max_heavy = max_heavy;
@@ -219,7 +220,7 @@ int run(int n, int B, int R, int low, int max_heavy, int factor, int store_mode,
     std::vector<Amp<real>> state(size_t(1) << n_eff, Amp<real>{0, 0});
     for (size_t i = 0; i < (size_t(1) << n); i++)
         state[i] = {static_cast<real>(st[2 * i]), static_cast<real>(st[2 * i + 1])};
-    Emu<real> emu{B, R, cfg.SW, low, n_eff, state};
+    Emu<real> emu{B, R, cfg.SW, cfg.SH, low, n_eff, state};
     uint64_t n_pass = 0, n_fact = 0, n_dense = 0, n_rounds = 0, n_fused = 0, n_staged = 0;
     for (const Pass &ps : build_schedule(prims, cfg)) {
         B2_ABORT_IF(ps.is_matk, "emulator: generic k-qubit matrices are not covered");

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Turn an `ncu --set full` report into the short text summary kept under profiles/.
 
-usage: python profiles/summarize_ncu.py gpurun_out/<name>.ncu-rep > profiles/<name>.summary.txt
+usage: python profiles/summarize_ncu.py gpurun_out/<name>.ncu-rep [launch] > profiles/<name>.summary.txt
+(`launch` = which captured launch the stall reasons and the SASS mix are taken from, default 0)
 (reads the report with `ncu -i ... --page raw --csv` and `--page source --csv`; no GPU needed)
 """
 import collections
@@ -25,6 +26,7 @@ KEYS = [
 
 def main():
     rep = sys.argv[1]
+    which = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -37,8 +39,8 @@ def main():
             i = hdr.index(k)
             print(f"{k} [{units[i]}]: " + ", ".join(r[i] for r in rows[2:]))
     stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio")]
-    print("# warp stall reasons (stalled warps per issued instruction), first launch")
-    vals = sorted(((float(rows[2][hdr.index(h)]), h) for h in stall), reverse=True)
+    print(f"# warp stall reasons (stalled warps per issued instruction), launch {which}")
+    vals = sorted(((float(rows[2 + which][hdr.index(h)]), h) for h in stall), reverse=True)
     for v, h in vals[:8]:
         print(f"  {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):28s} {v:.3f}")
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
@@ -46,10 +48,11 @@ def main():
     srows = list(csv.reader(io.StringIO(src)))
     starts = [i for i, r in enumerate(srows) if r and r[0] == "Address"]
     if starts:
-        h = srows[starts[0]]
+        st = starts[min(which, len(starts) - 1)]
+        h = srows[st]
         idx = {n: i for i, n in enumerate(h)}
         data = []
-        for r in srows[starts[0] + 1:]:
+        for r in srows[st + 1:]:
             if len(r) < len(h) or r[0] in ("Address", "Kernel Name"):
                 break
             data.append(r)
@@ -60,8 +63,8 @@ def main():
             exe[op] += int(r[idx["Instructions Executed"]])
             smp[op] += int(r[idx["# Samples"]])
         te, ts = sum(exe.values()), max(1, sum(smp.values()))
-        print("# SASS mix of the first launch (share of executed warp instructions / of stall samples)")
-        for op, c in exe.most_common(12):
+        print(f"# SASS mix of launch {which} (share of executed warp instructions / of stall samples)")
+        for op, c in exe.most_common(16):
             print(f"  {op:10s} {c / te * 100:5.1f}%  {smp[op] / ts * 100:5.1f}%")
 
 
