@@ -376,6 +376,20 @@ __device__ __forceinline__ void dense_factored(amp_t (&a)[NS], const DevDense &d
 #pragma unroll
     for (int k = 0; k < GG; k++) {
         const real t01 = t[2 * k], t10 = t[2 * k + 1];
+        if constexpr (sizeof(real) == 4) {
+            // complex64: a real shear acts on (re, im) alike -- one packed FFMA2 (sm_100 fma.rn.f32x2,
+            // each half rounded like a scalar FMA) per amplitude instead of two FFMA
+            const float2 T01 = make_float2(t01, t01), T10 = make_float2(t10, t10);
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                if (s & (1 << k))
+                    continue;
+                const int s1 = s | (1 << k);
+                const float2 v0 = a[s], v1 = a[s1];
+                a[s] = __ffma2_rn(T01, v1, v0);
+                a[s1] = __ffma2_rn(T10, v0, v1);
+            }
+        } else {
 #pragma unroll
         for (int s = 0; s < NS; s++) {
             if (s & (1 << k))
@@ -386,6 +400,7 @@ __device__ __forceinline__ void dense_factored(amp_t (&a)[NS], const DevDense &d
             a[s].y = fma(t01, v1.y, v0.y);
             a[s1].x = fma(t10, v0.x, v1.x);
             a[s1].y = fma(t10, v0.y, v1.y);
+        }
         }
     }
 #pragma unroll
