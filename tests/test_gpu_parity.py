@@ -521,6 +521,40 @@ def test_reference_param_gate_literals(ops, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_reference_measurement_known_answers(ops, dtype):
+    """The reference's known-answer measurement tests (Test_StateVectorKokkos_Expval.cpp:19-336,
+    Test_StateVectorKokkos_Var.cpp:19-122, extracted into tests/golden/ref_measure_kats.json): circuit from
+    |0..0>, one observable, one number -- through the direct calls and the observable classes."""
+    import json
+    import os
+    S = suffix(dtype)
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_measure_kats.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) >= 28
+    N = getattr(ops, f"NamedObsKokkos_{S}")
+    for c in cases:
+        n, o = c["n"], c["obs"]
+        sv = sv_class(ops, dtype)(n)
+        for g, w, inv, par in c["ops"]:
+            getattr(sv, g)(w, inv, par)
+        tol = (2e-6 if dtype == np.complex128 else 2e-5) * max(1.0, abs(c["expected"]))
+        where = (c["ref_file"], c["ref_line"])
+        if o["type"] == "named":
+            ob = N(o["name"], o["wires"])
+            if c["kind"] == "expval":
+                assert abs(sv.ExpectationValue(o["name"], o["wires"], [], np.zeros(0)) - c["expected"]) < tol, where
+        elif o["type"] == "hermitian":
+            mat = np.array([complex(a, b) for a, b in o["matrix"]])
+            ob = getattr(ops, f"HermitianObsKokkos_{S}")(mat, o["wires"])
+            if c["kind"] == "expval":
+                assert abs(sv.ExpectationValue(o["wires"], mat) - c["expected"]) < tol, where
+        else:
+            ob = getattr(ops, f"TensorProdObsKokkos_{S}")([N(f["name"], f["wires"]) for f in o["factors"]])
+        got = sv.expval(ob) if c["kind"] == "expval" else sv.var(ob)
+        assert abs(got - c["expected"]) < tol, where
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", [1, 2])
 def test_one_and_two_qubit_states(ops, ref, dtype, n):
     """States far below one tile (the reference's own tests mostly use 1-3 qubits): every gate that

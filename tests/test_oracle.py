@@ -222,3 +222,54 @@ def test_reference_param_gate_literals_pin_both_oracles():
             sv.h2d(ini)
             sv.apply(c["gate"], c["wires"], c["inverse"], c["params"])
             assert np.max(np.abs(sv.d2h() - want)) < 2e-6, (c["gate"], c["ref_line"])
+
+
+def _measure_kats():
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_measure_kats.json")
+    with open(path) as f:
+        return json.load(f)["cases"]
+
+
+def test_reference_measurement_known_answers_pin_both_oracles():
+    """The reference's own known-answer measurement tests (Test_StateVectorKokkos_Expval.cpp:19-336: named
+    observables by functor call and by NamedObs, 1- and 2-qubit matrices; Test_StateVectorKokkos_Var.cpp:19-122:
+    var of NamedObs / HermitianObs / TensorProdObs; extracted by tests/golden/make_ref_measure_kats.py)
+    pin the NumPy restatement and the compiled reference."""
+    cases = _measure_kats()
+    assert len(cases) >= 28
+    assert {c["kind"] for c in cases} == {"expval", "var"}
+    for c in cases:
+        n, o = c["n"], c["obs"]
+        ops = [(g, w, inv, par) for g, w, inv, par in c["ops"]]
+        psi = np.zeros(1 << n, dtype=complex)
+        psi[0] = 1
+        psi = npo.apply_ops(psi, n, ops)
+        if o["type"] == "named":
+            nob = ("named", o["name"], o["wires"])
+        elif o["type"] == "hermitian":
+            k = len(o["wires"])
+            mat = np.array([complex(a, b) for a, b in o["matrix"]]).reshape(1 << k, 1 << k)
+            nob = ("hermitian", mat, o["wires"])
+        else:
+            nob = ("tensor", [("named", f["name"], f["wires"]) for f in o["factors"]])
+        got = npo.expval(psi, n, nob) if c["kind"] == "expval" else npo.var(psi, n, nob)
+        tol = 2e-6 * max(1.0, abs(c["expected"]))  # Catch2 Approx / literals with 6-10 digits
+        assert abs(got - c["expected"]) < tol, (c["ref_file"], c["ref_line"])
+        if not ref.available():
+            continue
+        sv = ref.RefStateVector(n)
+        sv.apply_ops(ops)
+        if o["type"] == "named":
+            rob = ref.RefObs.named(o["name"], o["wires"])
+            direct = sv.expval_named(o["name"], o["wires"]) if c["kind"] == "expval" else None
+        elif o["type"] == "hermitian":
+            rob = ref.RefObs.hermitian(mat, o["wires"])
+            direct = sv.expval_matrix(mat, o["wires"]) if c["kind"] == "expval" else None
+        else:
+            rob = ref.RefObs.tensor([ref.RefObs.named(f["name"], f["wires"]) for f in o["factors"]])
+            direct = None
+        got_r = sv.expval_obs(rob) if c["kind"] == "expval" else sv.var_obs(rob)
+        assert abs(got_r - c["expected"]) < tol, (c["ref_file"], c["ref_line"])
+        if direct is not None:
+            assert abs(direct - c["expected"]) < tol, (c["ref_file"], c["ref_line"])
