@@ -521,6 +521,37 @@ def test_reference_param_gate_literals(ops, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_adjoint_reference_known_answers(ops, dtype):
+    """Every known-answer case of the reference's Test_AdjointDiffKokkos.cpp:34-455 (tests/adjoint_kats.py:
+    analytic -sin / cos values, parameter-shift and default.qubit literals, trainable subsets, tensor and
+    Hamiltonian observables, a non-basis initial state) through AdjointJacobianKokkos."""
+    import adjoint_kats
+    S = suffix(dtype)
+    N, T, H = (getattr(ops, f"{k}Kokkos_{S}") for k in ("NamedObs", "TensorProdObs", "Hamiltonian"))
+
+    def build(ob):
+        if ob[0] == "named":
+            return N(ob[1], ob[2])
+        if ob[0] == "tensor":
+            return T([build(o) for o in ob[1]])
+        return H(ob[1], [build(o) for o in ob[2]])
+
+    adj = getattr(ops, f"AdjointJacobianKokkos_{S}")()
+    for c in adjoint_kats.cases():
+        n = c["n"]
+        if c.get("init") is not None:
+            sv = sv_class(ops, dtype)(np.array(c["init"], dtype=dtype))
+        else:
+            sv = sv_class(ops, dtype)(n)
+        names, wires = [o[0] for o in c["ops"]], [o[1] for o in c["ops"]]
+        invs, params = [o[2] for o in c["ops"]], [o[3] for o in c["ops"]]
+        sv.apply(names, wires, invs, params)
+        ol = adj.create_ops_list(names, [np.array(x) for x in params], wires, invs, [np.zeros(0)] * len(names))
+        jac = adj.adjoint_jacobian(sv, [build(o) for o in c["obs"]], ol, c["tp"])
+        adjoint_kats.check(jac, c, extra_rel=0.0 if dtype == np.complex128 else 2e-5)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_reference_measurement_known_answers(ops, dtype):
     """The reference's known-answer measurement tests (Test_StateVectorKokkos_Expval.cpp:19-336,
     Test_StateVectorKokkos_Var.cpp:19-122, extracted into tests/golden/ref_measure_kats.json): circuit from

@@ -273,3 +273,34 @@ def test_reference_measurement_known_answers_pin_both_oracles():
         assert abs(got_r - c["expected"]) < tol, (c["ref_file"], c["ref_line"])
         if direct is not None:
             assert abs(direct - c["expected"]) < tol, (c["ref_file"], c["ref_line"])
+
+
+def _ref_obs(ob):
+    if ob[0] == "named":
+        return ref.RefObs.named(ob[1], ob[2])
+    if ob[0] == "tensor":
+        return ref.RefObs.tensor([_ref_obs(o) for o in ob[1]])
+    if ob[0] == "hamiltonian":
+        return ref.RefObs.hamiltonian(ob[1], [_ref_obs(o) for o in ob[2]])
+    raise KeyError(ob[0])
+
+
+def test_reference_adjoint_known_answers_pin_both_oracles():
+    """Every known-answer case of the reference's Test_AdjointDiffKokkos.cpp:34-455 (tests/adjoint_kats.py)
+    through the NumPy restatement and the compiled reference."""
+    import adjoint_kats
+    cases = adjoint_kats.cases()
+    assert len(cases) >= 20
+    for c in cases:
+        n = c["n"]
+        psi = np.zeros(1 << n, dtype=complex)
+        psi[0] = 1
+        if c.get("init") is not None:
+            psi = np.array(c["init"], dtype=complex)
+        fin = npo.apply_ops(psi, n, c["ops"])
+        adjoint_kats.check(npo.adjoint_jacobian(fin, n, c["obs"], c["ops"], c["tp"]), c)
+        if ref.available():
+            sv = ref.RefStateVector(n)
+            sv.h2d(psi)
+            sv.apply_ops(c["ops"])
+            adjoint_kats.check(sv.adjoint_jacobian([_ref_obs(o) for o in c["obs"]], c["ops"], c["tp"]), c)
