@@ -520,6 +520,76 @@ def test_reference_param_gate_literals(ops, dtype):
         assert np.max(np.abs(to_host(sv, n, dtype) - want)) < 2e-6, c["gate"]
 
 
+REF_INI_16 = [  # Test_StateVectorKokkos_Generator.cpp:26-43 (the 4-qubit input every generator test uses)
+    (0.267462841882, 0.010768564798), (0.228575129706, 0.010564590956), (0.099492749900, 0.260849823392),
+    (0.093690204310, 0.189847108173), (0.033390732374, 0.203836830144), (0.226979395737, 0.081852150975),
+    (0.031235505729, 0.176933497281), (0.294287602843, 0.145156781198), (0.152742706049, 0.111628061129),
+    (0.012553863703, 0.120027860480), (0.237156555364, 0.154658769755), (0.117001120872, 0.228059505033),
+    (0.041495873225, 0.065934827444), (0.089653239407, 0.221581340372), (0.217892322429, 0.291261296999),
+    (0.292993251871, 0.186570798697)]
+
+
+def test_generators_finite_difference_property(ops):
+    """The reference's generator tests (Test_StateVectorKokkos_Generator.cpp:17-1175): on its 4-qubit input,
+    scale * i * G|psi> equals the central difference (U(ep) - U(-ep))|psi> / (2 ep) of the matching gate,
+    ep = 1e-3, margin 1e-4 -- here for every generator, not only the ten the reference spells out."""
+    dtype = np.complex128
+    ini = np.array([complex(a, b) for a, b in REF_INI_16], dtype=dtype)
+    n, ep, margin = 4, 1e-3, 1e-4
+    rng = np.random.default_rng(12)
+    for name in GENERATORS:
+        nw = GATES[name][0] or 3
+        for wires in ([1, 0, 2, 3][:nw], [int(x) for x in rng.choice(n, size=nw, replace=False)]):
+            g = sv_class(ops, dtype)(ini)
+            scale = g.applyGenerator(name, wires, False, [])
+            up, um = sv_class(ops, dtype)(ini), sv_class(ops, dtype)(ini)
+            getattr(up, name)(wires, False, [ep])
+            getattr(um, name)(wires, False, [-ep])
+            gen, dp = to_host(g, n, dtype), (to_host(up, n, dtype) - to_host(um, n, dtype)) * (0.5 / ep)
+            assert np.max(np.abs(-scale * gen.imag - dp.real)) < margin, (name, wires)
+            assert np.max(np.abs(scale * gen.real - dp.imag)) < margin, (name, wires)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_multi_qubit_op_equals_named_gate(ops, dtype):
+    """Test_StateVectorKokkos_NonParam.cpp:932-1010: the Hadamard / CNOT / Toffoli matrices through the generic
+    matrix path give the named gate's result (Toffoli: on every basis state)."""
+    n = 4
+    h = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
+    cnot = np.eye(4, dtype=complex)[[0, 1, 3, 2]]
+    toff = np.eye(8, dtype=complex)[[0, 1, 2, 3, 4, 5, 7, 6]]
+    for name, mat, wires in (("Hadamard", h, [0]), ("CNOT", cnot, [0, 1]), ("Toffoli", toff, [0, 1, 2])):
+        for b in (range(1 << n) if name == "Toffoli" else [0]):
+            a, m = sv_class(ops, dtype)(n), sv_class(ops, dtype)(n)
+            a.setBasisState(b)
+            m.setBasisState(b)
+            getattr(a, name)(wires, False, [])
+            m.apply("QubitUnitary", wires, False, [], mat.ravel())
+            assert np.max(np.abs(to_host(a, n, dtype) - to_host(m, n, dtype))) < TOL[dtype], (name, b)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_set_state_vector_and_basis_state_literals(ops, dtype):
+    """Test_StateVectorKokkos_NonParam.cpp:1114-1200: setStateVector(indices, values) scatters values[i] to
+    indices[i] (here: swaps neighbours); setBasisState overwrites a populated state with one 1."""
+    init = np.array([0.267462849617 + 0.010768564418j, 0.228575125337 + 0.010564590804j,
+                     0.099492751062 + 0.260849833488j, 0.093690201640 + 0.189847111702j,
+                     0.015641822883 + 0.225092900621j, 0.205574608177 + 0.082808663337j,
+                     0.006827173322 + 0.211631480575j, 0.255280800811 + 0.161572331669j], dtype=dtype)
+    expected = init.copy()
+    expected[0::2], expected[1::2] = init[1::2], init[0::2]
+    sv = sv_class(ops, dtype)(3)
+    sv.HostToDevice(init)
+    sv.setStateVector([0, 2, 4, 6, 1, 3, 5, 7], np.array([init[1], init[3], init[5], init[7],
+                                                          init[0], init[2], init[4], init[6]]))
+    np.testing.assert_array_equal(to_host(sv, 3, dtype), expected)
+    sv.HostToDevice(init)
+    sv.setBasisState(3)
+    want = np.zeros(8, dtype=dtype)
+    want[3] = 1
+    np.testing.assert_array_equal(to_host(sv, 3, dtype), want)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_adjoint_reference_known_answers(ops, dtype):
     """Every known-answer case of the reference's Test_AdjointDiffKokkos.cpp:34-455 (tests/adjoint_kats.py:
