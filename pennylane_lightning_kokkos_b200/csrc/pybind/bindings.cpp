@@ -46,7 +46,7 @@ struct InitSettings {
     int num_threads = 0, device_id = 0;
     std::string map_device_id_by, tools_libs, tools_args;
     bool disable_warnings = false, print_configuration = false, tune_internals = false, tools_help = false;
-    unsigned has = 0;
+    unsigned has = 0x1ffu; // the reference's py::init calls every setter (Bindings.cpp:855-866)
 };
 
 template <int DT> struct ObsT { // ObservableKokkos<P> hierarchy (Bindings.cpp:591-736)

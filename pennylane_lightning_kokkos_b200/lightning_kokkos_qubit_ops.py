@@ -60,7 +60,9 @@ class InitializationSettings:
                "tools_help": False, "tools_args": ""}
 
     def __init__(self):
-        self._v = {}
+        # the reference's binding constructs the settings by calling every setter with its default
+        # (Bindings.cpp:855-866), so every has_*() is true from the start
+        self._v = dict(self._FIELDS)
 
     def __getattr__(self, item):
         for prefix in ("get_", "set_", "has_"):

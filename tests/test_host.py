@@ -59,7 +59,11 @@ def test_module_surface_matches_reference_binding(modname):
                "InitializationSettings"):
         assert hasattr(m, fn)
     s = m.InitializationSettings().set_device_id(1).set_num_threads(4)
-    assert s.get_device_id() == 1 and s.has_num_threads() and not s.has_tools_libs()
+    assert s.get_device_id() == 1 and s.get_num_threads() == 4 and s.has_num_threads()
+    # Bindings.cpp:855-866: the constructor calls every setter, so every has_*() is true
+    fresh = m.InitializationSettings()
+    assert fresh.has_tools_libs() and fresh.has_device_id() and fresh.get_tools_libs() == ""
+    assert fresh.get_disable_warnings() is False or fresh.get_disable_warnings() == 0
 
 
 @pytest.mark.skipif(HAS_GPU, reason="only meaningful on a box without a CUDA device")
