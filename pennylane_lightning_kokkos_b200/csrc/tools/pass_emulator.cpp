@@ -257,6 +257,9 @@ extern "C" {
 
 const char *b2emu_last_error() { return g_err.c_str(); }
 
+// the shared-memory swizzle of schedule.hpp, for the property tests
+uint32_t b2emu_phys_slot(uint32_t i, int B, int SW, int SH) { return phys_slot(i, B, SW, SH); }
+
 // names / wires / params as in b2sv_ops_create; state: 2^n interleaved (re, im) doubles, in place.
 // stats (6 values): passes, rounds, dense rounds, factored rounds, fused stores, plain-layout passes.
 // store_mode: 0 = always the store phase, 1 = fused stores where the schedule allows.

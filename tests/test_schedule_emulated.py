@@ -145,3 +145,31 @@ def test_plain_layout_passes_for_bulk_loads(monkeypatch):
     circ = random_circuit(n, 200, seed=23)
     got, st = emu.run(circ, n, psi0)
     assert np.max(np.abs(got - npo.apply_ops(psi0, n, circ))) < 1e-12
+
+
+def test_tile_swizzle_properties():
+    """phys_slot (schedule.hpp) = the tile kernel's phys<B,SW,SH>: a GF(2)-linear bijection of the tile; any 8
+    consecutive 16-byte units land in 8 distinct 16-byte bank groups of a 128-byte wavefront whatever higher bits
+    are set; complex64 (SH = 1) keeps the two amplitudes of a 16-byte unit together, which is what lets the load
+    warps copy 16 bytes at a time for both types."""
+    import ctypes as C
+    import emu
+    f = emu.lib().b2emu_phys_slot
+    f.restype = C.c_uint32
+    f.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_int]
+    for B, SW, SH in ((12, 3, 0), (13, 4, 1)):
+        n = 1 << B
+        slots = np.array([f(i, B, SW, SH) for i in range(n)], dtype=np.int64)
+        assert sorted(slots.tolist()) == list(range(n))                     # bijection
+        rng = np.random.default_rng(B)
+        for _ in range(200):                                                # linear over GF(2)
+            a, b = (int(x) for x in rng.integers(n, size=2))
+            assert slots[a ^ b] == slots[a] ^ slots[b]
+        unit = slots >> SH                                                  # 16-byte unit index of each slot
+        for base in rng.integers(n >> (SH + 3), size=64):                   # 8 consecutive units, any base
+            first = int(base) << (SH + 3)
+            groups = {int(unit[first + (u << SH)]) & 7 for u in range(8)}
+            assert len(groups) == 8
+        if SH:
+            even = np.arange(0, n, 2)
+            assert np.all(slots[even] % 2 == 0) and np.all(slots[even + 1] == slots[even] + 1)
